@@ -1,0 +1,136 @@
+"""The Python oracle (oracle/pyoracle.py) against vectors produced by the
+reference's own, unmodified window logic (oracle/gen_golden.py) and against the
+expected lists of the reference's tests (cases named ref_*)."""
+
+import json
+import os
+
+import pytest
+
+from oracle import pyoracle as po
+
+
+def _load(golden_dir, name):
+    with open(os.path.join(golden_dir, name)) as f:
+        return json.load(f)
+
+
+def _norm(rows):
+    out = []
+    for k, wid, tag, p in rows:
+        if isinstance(p, tuple):
+            p = list(p)
+        out.append([k, wid, tag, p])
+    return out
+
+
+def test_cases_match_reference_logic(golden_dir):
+    cases = _load(golden_dir, "window_fold_cases.json")
+    assert len(cases) >= 20
+    for name, case in cases.items():
+        s = case["spec"]
+        spec = po.FoldSpec(
+            reduction=s["reduction"], length_us=s["length_us"], offset_us=s["offset_us"],
+            align_us=s["align_us"], wait_us=s["wait_us"], ordered=s["ordered"],
+        )
+        acts = po.run_fold(spec, case["batches"])
+        assert len(acts) == len(case["acts"]), name
+        for i, (got, want) in enumerate(zip(acts, case["acts"])):
+            got = _norm(got)
+            if s["reduction"] in ("sum", "mean") and any(isinstance(v, float) for b in case["batches"] for v in b[2]):
+                # same left-to-right f64 additions -> still exact
+                pass
+            assert got == want, f"{name} activation {i}"
+
+
+def test_reference_test_expectations_present(golden_dir):
+    cases = _load(golden_dir, "window_fold_cases.json")
+    # expected lists copied from the reference's tests (file:line in `cite`)
+    want = {
+        "ref_count_window": [[1, 0, 2], [1, 1, 2], [2, 0, 1]],
+        "ref_reduce_window": [[1, 0, 3], [1, 1, 2]],
+        "ref_fold_window_tumbling": [[0, 0, 3], [0, 1, 1]],
+        "ref_fold_window_sliding": [[0, -1, 2], [0, 0, 3], [0, 1, 4], [0, 2, 4], [0, 3, 1]],
+        "ref_max_window": [[1, 0, 9], [1, 1, 7]],
+        "ref_min_window": [[1, 0, 3], [1, 1, 2]],
+    }
+    for name, down in want.items():
+        case = cases[name]
+        s = case["spec"]
+        spec = po.FoldSpec(s["reduction"], s["length_us"], s["offset_us"], s["align_us"], s["wait_us"], s["ordered"])
+        rows = [r for act in po.run_fold(spec, case["batches"]) for r in act]
+        assert [[k, w, p] for k, w, t, p in rows if t == "E"] == down, name
+        assert case["cite"].startswith("pytests/")
+
+
+def test_intersects_kats(golden_dir):
+    kats = _load(golden_dir, "windower_clock_kats.json")
+    for length, offset, align, t, ids in kats["intersects"]:
+        assert po.SlidingWindower(length, offset, align).intersects(t) == ids
+
+
+def test_intersects_reference_test_values():
+    # pytests/operators/windowing/test_sliding_windower.py:6-44, 392-510 (sample)
+    S = 1_000_000
+    w = po.SlidingWindower(10 * S, 5 * S, 0)
+    assert w.intersects(13 * S) == [1, 2]
+    assert w.intersects(-3 * S) == [-2, -1]
+    assert w.intersects(3 * S) == [-1, 0]
+    assert w.intersects(10 * S) == [1, 2]
+    t = po.SlidingWindower(10 * S, 10 * S, 0)
+    assert t.intersects(13 * S) == [1]
+    assert t.intersects(-3 * S) == [-1]
+    assert t.intersects(0) == [0]
+    assert t.intersects(10 * S) == [1]
+
+
+def test_clock_kats(golden_dir):
+    kats = _load(golden_dir, "windower_clock_kats.json")
+    for kat in kats["clock"]:
+        clock = po.EventClock(kat["wait_us"], kat["now_us"])
+        for step in kat["steps"]:
+            if step[0] == "adv":
+                clock.now_us += step[1]
+                clock.before_batch()
+            else:
+                _, wm = clock.on_item(step[1])
+                assert wm == step[2]
+
+
+def test_clock_reference_test_values():
+    # pytests/operators/windowing/test_event_clock.py:11-75
+    S = 1_000_000
+    c = po.EventClock(5 * S, 0)
+    assert c.on_notify() == po.UTC_MIN_US
+    c.before_batch()
+    assert c.on_item(7 * S)[1] == 2 * S
+    c.now_us += 2 * S
+    assert c.on_notify() == 4 * S
+    c2 = po.EventClock(5 * S, 0)
+    c2.before_batch()
+    c2.on_item(7 * S)
+    assert c2.on_item(10 * S)[1] == 5 * S
+    assert c2.on_item(8 * S)[1] == 5 * S  # does not reverse
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/pysrc"), reason="reference tree absent")
+def test_oracle_vs_live_reference_random():
+    """Extra seeds straight against the live reference (build container only)."""
+    import subprocess
+    import sys
+
+    code = (
+        "import sys, json; sys.path.insert(0, %r); sys.argv=['x'];"
+        "import oracle.gen_golden as g; from oracle import pyoracle as po;"
+        "S=10**6\n"
+        "for seed in range(30, 36):\n"
+        "    spec=g.spec_(['count','sum','min','max'][seed%%4], 10*S, [None,5*S,3*S][seed%%3], wait_us=(seed%%4)*S, ordered=bool(seed%%2) and (seed%%4)<2)\n"
+        "    b=g.gen_random(seed, 400, 7, 50*S, 4*S, [17, 60])\n"
+        "    want=g.run_reference(spec,b)\n"
+        "    got=po.run_fold(po.FoldSpec(spec['reduction'],spec['length_us'],spec['offset_us'],spec['align_us'],spec['wait_us'],spec['ordered']), b)\n"
+        "    got=[[[k,w,t,list(p) if isinstance(p,tuple) else p] for k,w,t,p in a] for a in got]\n"
+        "    assert got==want, seed\n"
+        "print('ok')\n"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
