@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""Benchmark of the north-star path: tumbling fold_window count-by-key (config C1).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): rows (u64 key, u64 val),
+key_i = splitmix64(0x5EED ^ i) mod 10^6, val_i = ts_i = i us after 2022-01-01,
+EventClock(wait=0), TumblingWindower(60 s), count fold.  One step = one
+activation (epoch batch) of 2^24 rows per GPU; the default 60 steps are the
+whole 10^9-row job.  Inputs (60 x 256 MiB per GPU) never fit the 126 MB L2.
+
+Printed JSON (one line, rank 0): `value` = events/s with inputs resident in
+HBM (CUDA events on the launching stream, max over ranks); `e2e` = the same
+job through the C ABI from pinned HOST buffers (H2D of every step and D2H of
+every emitted row inside the timed region); `roofline` for the fold kernel;
+`cpu_baseline` = the C restatement of the reference path (oracle/) on the
+host cores, bounded sample.
+
+`--impl reference` times that CPU restatement alone (the reference's Rust
+engine cannot be built here: no cargo, un-vendored timely -- DESIGN.md).
+"""
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALIGN_US = 1_640_995_200_000_000
+N_KEYS = 1_000_000
+WINDOW_US = 60_000_000
+BATCH_ROWS = 1 << 24
+BYTES_PER_EVENT = 16  # one read of the (u64, u64) record
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device=0):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.device)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        # under load == upper half of the samples
+        load = sm[len(sm) // 2:] if sm else []
+        med = load[len(load) // 2] if load else None
+        return {"sm_mhz": med, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_setup(n):
+    """torch.distributed is plumbing only: rendezvous, barrier, max-over-ranks."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    if world == 1:
+        return 0, 1, 0, None
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local, dist
+
+
+def barrier_max(dist, local, value):
+    if dist is None:
+        return value
+    import torch
+
+    t = torch.tensor([value], dtype=torch.float64, device=f"cuda:{local}")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier(dist, local):
+    if dist is not None:
+        import torch
+
+        dist.barrier(device_ids=[local])
+        torch.cuda.synchronize(local)
+
+
+def share_nccl_id(dist, rank, local):
+    from bytewax_b200 import gpu
+    import torch
+
+    buf = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{local}")
+    if rank == 0:
+        buf.copy_(torch.frombuffer(bytearray(gpu.Context.new_nccl_id()), dtype=torch.uint8))
+    dist.broadcast(buf, 0)
+    return bytes(buf.cpu().numpy().tobytes())
+
+
+def run_gpu(args):
+    from bytewax_b200 import _native as N, gpu
+
+    rank, world, local, dist = dist_setup(args.gpus)
+    nccl_id = share_nccl_id(dist, rank, local) if world > 1 else None
+    ctx = gpu.Context(local, rank, world, nccl_id)
+    K, W, B = args.steps, args.warmup, args.batch_rows
+
+    def make_fold(ring_slots=3, emit_order=N.ORDER_REFERENCE):
+        return gpu.WindowFold(
+            ctx, "count", WINDOW_US, None, ALIGN_US, 0, val_dtype="u64", ts_from_value=True,
+            emit_order=emit_order, capacity_hint=N_KEYS if world == 1 else (N_KEYS * 3) // (2 * world) + 1024,
+            max_batch_rows=B, max_emit_rows=max(1 << 20, (K + W + 2) * B // 40), max_late_rows=1 << 16,
+            ring_slots=ring_slots, exchange=N.XCHG_NCCL if args.exchange == "nccl" else N.XCHG_P2P)
+
+    # ---- device-resident inputs: step s of this rank = global rows [(s*world+rank)*B, +B) ----
+    nbuf = K + W
+    fold = make_fold()
+    dk = [ctx.dev_alloc(B * 8) for _ in range(nbuf)]
+    dv = [ctx.dev_alloc(B * 8) for _ in range(nbuf)]
+    for s in range(nbuf):
+        fold.gen_c1(dk[s], dv[s], (s * world + rank) * B, B, N_KEYS)
+    fold.sync()
+    # warm-up: W untimed steps on a scratch fold (same shapes), then a fresh fold for the job
+    for s in range(W):
+        fold.ingest_device(dk[K + s], dv[K + s], None, B)
+    fold.advance()
+    fold.close()
+    fold = make_fold()
+    st0 = fold.stats()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier(dist, local)
+    fold.time_begin()
+    for s in range(K):
+        fold.ingest_device(dk[s], dv[s], None, B)
+    ms = fold.time_end()
+    barrier(dist, local)
+    ms = barrier_max(dist, local, ms)
+    clocks = sampler.stop() if rank == 0 else None
+    st1 = fold.stats()
+    em = fold.advance()
+    em_eof = fold.eof()
+    total_counts = int(em.closed_acc.sum()) + int(em_eof.closed_acc.sum())
+    launches = int(st1.kernel_launches - st0.kernel_launches)
+    fold_ms_avg = st1.sum_fold_ms / max(1, st1.fold_launches)
+    rows_per_fold = st1.rows_received / max(1, st1.fold_launches) if world == 1 else B  # ~B per rank after the exchange
+    fold.close()
+    for p in dk + dv:
+        ctx.dev_free(p)
+    value = K * B * world / (ms / 1e3)
+
+    # ---- end to end: pinned host -> H2D -> kernels -> ordered rows D2H ----
+    e2e = None
+    if not args.no_e2e:
+        try:
+            e2e = run_e2e(ctx, make_fold, K if world == 1 else min(K, 16), B, rank, world, dist, local)
+        except Exception as ex:  # pinned allocation can fail on small hosts
+            e2e = {"value": None, "unit": "events/s", "error": str(ex)[:200]}
+
+    out = None
+    if rank == 0:
+        peak, peak_src = peaks()
+        achieved = BYTES_PER_EVENT * rows_per_fold / (fold_ms_avg / 1e3) / 1e9 if fold_ms_avg > 0 else None
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "fold_traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        out = {
+            "metric": "events/sec tumbling fold_window count-by-key",
+            "value": value, "unit": "events/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic",
+            "config": {
+                "workload": "C1: tumbling fold_window count-by-key, 2^24-row epochs of (u64 key, u64 val), "
+                            "1e6 distinct keys, 60 s windows, EventClock wait=0 (BASELINE.json configs[1])",
+                "rows_per_step_per_gpu": B, "total_rows": K * B * world, "n_keys": N_KEYS,
+                "l2": "inputs larger than L2 (each step reads a distinct 256 MiB batch; 16 GiB resident)",
+                "exchange": ("none" if world == 1 else args.exchange), "emit_order": "reference",
+                "sum_of_counts_check": total_counts,
+            },
+            "clocks": clocks,
+            "e2e": e2e,
+            "gpu_launches": launches,
+            "roofline": {
+                "bound": "hbm", "kernel": "k_fold", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                "peak_source": peak_src, "algorithmic_bytes_per_event": BYTES_PER_EVENT,
+                "avg_launch_ms": fold_ms_avg, "rows_per_launch": rows_per_fold,
+            },
+        }
+        if world == 1 and not args.no_cpu:
+            out["cpu_baseline"] = cpu_baseline(sample_rows=1 << 22, n_batches=6)
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out))
+
+
+def run_e2e(ctx, make_fold, K, B, rank, world, dist, local):
+    """Same job through the public C-ABI calls with HOST buffers."""
+    import numpy as np
+
+    fold = make_fold(ring_slots=K + 1)
+    # fill K pinned slots (untimed): generate on the device, copy back into the slot
+    dk, dv = ctx.dev_alloc(B * 8), ctx.dev_alloc(B * 8)
+    slots = []
+    for s in range(K):
+        b = fold.acquire(B)
+        fold.gen_c1(dk, dv, (s * world + rank) * B, B, 1_000_000)
+        fold.sync()
+        ctx.lib.bw_memcpy(ctx.h, C.cast(b.keys, C.c_void_p), C.c_void_p(dk), B * 8, 1)
+        ctx.lib.bw_memcpy(ctx.h, b.vals, C.c_void_p(dv), B * 8, 1)
+        slots.append(b)
+    ctx.dev_free(dk)
+    ctx.dev_free(dv)
+    barrier(dist, local)
+    t0 = time.perf_counter()
+    fold.time_begin()
+    for s in range(K):
+        fold.commit(slots[s], B)
+    em = fold.advance()  # waits, orders, copies every emitted row to the host
+    em2 = fold.eof()
+    dev_ms = fold.time_end()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    barrier(dist, local)
+    ms = barrier_max(dist, local, max(dev_ms, wall_ms))
+    out_rows = len(em.closed_key) + len(em2.closed_key)
+    assert int(em.closed_acc.sum()) + int(em2.closed_acc.sum()) > 0
+    fold.close()
+    return {
+        "value": K * B * world / (ms / 1e3), "unit": "events/s", "h2d_bytes_per_step": B * 16,
+        "d2h_bytes_per_step": out_rows * 40 // K, "ms_total": ms, "steps": K,
+        "path": "bw_ingest_commit (pinned slot -> async H2D) x steps, bw_advance + bw_eof (ordered rows D2H)",
+    }
+
+
+def cpu_baseline(sample_rows, n_batches, threads=None):
+    """The C restatement of the reference path (oracle/fold_oracle.c) on the host cores."""
+    from oracle import coracle
+
+    T = threads or min(os.cpu_count() or 1, 64)
+    l = coracle.lib()
+    orcs = [coracle.COracle("count", WINDOW_US, align_us=ALIGN_US) for _ in range(T)]
+    arr = (C.c_void_p * T)(*[o.h for o in orcs])
+    batches = [coracle.gen_c1(i * sample_rows, sample_rows, N_KEYS, ALIGN_US) for i in range(n_batches)]
+    t0 = time.perf_counter()
+    for keys, ts, _ in batches:
+        l.orc_on_batch_mt(arr, T, keys.ctypes.data_as(C.c_void_p), ts.ctypes.data_as(C.c_void_p), sample_rows)
+    dt = time.perf_counter() - t0
+    for o in orcs:
+        o.close()
+    return {
+        "value": sample_rows * n_batches / dt, "unit": "events/s", "cores": T, "kind": "port",
+        "sample": f"{n_batches} activations x {sample_rows} rows of C1 (first {sample_rows * n_batches} rows of the job), "
+                  f"{T} key-sharded worker threads, C restatement of the reference's Python logic + Rust engine order",
+        "seconds": dt,
+    }
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's CPU implementation of the path.
+
+    The Rust/Timely engine is unbuildable here, so this is the oracle port
+    (oracle/fold_oracle.c) with all host threads; each step is a bounded sample
+    (2^22 rows) of the same workload.  Under torchrun only rank 0 works."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import coracle
+
+    T = min(os.cpu_count() or 1, 64)
+    rows = 1 << 22
+    l = coracle.lib()
+    orcs = [coracle.COracle("count", WINDOW_US, align_us=ALIGN_US) for _ in range(T)]
+    arr = (C.c_void_p * T)(*[o.h for o in orcs])
+    K, W = args.steps, args.warmup
+    K = min(K, 24)  # keeps the whole run within minutes; each step is a bounded sample
+    times = []
+    for s in range(W + K):
+        keys, ts, _ = coracle.gen_c1(s * rows, rows, N_KEYS, ALIGN_US)
+        t0 = time.perf_counter()
+        l.orc_on_batch_mt(arr, T, keys.ctypes.data_as(C.c_void_p), ts.ctypes.data_as(C.c_void_p), rows)
+        if s >= W:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    value = rows * K / total
+    sample = f"{K} steps x {rows} rows of C1, {T} key-sharded worker threads (oracle/fold_oracle.c)"
+    print(json.dumps({
+        "impl": "reference", "metric": "events/sec tumbling fold_window count-by-key", "value": value,
+        "unit": "events/s", "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": total / K * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "C1: tumbling fold_window count-by-key (bounded sample per step)", "rows_per_step": rows,
+                   "n_keys": N_KEYS},
+        "cpu_baseline": {"value": value, "unit": "events/s", "cores": T, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--batch-rows", type=int, default=BATCH_ROWS)
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

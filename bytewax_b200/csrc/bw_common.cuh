@@ -1,0 +1,241 @@
+// bw_common.cuh -- shared types, hashing and PTX helpers for libbwgpu (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+typedef uint64_t u64;
+typedef int64_t i64;
+typedef uint32_t u32;
+typedef int32_t i32;
+
+#define BW_MAX_WORLD 8
+#define BW_SM_COUNT_FALLBACK 148
+
+// ---------------------------------------------------------------------------
+// Hash / routing.  The reference routes with an un-pinned SipHash
+// (src/timely.rs:455-465); any deterministic hash conforms.
+// ---------------------------------------------------------------------------
+__host__ __device__ __forceinline__ u64 bw_mix64(u64 z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ u64 bw_splitmix64(u64 x) {
+  return bw_mix64(x + 0x9E3779B97F4A7C15ULL);
+}
+// owning rank: high 32 bits scaled into [0, world)
+__host__ __device__ __forceinline__ u32 bw_route_hash(u64 h, u32 world) {
+  return (u32)(((h >> 32) * (u64)world) >> 32);
+}
+
+// ---------------------------------------------------------------------------
+// State layout in HBM (DESIGN.md "Data layout").
+//
+// One 32-byte HOT slot per key == exactly one L2 sector: everything the
+// steady-state fold touches.  One 32-byte COLD slot per key for what only
+// pane creation / close needs.  Extra live panes of a key hang off the cold
+// slot as a short linked list of 32-byte nodes.
+// ---------------------------------------------------------------------------
+struct __align__(32) HotSlot {
+  u64 key;      // BW_EMPTY_KEY when free
+  i64 max_ts;   // max event ts seen since the key was (re)created; INT64_MIN when none
+  i64 widtag;   // inline pane: (pane_id << 16) | older_delta << 8 | dirty << 7 | born & 63
+  u64 acc;      // inline pane accumulator (bits)
+};
+struct __align__(32) ColdSlot {
+  u64 open_seq;    // arrival sequence (batch << 32 | index) that opened the inline pane
+  u64 acc2;        // inline pane value count (MEAN divisor / row count)
+  u32 spill_head;  // first extra pane node, 0 == none
+  u32 lock;        // structural lock for the node list
+  i64 closed_upto; // sliding windows: window ids <= this were already emitted for this key incarnation
+};
+struct __align__(32) PaneNode {
+  i64 wid;
+  u64 acc;
+  u64 open_seq;
+  u32 next;
+  u32 born;  // batch number (low 32 bits) that created the node
+};
+
+#define BW_UTC_MIN_US_DEV (-62135596800000000LL)
+#define BW_EMPTY_KEY 0xFFFFFFFFFFFFFFFFULL
+#define BW_EMPTY_WIDTAG INT64_MIN
+#define BW_WID_SHIFT 16
+#define BW_WID_LIMIT (1LL << 46)  // |pane id| must stay below this
+#define BW_TAG_DIRTY 0x80LL
+#define BW_TAG_BORN_MASK 0x7FLL  // bits 5:0 = creating batch & 63, bit 6 = "not fresh" (set by K4)
+#define BW_TAG_STALE 0x40u
+#define BW_TAG_DELTA_SHIFT 8
+
+__host__ __device__ __forceinline__ i64 bw_pack_widtag(i64 q, u32 delta, u32 born) {
+  return (i64)((u64)q << BW_WID_SHIFT) | ((i64)(delta > 255u ? 255u : delta) << BW_TAG_DELTA_SHIFT) |
+         (i64)(born & 0x7Fu);
+}
+__host__ __device__ __forceinline__ i64 bw_widtag_q(i64 tag) { return tag >> BW_WID_SHIFT; }
+__host__ __device__ __forceinline__ u32 bw_widtag_delta(i64 tag) { return (u32)((tag >> BW_TAG_DELTA_SHIFT) & 0xFF); }
+
+// accumulator op codes (uniform per fold)
+enum BwOp : int {
+  BW_OP_ADD_ONE = 0,  // count
+  BW_OP_ADD_U64 = 1,  // integer sum (wraps mod 2^64, same bits signed/unsigned)
+  BW_OP_ADD_F64 = 2,  // float sum in binary64
+  BW_OP_MIN_S64 = 3,
+  BW_OP_MIN_U64 = 4,  // also floats through the order-preserving encoding
+  BW_OP_MAX_S64 = 5,
+  BW_OP_MAX_U64 = 6,
+};
+
+// order-preserving f64 -> u64 (for min/max by integer atomics)
+__host__ __device__ __forceinline__ u64 bw_f64_to_ordered(u64 b) {
+  return (b & 0x8000000000000000ULL) ? ~b : (b | 0x8000000000000000ULL);
+}
+__host__ __device__ __forceinline__ u64 bw_ordered_to_f64(u64 o) {
+  return (o & 0x8000000000000000ULL) ? (o & 0x7FFFFFFFFFFFFFFFULL) : ~o;
+}
+
+struct FoldParams {
+  i64 length_us, offset_us, align_us, wait_us;
+  // pane geometry: pane = [align + q*pane_us, align + (q+1)*pane_us);
+  // a window w covers panes [w*panes_per_offset, w*panes_per_offset + panes_per_window)
+  i64 pane_us;
+  i64 panes_per_offset;  // a
+  i64 panes_per_window;  // b
+  double inv_pane;       // 1.0 / pane_us
+  int op;                // BwOp of acc
+  int reduction;         // bw_reduction
+  int val_dtype;
+  int ts_from_value;
+  int track_wm;          // 0 when wait == forever (nothing is ever late or closed before EOF)
+  int ordered;
+  int need_count;        // maintain acc2 (MEAN)
+  u64 acc_identity;
+};
+
+struct Table {
+  HotSlot* hot;
+  ColdSlot* cold;
+  PaneNode* nodes;
+  u64* node_acc2;
+  u32* free_stack;
+  u32* dirty;      // list of slot indices with possibly closable panes
+  u64 mask;        // capacity - 1 (capacity is a power of two); slot `capacity` is the BW_EMPTY_KEY alias slot
+  u32 pool_cap;
+  // device counters
+  struct Counters* ctr;
+};
+
+struct Counters {
+  int free_top;          // free_stack fill
+  u32 pool_next;         // bump allocator (node 0 is the null node)
+  u32 dirty_count;
+  u32 err;               // sticky bw_status raised by a kernel
+  unsigned long long live_keys;
+  unsigned long long n_closed;   // rows in the closed emit buffer
+  unsigned long long n_late;     // rows in the late emit buffer
+  unsigned long long gmax_ts;    // i64 bits: max event ts over everything ingested (prepass chain)
+  u32 batch_clean;       // verdict of the prepass for the batch in flight
+  u32 pad;
+};
+
+__device__ __forceinline__ void bw_raise(Counters* c, u32 status) { atomicCAS(&c->err, 0u, status); }
+
+// up to BW_MAX_WORLD column segments forming one activation in arrival order
+struct BatchView {
+  const u64* keys[BW_MAX_WORLD];
+  const void* vals[BW_MAX_WORLD];
+  const i64* ts[BW_MAX_WORLD];
+  const u64* d_counts;          // device: rows per segment (after an exchange)
+  u64 h_counts[BW_MAX_WORLD];   // rows per segment when known on the host
+  u64 max_rows;                 // host-known bound on the total
+  int nseg;
+  int counts_on_device;
+};
+__device__ __forceinline__ u64 bw_seg_count(const BatchView& bv, int j) {
+  return bv.counts_on_device ? bv.d_counts[j] : bv.h_counts[j];
+}
+
+struct EmitBufs {
+  u64 *c_key, *c_acc, *c_count, *c_seq, *c_epoch;
+  i64* c_wid;
+  u64 *l_key, *l_val, *l_seq, *l_epoch;
+  i64 *l_wid, *l_ts;
+  u64 max_closed, max_late;
+};
+
+// ---------------------------------------------------------------------------
+// PTX helpers
+// ---------------------------------------------------------------------------
+// One 32-byte sector in one instruction (LDG.E.256), L2-coherent.
+__device__ __forceinline__ void bw_ld_slot(const HotSlot* p, u64& key, i64& max_ts, i64& widtag, u64& acc) {
+  asm volatile("ld.global.relaxed.gpu.v4.u64 {%0,%1,%2,%3}, [%4];"
+               : "=l"(key), "=l"(max_ts), "=l"(widtag), "=l"(acc)
+               : "l"(p)
+               : "memory");
+}
+// streaming 8-byte load that does not pollute L1
+__device__ __forceinline__ u64 bw_ld_stream_u64(const u64* p) {
+  u64 v;
+  asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ u32 bw_ld_stream_u32(const u32* p) {
+  u32 v;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void bw_red_add_u64(u64* p, u64 v) {
+  asm volatile("red.global.relaxed.gpu.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void bw_red_add_f64(u64* p, double v) {
+  asm volatile("red.global.relaxed.gpu.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ void bw_red_max_s64(i64* p, i64 v) {
+  asm volatile("red.global.relaxed.gpu.max.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void bw_red_min_s64(i64* p, i64 v) {
+  asm volatile("red.global.relaxed.gpu.min.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void bw_red_max_u64(u64* p, u64 v) {
+  asm volatile("red.global.relaxed.gpu.max.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void bw_red_min_u64(u64* p, u64 v) {
+  asm volatile("red.global.relaxed.gpu.min.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ void bw_apply(int op, u64* acc, u64 operand) {
+  switch (op) {
+    case BW_OP_ADD_ONE: bw_red_add_u64(acc, 1ULL); break;
+    case BW_OP_ADD_U64: bw_red_add_u64(acc, operand); break;
+    case BW_OP_ADD_F64: bw_red_add_f64(acc, __longlong_as_double((i64)operand)); break;
+    case BW_OP_MIN_S64: bw_red_min_s64((i64*)acc, (i64)operand); break;
+    case BW_OP_MIN_U64: bw_red_min_u64(acc, operand); break;
+    case BW_OP_MAX_S64: bw_red_max_s64((i64*)acc, (i64)operand); break;
+    default: bw_red_max_u64(acc, operand); break;
+  }
+}
+
+// floor((ts - align) / pane) for any sign; exact (double estimate + integer fix-up).
+__device__ __forceinline__ i64 bw_pane_of(i64 ts, const FoldParams& p) {
+  i64 d = ts - p.align_us;
+  i64 q = (i64)floor((double)d * p.inv_pane);
+  i64 r = d - q * p.pane_us;
+  while (r < 0) { r += p.pane_us; --q; }
+  while (r >= p.pane_us) { r -= p.pane_us; ++q; }
+  return q;
+}
+// host/device exact floor division
+__host__ __device__ __forceinline__ i64 bw_floordiv(i64 a, i64 b) {
+  i64 q = a / b, r = a % b;
+  return (r != 0 && ((r < 0) != (b < 0))) ? q - 1 : q;
+}
+// Time at which pane q can be dropped == close time of the last window covering it:
+// last window = floor(q / a); close = align + w*offset + length.
+__device__ __forceinline__ i64 bw_pane_release(i64 q, const FoldParams& p) {
+  i64 w = (p.panes_per_offset == 1) ? q : bw_floordiv(q, p.panes_per_offset);
+  return p.align_us + w * p.offset_us + p.length_us;
+}
+// saturating ts - wait (the reference's OverflowError branch, windowing.py:281-285)
+__host__ __device__ __forceinline__ i64 bw_sub_sat(i64 ts, i64 wait) {
+  if (ts < INT64_MIN + wait) return INT64_MIN;
+  return ts - wait;
+}

@@ -1,0 +1,1136 @@
+// bwgpu.cu -- libbwgpu.so: C ABI (include/bwgpu.h) over the sm_100a kernels.
+//
+// Host side of the epoch pump for ONE stateful step: what src/worker.rs:68-83
+// (`Worker::run`) + src/operators.rs:667-1024 (one activation of
+// `stateful_batch`) do per epoch, restated as stream-ordered kernel launches:
+//
+//   commit(epoch):  [H2D] -> (world>1: K1 partition + K2 exchange) -> prepass
+//                   -> K3 fold (or the exact slow path) -> K4 close
+//   advance():      wait, order rows like the reference, D2H
+//   eof():          K4 over every key with watermark = UTC_MAX
+//
+// No torch, no Python: CUDA runtime + NCCL only.
+#include <cub/cub.cuh>
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/bwgpu.h"
+#include "bw_close.cuh"
+#include "bw_common.cuh"
+#include "bw_exchange.cuh"
+#include "bw_fold.cuh"
+#include "bw_prepass.cuh"
+#include "bw_slow.cuh"
+
+static thread_local std::string g_last_error;
+
+struct bw_ctx {
+  int device = 0, rank = 0, world = 1, sm_count = BW_SM_COUNT_FALLBACK;
+  ncclComm_t comm = nullptr;
+  std::string err;
+  void* flush_buf = nullptr;
+  size_t flush_bytes = 0;
+};
+
+#define CTX_FAIL(ctx, code, ...)                         \
+  do {                                                   \
+    char _b[512];                                        \
+    snprintf(_b, sizeof _b, __VA_ARGS__);                \
+    if (ctx) (ctx)->err = _b; else g_last_error = _b;    \
+    return (code);                                       \
+  } while (0)
+
+#define CU(ctx, call)                                                                              \
+  do {                                                                                             \
+    cudaError_t _e = (call);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      CTX_FAIL(ctx, BW_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, \
+               __LINE__);                                                                          \
+  } while (0)
+
+#define NC(ctx, call)                                                                               \
+  do {                                                                                              \
+    ncclResult_t _e = (call);                                                                       \
+    if (_e != ncclSuccess)                                                                          \
+      CTX_FAIL(ctx, BW_ERR_NCCL, "%s failed: %s (%s:%d)", #call, ncclGetErrorString(_e), __FILE__,  \
+               __LINE__);                                                                           \
+  } while (0)
+
+struct Slot {
+  u64* h_keys = nullptr;
+  void* h_vals = nullptr;
+  i64* h_ts = nullptr;
+  bool acquired = false;
+};
+struct Stage {  // device staging for host-ingested batches
+  u64* d_keys = nullptr;
+  void* d_vals = nullptr;
+  i64* d_ts = nullptr;
+  cudaEvent_t consumed = nullptr;  // recorded after the kernels that read it
+  bool used = false;
+};
+
+struct EventPair {
+  cudaEvent_t a, b;
+  u64 rows;
+};
+
+struct bw_fold {
+  bw_ctx* ctx = nullptr;
+  bw_fold_spec spec{};
+  FoldParams p{};
+  Table t{};
+  EmitBufs e{};
+  Counters* d_ctr = nullptr;
+  Counters* h_ctr = nullptr;  // pinned mirror
+  cudaStream_t s_compute = nullptr, s_copy = nullptr, s_pre = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_pre = nullptr, ev_h2d = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+  int val_bytes = 8;
+  bool has_vals = true, has_ts = false;
+  // ingest
+  std::vector<Slot> slots;
+  std::vector<Stage> stages;
+  u32 stage_next = 0;
+  // prepass
+  i64 *d_rmin = nullptr, *d_rmax = nullptr;
+  u32* d_rbad = nullptr;
+  u32* h_verdict = nullptr;  // pinned
+  u32* d_verdict = nullptr;
+  u64 max_recv_rows = 0;
+  // slow path temp (lazy)
+  u64 slow_cap = 0;
+  u64 *d_kflat = nullptr, *d_ksorted = nullptr;
+  i64 *d_tsflat = nullptr, *d_tssorted = nullptr, *d_prefmax = nullptr;
+  u32 *d_idx = nullptr, *d_idxsorted = nullptr;
+  unsigned char* d_late = nullptr;
+  void* d_cub = nullptr;
+  size_t cub_bytes = 0;
+  // emit sort temp (lazy)
+  u64 sort_cap = 0;
+  u64 *d_sk = nullptr, *d_sk2 = nullptr, *d_gather = nullptr;
+  u32 *d_perm = nullptr, *d_perm2 = nullptr;
+  // host output (pinned, grown on demand)
+  u64 hout_cap_c = 0, hout_cap_l = 0;
+  u64 *ho_ckey = nullptr, *ho_cacc = nullptr, *ho_ccount = nullptr, *ho_cepoch = nullptr;
+  i64* ho_cwid = nullptr;
+  u64 *ho_lkey = nullptr, *ho_lval = nullptr, *ho_lepoch = nullptr;
+  i64 *ho_lwid = nullptr, *ho_lts = nullptr;
+  // bookkeeping
+  u32 batch_no = 0;
+  std::vector<u64> ordinal_epoch;  // batch ordinal -> user epoch (since last advance)
+  u64 ordinal_base = 0;
+  bool eof_done = false;
+  int fold_grid = 0, close_grid = 0;
+  // multi-GPU exchange
+  void* xchg_base = nullptr;  // one allocation, IPC-shared
+  size_t xchg_bytes = 0;
+  void* peer_base[BW_MAX_WORLD] = {nullptr};
+  u64 region_cap = 0;
+  u32* d_tile_counts = nullptr;
+  u64* d_send_counts = nullptr;   // NCCL mode
+  u64* d_all_counts = nullptr;    // NCCL mode [world][world]
+  u64* h_all_counts = nullptr;    // pinned
+  u64 *send_keys = nullptr;       // NCCL mode local send regions
+  void* send_vals = nullptr;
+  i64* send_ts = nullptr;
+  int xbuf = 0;
+  // stats
+  bw_stats st{};
+  std::vector<EventPair> timers;
+  size_t timers_used = 0;
+};
+
+#define FAIL(f, code, ...) CTX_FAIL((f)->ctx, code, __VA_ARGS__)
+
+// ---------------------------------------------------------------------------
+// small kernels
+// ---------------------------------------------------------------------------
+__global__ void k_init_table(Table t, u64 acc_identity) {
+  const u64 n = t.mask + 2;
+  for (u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += (u64)gridDim.x * blockDim.x) {
+    HotSlot h;
+    h.key = BW_EMPTY_KEY;
+    h.max_ts = INT64_MIN;
+    h.widtag = BW_EMPTY_WIDTAG;
+    h.acc = acc_identity;
+    t.hot[s] = h;
+    ColdSlot c;
+    c.open_seq = ~0ULL;
+    c.acc2 = 0;
+    c.spill_head = 0;
+    c.lock = 0;
+    c.closed_upto = INT64_MIN;
+    t.cold[s] = c;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    Counters z;
+    memset(&z, 0, sizeof z);
+    z.pool_next = 1;  // node 0 is the null node
+    z.gmax_ts = (unsigned long long)INT64_MIN;
+    *t.ctr = z;
+  }
+}
+
+__global__ void k_gen_c1(u64* keys, u64* vals, u64 start, u64 rows, u64 n_keys) {
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (u64)gridDim.x * blockDim.x) {
+    u64 g = start + i;
+    keys[i] = bw_splitmix64(0x5EEDULL ^ g) % n_keys;
+    vals[i] = g;
+  }
+}
+
+__global__ void k_fill(unsigned char* p, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n / 16; i += (size_t)gridDim.x * blockDim.x)
+    ((uint4*)p)[i] = make_uint4(0xA5A5A5A5u, 0xA5A5A5A5u, 0xA5A5A5A5u, 0xA5A5A5A5u);
+}
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+// (C linkage comes from the declarations in include/bwgpu.h)
+
+uint32_t bw_abi_version(void) { return BW_ABI_VERSION; }
+const char* bw_last_global_error(void) { return g_last_error.c_str(); }
+const char* bw_last_error(const bw_ctx* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+
+uint32_t bw_route(uint64_t key, uint32_t world) { return bw_route_hash(bw_mix64(key), world); }
+
+bw_status bw_nccl_unique_id(void* out128) {
+  ncclUniqueId id;
+  ncclResult_t r = ncclGetUniqueId(&id);
+  if (r != ncclSuccess) {
+    g_last_error = std::string("ncclGetUniqueId failed: ") + ncclGetErrorString(r);
+    return BW_ERR_NCCL;
+  }
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  memcpy(out128, &id, 128);
+  return BW_OK;
+}
+
+bw_status bw_ctx_create(int device, int rank, int world, const void* nccl_unique_id, bw_ctx** out) {
+  bw_ctx* null_ctx = nullptr;
+  if (!out) CTX_FAIL(null_ctx, BW_ERR_SPEC, "bw_ctx_create: out is NULL");
+  if (world < 1 || world > BW_MAX_WORLD || rank < 0 || rank >= world)
+    CTX_FAIL(null_ctx, BW_ERR_SPEC, "bw_ctx_create: bad rank/world %d/%d (max world %d)", rank, world, BW_MAX_WORLD);
+  if (world > 1 && !nccl_unique_id) CTX_FAIL(null_ctx, BW_ERR_SPEC, "bw_ctx_create: world > 1 needs an NCCL id");
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev <= 0)
+    CTX_FAIL(null_ctx, BW_ERR_CUDA, "no CUDA device: %s", cudaGetErrorString(ce));
+  if (device < 0 || device >= ndev) CTX_FAIL(null_ctx, BW_ERR_SPEC, "device %d out of range (%d devices)", device, ndev);
+  CU(null_ctx, cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(null_ctx, cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    CTX_FAIL(null_ctx, BW_ERR_CUDA, "libbwgpu is built for sm_100a only; device %d is sm_%d%d", device, prop.major,
+             prop.minor);
+  bw_ctx* c = new bw_ctx();
+  c->device = device;
+  c->rank = rank;
+  c->world = world;
+  c->sm_count = prop.multiProcessorCount;
+  if (world > 1) {
+    ncclUniqueId id;
+    memcpy(&id, nccl_unique_id, 128);
+    ncclResult_t r = ncclCommInitRank(&c->comm, world, id, rank);
+    if (r != ncclSuccess) {
+      g_last_error = std::string("ncclCommInitRank failed: ") + ncclGetErrorString(r);
+      delete c;
+      return BW_ERR_NCCL;
+    }
+  }
+  *out = c;
+  return BW_OK;
+}
+
+void bw_ctx_destroy(bw_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->comm) ncclCommDestroy(ctx->comm);
+  if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+  delete ctx;
+}
+
+bw_status bw_dev_alloc(bw_ctx* ctx, uint64_t bytes, void** out) {
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaMalloc(out, bytes ? bytes : 16));
+  return BW_OK;
+}
+bw_status bw_dev_free(bw_ctx* ctx, void* ptr) {
+  CU(ctx, cudaFree(ptr));
+  return BW_OK;
+}
+bw_status bw_host_alloc(bw_ctx* ctx, uint64_t bytes, void** out) {
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaHostAlloc(out, bytes ? bytes : 16, cudaHostAllocDefault));
+  return BW_OK;
+}
+bw_status bw_host_free(bw_ctx* ctx, void* ptr) {
+  CU(ctx, cudaFreeHost(ptr));
+  return BW_OK;
+}
+bw_status bw_memcpy(bw_ctx* ctx, void* dst, const void* src, uint64_t bytes, int kind) {
+  cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  CU(ctx, cudaMemcpy(dst, src, bytes, k));
+  return BW_OK;
+}
+bw_status bw_flush_l2(bw_ctx* ctx) {
+  CU(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->flush_buf) {
+    ctx->flush_bytes = (size_t)256 << 20;  // 256 MiB > 126 MB L2
+    CU(ctx, cudaMalloc(&ctx->flush_buf, ctx->flush_bytes));
+  }
+  k_fill<<<ctx->sm_count * 8, 256>>>((unsigned char*)ctx->flush_buf, ctx->flush_bytes);
+  CU(ctx, cudaGetLastError());
+  CU(ctx, cudaDeviceSynchronize());
+  return BW_OK;
+}
+
+// ---------------------------------------------------------------------------
+// fold create / destroy
+// ---------------------------------------------------------------------------
+static i64 gcd_i64(i64 a, i64 b) {
+  while (b) {
+    i64 t = a % b;
+    a = b;
+    b = t;
+  }
+  return a;
+}
+
+template <typename T>
+static cudaError_t dmalloc(T** p, size_t n) {
+  return cudaMalloc((void**)p, (n ? n : 1) * sizeof(T));
+}
+
+static bw_status fold_alloc(bw_fold* f) {
+  bw_ctx* ctx = f->ctx;
+  const bw_fold_spec& s = f->spec;
+  // table: power of two >= 2 * hint, at least 1024
+  u64 cap = 1024;
+  while (cap < 2 * std::max<u64>(s.capacity_hint, 1)) cap <<= 1;
+  if (cap > (1ULL << 31)) FAIL(f, BW_ERR_SPEC, "capacity_hint too large");
+  f->t.mask = cap - 1;
+  f->t.pool_cap = (u32)std::min<u64>(2 * cap + 1024, 0xFFFFFFF0ULL);
+  CU(ctx, dmalloc(&f->t.hot, cap + 1));
+  CU(ctx, dmalloc(&f->t.cold, cap + 1));
+  CU(ctx, dmalloc(&f->t.nodes, f->t.pool_cap));
+  CU(ctx, dmalloc(&f->t.node_acc2, f->t.pool_cap));
+  CU(ctx, dmalloc(&f->t.free_stack, f->t.pool_cap));
+  CU(ctx, dmalloc(&f->t.dirty, cap + 2));
+  CU(ctx, dmalloc(&f->d_ctr, 1));
+  f->t.ctr = f->d_ctr;
+  CU(ctx, cudaHostAlloc((void**)&f->h_ctr, sizeof(Counters), cudaHostAllocDefault));
+  // emit buffers
+  f->e.max_closed = s.max_emit_rows;
+  f->e.max_late = s.max_late_rows;
+  CU(ctx, dmalloc(&f->e.c_key, s.max_emit_rows));
+  CU(ctx, dmalloc(&f->e.c_wid, s.max_emit_rows));
+  CU(ctx, dmalloc(&f->e.c_acc, s.max_emit_rows));
+  CU(ctx, dmalloc(&f->e.c_count, s.max_emit_rows));
+  CU(ctx, dmalloc(&f->e.c_seq, s.max_emit_rows));
+  CU(ctx, dmalloc(&f->e.c_epoch, s.max_emit_rows));
+  CU(ctx, dmalloc(&f->e.l_key, s.max_late_rows));
+  CU(ctx, dmalloc(&f->e.l_wid, s.max_late_rows));
+  CU(ctx, dmalloc(&f->e.l_val, s.max_late_rows));
+  CU(ctx, dmalloc(&f->e.l_ts, s.max_late_rows));
+  CU(ctx, dmalloc(&f->e.l_seq, s.max_late_rows));
+  CU(ctx, dmalloc(&f->e.l_epoch, s.max_late_rows));
+  // prepass
+  f->max_recv_rows = s.max_batch_rows * (u64)ctx->world;
+  u64 nranges = (f->max_recv_rows + BW_RANGE_ROWS - 1) / BW_RANGE_ROWS + 1;
+  CU(ctx, dmalloc(&f->d_rmin, nranges));
+  CU(ctx, dmalloc(&f->d_rmax, nranges));
+  CU(ctx, dmalloc(&f->d_rbad, nranges));
+  CU(ctx, dmalloc(&f->d_verdict, 1));
+  CU(ctx, cudaHostAlloc((void**)&f->h_verdict, 64, cudaHostAllocDefault));
+  CU(ctx, cudaStreamCreateWithFlags(&f->s_compute, cudaStreamNonBlocking));
+  CU(ctx, cudaStreamCreateWithFlags(&f->s_copy, cudaStreamNonBlocking));
+  CU(ctx, cudaStreamCreateWithFlags(&f->s_pre, cudaStreamNonBlocking));
+  CU(ctx, cudaEventCreateWithFlags(&f->ev_in, cudaEventDisableTiming));
+  CU(ctx, cudaEventCreateWithFlags(&f->ev_pre, cudaEventDisableTiming));
+  CU(ctx, cudaEventCreateWithFlags(&f->ev_h2d, cudaEventDisableTiming));
+  int occ = 0;
+  CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fold, BW_FOLD_THREADS, 0));
+  if (occ < 1) occ = 1;
+  f->fold_grid = ctx->sm_count * occ;
+  f->close_grid = ctx->sm_count * 8;
+  k_init_table<<<ctx->sm_count * 8, 256, 0, f->s_compute>>>(f->t, f->p.acc_identity);
+  CU(ctx, cudaGetLastError());
+  f->st.kernel_launches++;
+  f->st.table_capacity = cap;
+  return BW_OK;
+}
+
+// one IPC-shared allocation per rank holding both receive buffers + count tables
+struct XLayout {
+  size_t counts_off[2], keys_off[2], vals_off[2], ts_off[2], total;
+};
+static XLayout xlayout(const bw_fold* f) {
+  XLayout L;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return o;
+  };
+  const size_t rows = (size_t)f->region_cap * f->ctx->world;
+  for (int b = 0; b < 2; ++b) {
+    L.counts_off[b] = take(sizeof(u64) * BW_MAX_WORLD);
+    L.keys_off[b] = take(rows * 8);
+    L.vals_off[b] = f->has_vals ? take(rows * (size_t)f->val_bytes) : 0;
+    L.ts_off[b] = f->has_ts ? take(rows * 8) : 0;
+  }
+  L.total = off;
+  return L;
+}
+
+static bw_status xchg_setup(bw_fold* f) {
+  bw_ctx* ctx = f->ctx;
+  const int W = ctx->world;
+  f->region_cap = f->spec.max_batch_rows;  // worst case: every row of a source goes to one rank
+  XLayout L = xlayout(f);
+  f->xchg_bytes = L.total;
+  CU(ctx, cudaMalloc(&f->xchg_base, L.total));
+  CU(ctx, cudaMemset(f->xchg_base, 0, L.total));
+  u64 ntiles = (f->spec.max_batch_rows + BW_PART_TILE - 1) / BW_PART_TILE + 1;
+  CU(ctx, dmalloc(&f->d_tile_counts, ntiles * BW_MAX_WORLD));
+  if (f->spec.exchange == BW_XCHG_P2P) {
+    // all-gather the IPC handles through NCCL (device buffers), then map every peer
+    cudaIpcMemHandle_t mine;
+    CU(ctx, cudaIpcGetMemHandle(&mine, f->xchg_base));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+    unsigned char *d_in = nullptr, *d_all = nullptr;
+    CU(ctx, cudaMalloc(&d_in, 64));
+    CU(ctx, cudaMalloc(&d_all, 64 * W));
+    CU(ctx, cudaMemcpy(d_in, &mine, 64, cudaMemcpyHostToDevice));
+    NC(ctx, ncclAllGather(d_in, d_all, 64, ncclChar, ctx->comm, f->s_compute));
+    CU(ctx, cudaStreamSynchronize(f->s_compute));
+    std::vector<cudaIpcMemHandle_t> all(W);
+    CU(ctx, cudaMemcpy(all.data(), d_all, 64 * W, cudaMemcpyDeviceToHost));
+    cudaFree(d_in);
+    cudaFree(d_all);
+    for (int r = 0; r < W; ++r) {
+      if (r == ctx->rank) {
+        f->peer_base[r] = f->xchg_base;
+      } else {
+        CU(ctx, cudaIpcOpenMemHandle(&f->peer_base[r], all[r], cudaIpcMemLazyEnablePeerAccess));
+      }
+    }
+  } else {
+    const size_t rows = (size_t)f->region_cap * W;
+    CU(ctx, dmalloc(&f->send_keys, rows));
+    if (f->has_vals) CU(ctx, cudaMalloc(&f->send_vals, rows * (size_t)f->val_bytes));
+    if (f->has_ts) CU(ctx, dmalloc(&f->send_ts, rows));
+    CU(ctx, dmalloc(&f->d_send_counts, BW_MAX_WORLD));
+    CU(ctx, dmalloc(&f->d_all_counts, (size_t)BW_MAX_WORLD * BW_MAX_WORLD));
+    CU(ctx, cudaHostAlloc((void**)&f->h_all_counts, sizeof(u64) * BW_MAX_WORLD * BW_MAX_WORLD, cudaHostAllocDefault));
+    for (int r = 0; r < W; ++r) f->peer_base[r] = nullptr;
+    f->peer_base[ctx->rank] = f->xchg_base;
+  }
+  return BW_OK;
+}
+
+bw_status bw_fold_create(bw_ctx* ctx, const bw_fold_spec* spec, bw_fold** out) {
+  if (!ctx || !spec || !out) CTX_FAIL(ctx, BW_ERR_SPEC, "bw_fold_create: NULL argument");
+  if (spec->struct_size != sizeof(bw_fold_spec))
+    CTX_FAIL(ctx, BW_ERR_SPEC, "bw_fold_spec.struct_size %u != %zu", spec->struct_size, sizeof(bw_fold_spec));
+  if (spec->reduction < 0 || spec->reduction > BW_RED_MEAN) CTX_FAIL(ctx, BW_ERR_SPEC, "bad reduction %d", spec->reduction);
+  if (spec->val_dtype < 0 || spec->val_dtype > BW_VAL_F64) CTX_FAIL(ctx, BW_ERR_SPEC, "bad val_dtype %d", spec->val_dtype);
+  if (spec->length_us <= 0 || spec->offset_us <= 0 || spec->offset_us > spec->length_us)
+    CTX_FAIL(ctx, BW_ERR_SPEC, "need 0 < offset_us <= length_us (windowing.py:880-883)");
+  if (spec->wait_us < 0) CTX_FAIL(ctx, BW_ERR_SPEC, "wait_us must be >= 0");
+  if (spec->ts_source == BW_TS_FROM_VALUE && spec->val_dtype > BW_VAL_I64)
+    CTX_FAIL(ctx, BW_ERR_SPEC, "BW_TS_FROM_VALUE needs an integer val_dtype");
+  if (spec->max_batch_rows == 0 || spec->max_batch_rows >= (1ULL << 32) / (u64)ctx->world)
+    CTX_FAIL(ctx, BW_ERR_SPEC, "max_batch_rows * world must be in [1, 2^32)");
+  CU(ctx, cudaSetDevice(ctx->device));
+  bw_fold* f = new bw_fold();
+  f->ctx = ctx;
+  f->spec = *spec;
+  FoldParams& p = f->p;
+  p.length_us = spec->length_us;
+  p.offset_us = spec->offset_us;
+  p.align_us = spec->align_to_us;
+  p.wait_us = spec->wait_us;
+  p.pane_us = gcd_i64(spec->length_us, spec->offset_us);
+  p.panes_per_offset = spec->offset_us / p.pane_us;
+  p.panes_per_window = spec->length_us / p.pane_us;
+  p.inv_pane = 1.0 / (double)p.pane_us;
+  p.reduction = spec->reduction;
+  p.val_dtype = spec->val_dtype;
+  p.ts_from_value = spec->ts_source == BW_TS_FROM_VALUE;
+  p.track_wm = spec->wait_us != BW_WAIT_FOREVER;
+  p.ordered = spec->ordered;
+  p.need_count = spec->reduction == BW_RED_MEAN;
+  const bool is_float = spec->val_dtype >= BW_VAL_F32, is_signed = spec->val_dtype == BW_VAL_I64;
+  switch (spec->reduction) {
+    case BW_RED_COUNT: p.op = BW_OP_ADD_ONE; p.acc_identity = 0; break;
+    case BW_RED_SUM: p.op = is_float ? BW_OP_ADD_F64 : BW_OP_ADD_U64; p.acc_identity = 0; break;
+    case BW_RED_MEAN: p.op = BW_OP_ADD_F64; p.acc_identity = 0; break;
+    case BW_RED_MIN:
+      p.op = (is_float || !is_signed) ? BW_OP_MIN_U64 : BW_OP_MIN_S64;
+      p.acc_identity = (p.op == BW_OP_MIN_S64) ? (u64)INT64_MAX : ~0ULL;
+      break;
+    default:
+      p.op = (is_float || !is_signed) ? BW_OP_MAX_U64 : BW_OP_MAX_S64;
+      p.acc_identity = (p.op == BW_OP_MAX_S64) ? (u64)INT64_MIN : 0ULL;
+      break;
+  }
+  f->val_bytes = spec->val_dtype == BW_VAL_F32 ? 4 : 8;
+  f->has_ts = spec->ts_source == BW_TS_COLUMN;
+  f->has_vals = !(spec->reduction == BW_RED_COUNT && f->has_ts);
+  bw_status st = fold_alloc(f);
+  if (st != BW_OK) return st;
+  if (ctx->world > 1) {
+    st = xchg_setup(f);
+    if (st != BW_OK) return st;
+  }
+  CU(ctx, cudaStreamSynchronize(f->s_compute));
+  *out = f;
+  return BW_OK;
+}
+
+void bw_fold_destroy(bw_fold* f) {
+  if (!f) return;
+  cudaSetDevice(f->ctx->device);
+  cudaDeviceSynchronize();
+  for (int r = 0; r < f->ctx->world; ++r)
+    if (f->peer_base[r] && r != f->ctx->rank && f->spec.exchange == BW_XCHG_P2P) cudaIpcCloseMemHandle(f->peer_base[r]);
+  void* dev[] = {f->t.hot, f->t.cold, f->t.nodes, f->t.node_acc2, f->t.free_stack, f->t.dirty, f->d_ctr, f->e.c_key,
+                 f->e.c_wid, f->e.c_acc, f->e.c_count, f->e.c_seq, f->e.c_epoch, f->e.l_key, f->e.l_wid, f->e.l_val,
+                 f->e.l_ts, f->e.l_seq, f->e.l_epoch, f->d_rmin, f->d_rmax, f->d_rbad, f->d_verdict, f->d_kflat,
+                 f->d_ksorted, f->d_tsflat, f->d_tssorted, f->d_prefmax, f->d_idx, f->d_idxsorted, f->d_late, f->d_cub,
+                 f->d_sk, f->d_sk2, f->d_gather, f->d_perm, f->d_perm2, f->xchg_base, f->d_tile_counts,
+                 f->d_send_counts, f->d_all_counts, f->send_keys, f->send_vals, f->send_ts};
+  for (void* p : dev)
+    if (p) cudaFree(p);
+  for (auto& s : f->stages) {
+    if (s.d_keys) cudaFree(s.d_keys);
+    if (s.d_vals) cudaFree(s.d_vals);
+    if (s.d_ts) cudaFree(s.d_ts);
+    if (s.consumed) cudaEventDestroy(s.consumed);
+  }
+  for (auto& s : f->slots) {
+    if (s.h_keys) cudaFreeHost(s.h_keys);
+    if (s.h_vals) cudaFreeHost(s.h_vals);
+    if (s.h_ts) cudaFreeHost(s.h_ts);
+  }
+  void* host[] = {f->h_ctr, f->h_verdict, f->h_all_counts, f->ho_ckey, f->ho_cacc, f->ho_ccount, f->ho_cepoch,
+                  f->ho_cwid, f->ho_lkey, f->ho_lval, f->ho_lepoch, f->ho_lwid, f->ho_lts};
+  for (void* p : host)
+    if (p) cudaFreeHost(p);
+  for (auto& t : f->timers) {
+    cudaEventDestroy(t.a);
+    cudaEventDestroy(t.b);
+  }
+  if (f->s_compute) cudaStreamDestroy(f->s_compute);
+  if (f->s_copy) cudaStreamDestroy(f->s_copy);
+  if (f->s_pre) cudaStreamDestroy(f->s_pre);
+  if (f->ev_in) cudaEventDestroy(f->ev_in);
+  if (f->ev_pre) cudaEventDestroy(f->ev_pre);
+  if (f->ev_h2d) cudaEventDestroy(f->ev_h2d);
+  delete f;
+}
+
+// ---------------------------------------------------------------------------
+// ingest
+// ---------------------------------------------------------------------------
+bw_status bw_ingest_acquire(bw_fold* f, uint64_t max_rows, bw_batch* out) {
+  if (!f || !out) return BW_ERR_SPEC;
+  bw_ctx* ctx = f->ctx;
+  if (max_rows > f->spec.max_batch_rows) FAIL(f, BW_ERR_SPEC, "acquire: %llu rows > max_batch_rows", (unsigned long long)max_rows);
+  CU(ctx, cudaSetDevice(ctx->device));
+  const u32 nslots = f->spec.ring_slots > 0 ? (u32)f->spec.ring_slots : 3u;
+  u32 pick = ~0u;
+  for (u32 i = 0; i < f->slots.size(); ++i)
+    if (!f->slots[i].acquired) {
+      pick = i;
+      break;
+    }
+  if (pick == ~0u) {
+    if (f->slots.size() >= nslots) FAIL(f, BW_ERR_STATE, "all %u ingest slots are acquired; commit one first", nslots);
+    Slot s;
+    const size_t rows = f->spec.max_batch_rows;
+    CU(ctx, cudaHostAlloc((void**)&s.h_keys, rows * 8, cudaHostAllocDefault));
+    if (f->has_vals) CU(ctx, cudaHostAlloc(&s.h_vals, rows * (size_t)f->val_bytes, cudaHostAllocDefault));
+    if (f->has_ts) CU(ctx, cudaHostAlloc((void**)&s.h_ts, rows * 8, cudaHostAllocDefault));
+    f->slots.push_back(s);
+    pick = (u32)f->slots.size() - 1;
+  }
+  Slot& s = f->slots[pick];
+  s.acquired = true;
+  out->keys = s.h_keys;
+  out->vals = s.h_vals;
+  out->ts_us = s.h_ts;
+  out->capacity = f->spec.max_batch_rows;
+  out->slot = pick;
+  out->reserved = 0;
+  return BW_OK;
+}
+
+static EventPair* next_timer(bw_fold* f) {
+  if (f->timers_used == f->timers.size()) {
+    if (f->timers.size() >= 4096) return nullptr;
+    EventPair ep;
+    if (cudaEventCreate(&ep.a) != cudaSuccess || cudaEventCreate(&ep.b) != cudaSuccess) return nullptr;
+    ep.rows = 0;
+    f->timers.push_back(ep);
+  }
+  return &f->timers[f->timers_used++];
+}
+
+static bw_status slow_path(bw_fold* f, const BatchView& bv, u64 total, u64 epoch_ord);
+
+// Partition + exchange of this rank's rows; fills `bv` with the received segments.
+static bw_status exchange(bw_fold* f, const u64* d_keys, const void* d_vals, const i64* d_ts, u64 rows, BatchView* bv) {
+  bw_ctx* ctx = f->ctx;
+  const int W = ctx->world, R = ctx->rank;
+  cudaStream_t s = f->s_compute;
+  const int buf = f->xbuf;
+  f->xbuf ^= 1;
+  XLayout L = xlayout(f);
+  PartIn in;
+  in.keys = d_keys;
+  in.vals = f->has_vals ? d_vals : nullptr;
+  in.ts = f->has_ts ? d_ts : nullptr;
+  in.n = rows;
+  in.val_bytes = f->has_vals ? f->val_bytes : 0;
+  in.world = W;
+  PartOut po;
+  memset(&po, 0, sizeof po);
+  po.region_cap = f->region_cap;
+  const bool p2p = f->spec.exchange == BW_XCHG_P2P;
+  for (int d = 0; d < W; ++d) {
+    if (p2p) {
+      char* base = (char*)f->peer_base[d];
+      po.keys[d] = (u64*)(base + L.keys_off[buf]) + (size_t)R * f->region_cap;
+      po.vals[d] = f->has_vals ? (void*)(base + L.vals_off[buf] + (size_t)R * f->region_cap * f->val_bytes) : nullptr;
+      po.ts[d] = f->has_ts ? (i64*)(base + L.ts_off[buf]) + (size_t)R * f->region_cap : nullptr;
+      po.counts[d] = (u64*)(base + L.counts_off[buf]) + R;
+    } else {
+      po.keys[d] = f->send_keys + (size_t)d * f->region_cap;
+      po.vals[d] = f->has_vals ? (void*)((char*)f->send_vals + (size_t)d * f->region_cap * f->val_bytes) : nullptr;
+      po.ts[d] = f->has_ts ? f->send_ts + (size_t)d * f->region_cap : nullptr;
+      po.counts[d] = f->d_send_counts + d;
+    }
+  }
+  const u64 ntiles = (rows + BW_PART_TILE - 1) / BW_PART_TILE;
+  int grid = (int)std::min<u64>(std::max<u64>(ntiles, 1), (u64)ctx->sm_count * 8);
+  k_part_hist<<<grid, BW_PART_THREADS, 0, s>>>(in, f->d_tile_counts);
+  k_part_scan<<<1, 1024, 0, s>>>(rows, W, f->d_tile_counts, po, f->d_ctr);
+  k_part_scatter<<<grid, BW_PART_THREADS, 0, s>>>(in, f->d_tile_counts, po);
+  CU(ctx, cudaGetLastError());
+  f->st.kernel_launches += 3;
+  char* mine = (char*)f->xchg_base;
+  u64* my_counts = (u64*)(mine + L.counts_off[buf]);
+  if (p2p) {
+    // every rank's stores are complete once it enters this collective (stream
+    // order); its completion here means all peers have entered it.
+    NC(ctx, ncclAllReduce(f->d_verdict, f->d_verdict, 1, ncclUint32, ncclMax, ctx->comm, s));
+  } else {
+    NC(ctx, ncclAllGather(f->d_send_counts, f->d_all_counts, BW_MAX_WORLD, ncclUint64, ctx->comm, s));
+    CU(ctx, cudaMemcpyAsync(f->h_all_counts, f->d_all_counts, sizeof(u64) * BW_MAX_WORLD * W, cudaMemcpyDeviceToHost, s));
+    CU(ctx, cudaStreamSynchronize(s));
+    u64 recv_counts[BW_MAX_WORLD];
+    NC(ctx, ncclGroupStart());
+    for (int r = 0; r < W; ++r) {
+      const u64 nsend = f->h_all_counts[(size_t)R * BW_MAX_WORLD + r];
+      const u64 nrecv = f->h_all_counts[(size_t)r * BW_MAX_WORLD + R];
+      recv_counts[r] = nrecv;
+      u64* rk = (u64*)(mine + L.keys_off[buf]) + (size_t)r * f->region_cap;
+      NC(ctx, ncclSend(f->send_keys + (size_t)r * f->region_cap, nsend, ncclUint64, r, ctx->comm, s));
+      NC(ctx, ncclRecv(rk, nrecv, ncclUint64, r, ctx->comm, s));
+      if (f->has_vals) {
+        char* rv = mine + L.vals_off[buf] + (size_t)r * f->region_cap * f->val_bytes;
+        NC(ctx, ncclSend((char*)f->send_vals + (size_t)r * f->region_cap * f->val_bytes, nsend * f->val_bytes, ncclChar, r,
+                         ctx->comm, s));
+        NC(ctx, ncclRecv(rv, nrecv * f->val_bytes, ncclChar, r, ctx->comm, s));
+      }
+      if (f->has_ts) {
+        i64* rt = (i64*)(mine + L.ts_off[buf]) + (size_t)r * f->region_cap;
+        NC(ctx, ncclSend(f->send_ts + (size_t)r * f->region_cap, nsend, ncclInt64, r, ctx->comm, s));
+        NC(ctx, ncclRecv(rt, nrecv, ncclInt64, r, ctx->comm, s));
+      }
+    }
+    NC(ctx, ncclGroupEnd());
+    CU(ctx, cudaMemcpyAsync(my_counts, recv_counts, sizeof(u64) * W, cudaMemcpyHostToDevice, s));
+    // recv_counts is a stack array: make the copy complete before returning
+    CU(ctx, cudaStreamSynchronize(s));
+  }
+  memset(bv, 0, sizeof *bv);
+  bv->nseg = W;
+  bv->counts_on_device = 1;
+  bv->d_counts = my_counts;
+  bv->max_rows = f->max_recv_rows;
+  for (int r = 0; r < W; ++r) {
+    bv->keys[r] = (const u64*)(mine + L.keys_off[buf]) + (size_t)r * f->region_cap;
+    bv->vals[r] = f->has_vals ? (const void*)(mine + L.vals_off[buf] + (size_t)r * f->region_cap * f->val_bytes) : nullptr;
+    bv->ts[r] = f->has_ts ? (const i64*)(mine + L.ts_off[buf]) + (size_t)r * f->region_cap : nullptr;
+  }
+  return BW_OK;
+}
+
+// Everything after the columns are on the device (on s_compute's dependency chain).
+static bw_status run_batch(bw_fold* f, const u64* d_keys, const void* d_vals, const i64* d_ts, u64 rows, u64 epoch) {
+  bw_ctx* ctx = f->ctx;
+  const u32 batch_no = f->batch_no++;
+  const u64 ord = f->ordinal_base + f->ordinal_epoch.size();
+  f->ordinal_epoch.push_back(epoch);
+  f->st.rows_ingested += rows;
+  BatchView bv;
+  memset(&bv, 0, sizeof bv);
+  u64 max_total = rows;
+  cudaStream_t pre_stream = f->s_pre;
+  if (ctx->world > 1) {
+    bw_status st = exchange(f, d_keys, d_vals, d_ts, rows, &bv);
+    if (st != BW_OK) return st;
+    max_total = f->max_recv_rows;
+    pre_stream = f->s_compute;  // received counts live on the device: keep one stream
+  } else {
+    bv.nseg = 1;
+    bv.keys[0] = d_keys;
+    bv.vals[0] = f->has_vals ? d_vals : nullptr;
+    bv.ts[0] = f->has_ts ? d_ts : nullptr;
+    bv.h_counts[0] = rows;
+    bv.max_rows = rows;
+    f->st.rows_received += rows;
+  }
+  bool clean = true;
+  if (f->p.track_wm && max_total > 0) {
+    if (pre_stream != f->s_compute) CU(ctx, cudaStreamWaitEvent(pre_stream, f->ev_in, 0));
+    const u64 nranges = (max_total + BW_RANGE_ROWS - 1) / BW_RANGE_ROWS;
+    int grid = (int)std::min<u64>((nranges * 32 + BW_PRE_THREADS - 1) / BW_PRE_THREADS, (u64)ctx->sm_count * 8);
+    if (grid < 1) grid = 1;
+    k_prepass_ranges<<<grid, BW_PRE_THREADS, 0, pre_stream>>>(bv, f->p, f->d_rmin, f->d_rmax, f->d_rbad);
+    k_prepass_scan<<<1, 1024, 0, pre_stream>>>(bv, f->p, f->d_rmin, f->d_rmax, f->d_rbad, f->d_ctr, f->d_verdict);
+    CU(ctx, cudaGetLastError());
+    f->st.kernel_launches += 2;
+    CU(ctx, cudaMemcpyAsync(f->h_verdict, f->d_verdict, sizeof(u32), cudaMemcpyDeviceToHost, pre_stream));
+    CU(ctx, cudaEventRecord(f->ev_pre, pre_stream));
+    CU(ctx, cudaEventSynchronize(f->ev_pre));
+    clean = (*f->h_verdict != 0);
+    if (pre_stream != f->s_compute) CU(ctx, cudaStreamWaitEvent(f->s_compute, f->ev_pre, 0));
+  }
+  if (max_total > 0) {
+    if (clean) {
+      EventPair* ep = next_timer(f);
+      if (ep) {
+        ep->rows = (ctx->world > 1) ? 0 : rows;
+        CU(ctx, cudaEventRecord(ep->a, f->s_compute));
+      }
+      const u64 tile = (u64)BW_FOLD_THREADS * BW_FOLD_UNROLL;
+      int grid = (int)std::min<u64>((max_total + tile - 1) / tile, (u64)f->fold_grid);
+      k_fold<<<grid, BW_FOLD_THREADS, 0, f->s_compute>>>(bv, f->t, f->p, batch_no, 0);
+      CU(ctx, cudaGetLastError());
+      if (ep) CU(ctx, cudaEventRecord(ep->b, f->s_compute));
+      f->st.kernel_launches++;
+      f->st.fold_launches++;
+    } else {
+      u64 total = rows;
+      if (ctx->world > 1) {
+        u64 hc[BW_MAX_WORLD];
+        CU(ctx, cudaMemcpyAsync(hc, bv.d_counts, sizeof(u64) * ctx->world, cudaMemcpyDeviceToHost, f->s_compute));
+        CU(ctx, cudaStreamSynchronize(f->s_compute));
+        total = 0;
+        for (int r = 0; r < ctx->world; ++r) total += hc[r];
+      }
+      bw_status st = slow_path(f, bv, total, ord);
+      if (st != BW_OK) return st;
+      f->st.slow_batches++;
+    }
+    k_close_dirty<<<f->close_grid, 256, 0, f->s_compute>>>(f->t, f->p, f->e, ord);
+    k_reset_dirty<<<1, 1, 0, f->s_compute>>>(f->t);
+    CU(ctx, cudaGetLastError());
+    f->st.kernel_launches += 2;
+  }
+  return BW_OK;
+}
+
+bw_status bw_ingest_commit(bw_fold* f, const bw_batch* batch, uint64_t rows, uint64_t epoch) {
+  if (!f || !batch) return BW_ERR_SPEC;
+  bw_ctx* ctx = f->ctx;
+  if (f->eof_done) FAIL(f, BW_ERR_STATE, "commit after eof");
+  if (batch->slot >= f->slots.size() || !f->slots[batch->slot].acquired) FAIL(f, BW_ERR_STATE, "commit of a slot that is not acquired");
+  if (rows > f->spec.max_batch_rows) FAIL(f, BW_ERR_SPEC, "commit: rows > max_batch_rows");
+  CU(ctx, cudaSetDevice(ctx->device));
+  Slot& sl = f->slots[batch->slot];
+  // device staging: 3 buffers, reused once the kernels that read them are done
+  if (f->stages.empty()) f->stages.resize(3);
+  Stage& sg = f->stages[f->stage_next];
+  f->stage_next = (f->stage_next + 1) % (u32)f->stages.size();
+  if (!sg.d_keys) {
+    const size_t cap = f->spec.max_batch_rows;
+    CU(ctx, dmalloc(&sg.d_keys, cap));
+    if (f->has_vals) CU(ctx, cudaMalloc(&sg.d_vals, cap * (size_t)f->val_bytes));
+    if (f->has_ts) CU(ctx, dmalloc(&sg.d_ts, cap));
+    CU(ctx, cudaEventCreateWithFlags(&sg.consumed, cudaEventDisableTiming));
+  }
+  if (sg.used) CU(ctx, cudaStreamWaitEvent(f->s_copy, sg.consumed, 0));
+  if (rows) {
+    CU(ctx, cudaMemcpyAsync(sg.d_keys, sl.h_keys, rows * 8, cudaMemcpyHostToDevice, f->s_copy));
+    if (f->has_vals) CU(ctx, cudaMemcpyAsync(sg.d_vals, sl.h_vals, rows * (size_t)f->val_bytes, cudaMemcpyHostToDevice, f->s_copy));
+    if (f->has_ts) CU(ctx, cudaMemcpyAsync(sg.d_ts, sl.h_ts, rows * 8, cudaMemcpyHostToDevice, f->s_copy));
+  }
+  CU(ctx, cudaEventRecord(f->ev_h2d, f->s_copy));
+  CU(ctx, cudaStreamWaitEvent(f->s_compute, f->ev_h2d, 0));
+  CU(ctx, cudaEventRecord(f->ev_in, f->s_copy));
+  bw_status st = run_batch(f, sg.d_keys, sg.d_vals, sg.d_ts, rows, epoch);
+  if (st != BW_OK) return st;
+  CU(ctx, cudaEventRecord(sg.consumed, f->s_compute));
+  sg.used = true;
+  // the pinned slot may be refilled once its H2D is done
+  CU(ctx, cudaEventSynchronize(f->ev_h2d));
+  sl.acquired = false;
+  return BW_OK;
+}
+
+bw_status bw_ingest_device(bw_fold* f, const uint64_t* d_keys, const void* d_vals, const int64_t* d_ts_us, uint64_t rows,
+                           uint64_t epoch) {
+  if (!f) return BW_ERR_SPEC;
+  bw_ctx* ctx = f->ctx;
+  if (f->eof_done) FAIL(f, BW_ERR_STATE, "ingest after eof");
+  if (rows > f->spec.max_batch_rows) FAIL(f, BW_ERR_SPEC, "ingest: rows > max_batch_rows");
+  if (rows && (!d_keys || (f->has_vals && !d_vals) || (f->has_ts && !d_ts_us))) FAIL(f, BW_ERR_SPEC, "ingest: missing column");
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaEventRecord(f->ev_in, f->s_compute));
+  return run_batch(f, d_keys, d_vals, d_ts_us, rows, epoch);
+}
+
+// ---------------------------------------------------------------------------
+// exact path for an activation with possible late items
+// ---------------------------------------------------------------------------
+struct MaxI64 {
+  __host__ __device__ __forceinline__ i64 operator()(const i64& a, const i64& b) const { return a > b ? a : b; }
+};
+
+static bw_status slow_path(bw_fold* f, const BatchView& bv, u64 total, u64 epoch_ord) {
+  bw_ctx* ctx = f->ctx;
+  cudaStream_t s = f->s_compute;
+  const u32 batch_no = f->batch_no - 1;
+  if (total == 0) return BW_OK;
+  if (total > f->slow_cap) {
+    void* old[] = {f->d_kflat, f->d_ksorted, f->d_tsflat, f->d_tssorted, f->d_prefmax, f->d_idx, f->d_idxsorted, f->d_late, f->d_cub};
+    CU(ctx, cudaStreamSynchronize(s));
+    for (void* p : old)
+      if (p) cudaFree(p);
+    u64 cap = std::max<u64>(total, 1024);
+    CU(ctx, dmalloc(&f->d_kflat, cap));
+    CU(ctx, dmalloc(&f->d_ksorted, cap));
+    CU(ctx, dmalloc(&f->d_tsflat, cap));
+    CU(ctx, dmalloc(&f->d_tssorted, cap));
+    CU(ctx, dmalloc(&f->d_prefmax, cap));
+    CU(ctx, dmalloc(&f->d_idx, cap));
+    CU(ctx, dmalloc(&f->d_idxsorted, cap));
+    CU(ctx, dmalloc(&f->d_late, cap));
+    size_t b1 = 0, b2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, b1, f->d_kflat, f->d_ksorted, f->d_idx, f->d_idxsorted, (int)cap, 0, 64, s);
+    cub::DeviceScan::ExclusiveScanByKey(nullptr, b2, f->d_ksorted, f->d_tssorted, f->d_prefmax, MaxI64(), (i64)INT64_MIN,
+                                        (int)cap, cub::Equality(), s);
+    f->cub_bytes = std::max(b1, b2) + 256;
+    CU(ctx, cudaMalloc(&f->d_cub, f->cub_bytes));
+    f->slow_cap = cap;
+  }
+  const int grid = ctx->sm_count * 8;
+  k_slow_flatten<<<grid, 256, 0, s>>>(bv, f->p, f->d_kflat, f->d_tsflat, f->d_idx);
+  size_t tb = f->cub_bytes;
+  CU(ctx, cub::DeviceRadixSort::SortPairs(f->d_cub, tb, f->d_kflat, f->d_ksorted, f->d_idx, f->d_idxsorted, (int)total, 0, 64, s));
+  k_gather_i64<<<grid, 256, 0, s>>>(f->d_tsflat, f->d_idxsorted, f->d_tssorted, total);
+  tb = f->cub_bytes;
+  CU(ctx, cub::DeviceScan::ExclusiveScanByKey(f->d_cub, tb, f->d_ksorted, f->d_tssorted, f->d_prefmax, MaxI64(),
+                                              (i64)INT64_MIN, (int)total, cub::Equality(), s));
+  k_slow_classify<<<grid, 256, 0, s>>>(f->t, f->p, f->d_ksorted, f->d_idxsorted, f->d_tssorted, f->d_prefmax, f->d_late, total);
+  k_slow_fold<<<f->fold_grid, BW_FOLD_THREADS, 0, s>>>(bv, f->t, f->p, f->e, f->d_late, batch_no, epoch_ord);
+  CU(ctx, cudaGetLastError());
+  f->st.kernel_launches += 4;  // ours; CUB's launches are not counted
+  return BW_OK;
+}
+
+// ---------------------------------------------------------------------------
+// advance / eof
+// ---------------------------------------------------------------------------
+static bw_status ensure_sort_cap(bw_fold* f, u64 n) {
+  bw_ctx* ctx = f->ctx;
+  if (n <= f->sort_cap) return BW_OK;
+  void* old[] = {f->d_sk, f->d_sk2, f->d_gather, f->d_perm, f->d_perm2};
+  for (void* p : old)
+    if (p) cudaFree(p);
+  u64 cap = std::max<u64>(n, 4096);
+  CU(ctx, dmalloc(&f->d_sk, cap));
+  CU(ctx, dmalloc(&f->d_sk2, cap));
+  CU(ctx, dmalloc(&f->d_gather, cap));
+  CU(ctx, dmalloc(&f->d_perm, cap));
+  CU(ctx, dmalloc(&f->d_perm2, cap));
+  size_t b = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, b, f->d_sk, f->d_sk2, f->d_perm, f->d_perm2, (int)cap, 0, 64, f->s_compute);
+  if (b + 256 > f->cub_bytes) {
+    if (f->d_cub) cudaFree(f->d_cub);
+    f->cub_bytes = b + 256;
+    CU(ctx, cudaMalloc(&f->d_cub, f->cub_bytes));
+  }
+  f->sort_cap = cap;
+  return BW_OK;
+}
+
+// Build the reference-order permutation of n rows (LSD passes of stable radix sorts).
+static bw_status order_rows(bw_fold* f, u64 n, const u64* key, const u64* seq, const u64* epoch, const i64* wid,
+                            bool wid_pass, u64 n_ordinals) {
+  bw_ctx* ctx = f->ctx;
+  cudaStream_t s = f->s_compute;
+  const int grid = ctx->sm_count * 4;
+  k_iota<<<grid, 256, 0, s>>>(f->d_perm, n);
+  f->st.kernel_launches++;
+  struct Pass {
+    int kind, bits;
+  };
+  int ebits = 1;
+  while ((1ULL << ebits) < n_ordinals + 1) ++ebits;
+  std::vector<Pass> passes;
+  if (wid_pass) passes.push_back({BW_SK_WID, 64});
+  passes.push_back({BW_SK_SEQ, 64});
+  passes.push_back({BW_SK_DIGITS, 16});
+  passes.push_back({BW_SK_ALIGNED, 64});
+  if (n_ordinals > 1) passes.push_back({BW_SK_EPOCH, ebits});
+  for (const Pass& ps : passes) {
+    k_sortkey<<<grid, 256, 0, s>>>(ps.kind, key, seq, epoch, wid, f->d_perm, f->d_sk, n, f->ordinal_base);
+    size_t tb = f->cub_bytes;
+    CU(ctx, cub::DeviceRadixSort::SortPairs(f->d_cub, tb, f->d_sk, f->d_sk2, f->d_perm, f->d_perm2, (int)n, 0, ps.bits, s));
+    std::swap(f->d_perm, f->d_perm2);
+    f->st.kernel_launches++;
+  }
+  CU(ctx, cudaGetLastError());
+  return BW_OK;
+}
+
+static bw_status grow_host(bw_fold* f, u64 nc, u64 nl) {
+  bw_ctx* ctx = f->ctx;
+  if (nc > f->hout_cap_c) {
+    void* old[] = {f->ho_ckey, f->ho_cacc, f->ho_ccount, f->ho_cepoch, f->ho_cwid};
+    for (void* p : old)
+      if (p) cudaFreeHost(p);
+    u64 cap = std::max<u64>(nc, 4096);
+    CU(ctx, cudaHostAlloc((void**)&f->ho_ckey, cap * 8, cudaHostAllocDefault));
+    CU(ctx, cudaHostAlloc((void**)&f->ho_cacc, cap * 8, cudaHostAllocDefault));
+    CU(ctx, cudaHostAlloc((void**)&f->ho_ccount, cap * 8, cudaHostAllocDefault));
+    CU(ctx, cudaHostAlloc((void**)&f->ho_cepoch, cap * 8, cudaHostAllocDefault));
+    CU(ctx, cudaHostAlloc((void**)&f->ho_cwid, cap * 8, cudaHostAllocDefault));
+    f->hout_cap_c = cap;
+  }
+  if (nl > f->hout_cap_l) {
+    void* old[] = {f->ho_lkey, f->ho_lval, f->ho_lepoch, f->ho_lwid, f->ho_lts};
+    for (void* p : old)
+      if (p) cudaFreeHost(p);
+    u64 cap = std::max<u64>(nl, 4096);
+    CU(ctx, cudaHostAlloc((void**)&f->ho_lkey, cap * 8, cudaHostAllocDefault));
+    CU(ctx, cudaHostAlloc((void**)&f->ho_lval, cap * 8, cudaHostAllocDefault));
+    CU(ctx, cudaHostAlloc((void**)&f->ho_lepoch, cap * 8, cudaHostAllocDefault));
+    CU(ctx, cudaHostAlloc((void**)&f->ho_lwid, cap * 8, cudaHostAllocDefault));
+    CU(ctx, cudaHostAlloc((void**)&f->ho_lts, cap * 8, cudaHostAllocDefault));
+    f->hout_cap_l = cap;
+  }
+  return BW_OK;
+}
+
+static const char* status_name(u32 s) {
+  switch (s) {
+    case BW_ERR_CAPACITY: return "capacity exhausted (key table, pane pool, exchange region or emit buffer): raise capacity_hint / max_emit_rows / max_late_rows";
+    case BW_ERR_RANGE: return "window id out of range (timestamp too far from align_to for this window length)";
+    default: return "device-side failure";
+  }
+}
+
+static bw_status collect(bw_fold* f, bw_emit* out) {
+  bw_ctx* ctx = f->ctx;
+  cudaStream_t s = f->s_compute;
+  CU(ctx, cudaMemcpyAsync(f->h_ctr, f->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+  CU(ctx, cudaStreamSynchronize(s));
+  if (f->h_ctr->err) FAIL(f, (bw_status)f->h_ctr->err, "kernel raised status %u: %s", f->h_ctr->err, status_name(f->h_ctr->err));
+  const u64 nc = std::min<u64>(f->h_ctr->n_closed, f->e.max_closed);
+  const u64 nl = std::min<u64>(f->h_ctr->n_late, f->e.max_late);
+  f->st.live_keys = f->h_ctr->live_keys;
+  f->st.pane_nodes_used = f->h_ctr->pool_next - 1;
+  bw_status st = grow_host(f, nc, nl);
+  if (st != BW_OK) return st;
+  const bool ordered = f->spec.emit_order == BW_ORDER_REFERENCE;
+  const int grid = ctx->sm_count * 4;
+  const u64 n_ord = f->ordinal_epoch.size() + 1;  // +1: the eof activation
+  const bool sliding = f->p.panes_per_window > 1 || f->p.panes_per_offset > 1;
+  auto ship = [&](u64 n, const u64* src, u64* dst, bool use_perm) -> bw_status {
+    if (use_perm) {
+      k_gather_u64<<<grid, 256, 0, s>>>(src, f->d_perm, f->d_gather, n);
+      f->st.kernel_launches++;
+      CU(ctx, cudaMemcpyAsync(dst, f->d_gather, n * 8, cudaMemcpyDeviceToHost, s));
+    } else {
+      CU(ctx, cudaMemcpyAsync(dst, src, n * 8, cudaMemcpyDeviceToHost, s));
+    }
+    return BW_OK;
+  };
+  if (nc) {
+    if (ordered) {
+      st = ensure_sort_cap(f, nc);
+      if (st != BW_OK) return st;
+      st = order_rows(f, nc, f->e.c_key, f->e.c_seq, f->e.c_epoch, f->e.c_wid, sliding, n_ord);
+      if (st != BW_OK) return st;
+    }
+    if ((st = ship(nc, f->e.c_key, f->ho_ckey, ordered))) return st;
+    if ((st = ship(nc, (const u64*)f->e.c_wid, (u64*)f->ho_cwid, ordered))) return st;
+    if ((st = ship(nc, f->e.c_acc, f->ho_cacc, ordered))) return st;
+    if ((st = ship(nc, f->e.c_count, f->ho_ccount, ordered))) return st;
+    if ((st = ship(nc, f->e.c_epoch, f->ho_cepoch, ordered))) return st;
+  }
+  if (nl) {
+    if (ordered) {
+      st = ensure_sort_cap(f, nl);
+      if (st != BW_OK) return st;
+      // rows of one late item were reserved contiguously in ascending window id; stable sorts keep that
+      st = order_rows(f, nl, f->e.l_key, f->e.l_seq, f->e.l_epoch, f->e.l_wid, false, n_ord);
+      if (st != BW_OK) return st;
+    }
+    if ((st = ship(nl, f->e.l_key, f->ho_lkey, ordered))) return st;
+    if ((st = ship(nl, (const u64*)f->e.l_wid, (u64*)f->ho_lwid, ordered))) return st;
+    if ((st = ship(nl, f->e.l_val, f->ho_lval, ordered))) return st;
+    if ((st = ship(nl, (const u64*)f->e.l_ts, (u64*)f->ho_lts, ordered))) return st;
+    if ((st = ship(nl, f->e.l_epoch, f->ho_lepoch, ordered))) return st;
+  }
+  // reset the row counters for the next round
+  CU(ctx, cudaMemsetAsync(&f->d_ctr->n_closed, 0, sizeof(unsigned long long) * 2, s));
+  CU(ctx, cudaStreamSynchronize(s));
+  // ordinal -> user epoch
+  const u64 base = f->ordinal_base;
+  const u64 last_epoch = f->ordinal_epoch.empty() ? 0 : f->ordinal_epoch.back();
+  auto to_epoch = [&](u64 o) -> u64 {
+    u64 i = o - base;
+    return i < f->ordinal_epoch.size() ? f->ordinal_epoch[i] : last_epoch;
+  };
+  for (u64 i = 0; i < nc; ++i) f->ho_cepoch[i] = to_epoch(f->ho_cepoch[i]);
+  for (u64 i = 0; i < nl; ++i) f->ho_lepoch[i] = to_epoch(f->ho_lepoch[i]);
+  f->ordinal_base += f->ordinal_epoch.size();
+  if (!f->ordinal_epoch.empty()) {
+    u64 keep = f->ordinal_epoch.back();
+    f->ordinal_epoch.clear();
+    (void)keep;
+  }
+  out->n_closed = nc;
+  out->closed_key = f->ho_ckey;
+  out->closed_window_id = f->ho_cwid;
+  out->closed_acc = f->ho_cacc;
+  out->closed_count = f->ho_ccount;
+  out->closed_epoch = f->ho_cepoch;
+  out->n_late = nl;
+  out->late_key = f->ho_lkey;
+  out->late_window_id = f->ho_lwid;
+  out->late_val = f->ho_lval;
+  out->late_ts_us = f->ho_lts;
+  out->late_epoch = f->ho_lepoch;
+  return BW_OK;
+}
+
+bw_status bw_advance(bw_fold* f, uint64_t closed_epoch, int64_t system_now_us, bw_emit* out) {
+  (void)closed_epoch;
+  (void)system_now_us;
+  if (!f || !out) return BW_ERR_SPEC;
+  CU(f->ctx, cudaSetDevice(f->ctx->device));
+  return collect(f, out);
+}
+
+bw_status bw_eof(bw_fold* f, bw_emit* out) {
+  if (!f || !out) return BW_ERR_SPEC;
+  bw_ctx* ctx = f->ctx;
+  CU(ctx, cudaSetDevice(ctx->device));
+  if (f->eof_done) FAIL(f, BW_ERR_STATE, "eof called twice");
+  const u64 ord = f->ordinal_base + f->ordinal_epoch.size();
+  k_close_all<<<f->close_grid, 256, 0, f->s_compute>>>(f->t, f->p, f->e, ord);
+  CU(ctx, cudaGetLastError());
+  f->st.kernel_launches++;
+  f->eof_done = true;
+  return collect(f, out);
+}
+
+void bw_window_bounds(const bw_fold_spec* spec, int64_t window_id, int64_t* open_us, int64_t* close_us) {
+  const int64_t o = spec->align_to_us + spec->offset_us * window_id;
+  if (open_us) *open_us = o;
+  if (close_us) *close_us = o + spec->length_us;
+}
+
+static void drain_timers(bw_fold* f) {
+  for (size_t i = 0; i < f->timers_used; ++i) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, f->timers[i].a, f->timers[i].b) == cudaSuccess) {
+      f->st.last_fold_ms = ms;
+      f->st.sum_fold_ms += ms;
+      f->st.fold_rows += f->timers[i].rows;
+    }
+  }
+  f->timers_used = 0;
+}
+
+bw_status bw_fold_stats(bw_fold* f, bw_stats* out) {
+  if (!f || !out) return BW_ERR_SPEC;
+  CU(f->ctx, cudaSetDevice(f->ctx->device));
+  CU(f->ctx, cudaStreamSynchronize(f->s_compute));
+  drain_timers(f);
+  *out = f->st;
+  return BW_OK;
+}
+bw_status bw_fold_reset_timers(bw_fold* f) {
+  if (!f) return BW_ERR_SPEC;
+  CU(f->ctx, cudaStreamSynchronize(f->s_compute));
+  drain_timers(f);
+  f->st.sum_fold_ms = 0;
+  f->st.last_fold_ms = 0;
+  f->st.fold_rows = 0;
+  f->st.fold_launches = 0;
+  return BW_OK;
+}
+bw_status bw_fold_sync(bw_fold* f) {
+  if (!f) return BW_ERR_SPEC;
+  CU(f->ctx, cudaSetDevice(f->ctx->device));
+  CU(f->ctx, cudaStreamSynchronize(f->s_copy));
+  CU(f->ctx, cudaStreamSynchronize(f->s_pre));
+  CU(f->ctx, cudaStreamSynchronize(f->s_compute));
+  return BW_OK;
+}
+bw_status bw_fold_time_begin(bw_fold* f) {
+  if (!f) return BW_ERR_SPEC;
+  bw_ctx* ctx = f->ctx;
+  CU(ctx, cudaSetDevice(ctx->device));
+  if (!f->ev_t0) {
+    CU(ctx, cudaEventCreate(&f->ev_t0));
+    CU(ctx, cudaEventCreate(&f->ev_t1));
+  }
+  // everything submitted so far (copies, prepass) must be done before the clock starts
+  CU(ctx, cudaStreamSynchronize(f->s_copy));
+  CU(ctx, cudaStreamSynchronize(f->s_pre));
+  CU(ctx, cudaStreamSynchronize(f->s_compute));
+  CU(ctx, cudaEventRecord(f->ev_t0, f->s_compute));
+  return BW_OK;
+}
+bw_status bw_fold_time_end(bw_fold* f, float* ms) {
+  if (!f || !ms || !f->ev_t0) return BW_ERR_SPEC;
+  bw_ctx* ctx = f->ctx;
+  CU(ctx, cudaStreamSynchronize(f->s_copy));
+  CU(ctx, cudaStreamSynchronize(f->s_pre));
+  CU(ctx, cudaEventRecord(f->ev_t1, f->s_compute));
+  CU(ctx, cudaEventSynchronize(f->ev_t1));
+  CU(ctx, cudaEventElapsedTime(ms, f->ev_t0, f->ev_t1));
+  return BW_OK;
+}
+void* bw_fold_stream(bw_fold* f) { return f ? (void*)f->s_compute : nullptr; }
+
+bw_status bw_gen_c1(bw_fold* f, uint64_t* d_keys, uint64_t* d_vals, uint64_t start, uint64_t rows, uint64_t n_keys) {
+  if (!f || !n_keys) return BW_ERR_SPEC;
+  CU(f->ctx, cudaSetDevice(f->ctx->device));
+  k_gen_c1<<<f->ctx->sm_count * 8, 256, 0, f->s_compute>>>(d_keys, d_vals, start, rows, n_keys);
+  CU(f->ctx, cudaGetLastError());
+  f->st.kernel_launches++;
+  return BW_OK;
+}
+

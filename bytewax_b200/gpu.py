@@ -1,0 +1,258 @@
+"""Host-side handle on the CUDA windowed-fold path (numpy in, numpy out).
+
+``WindowFold`` is the GPU stand-in for one ``stateful_batch`` step whose logic
+is the reference's ``_WindowLogic`` over an ``EventClock`` and a
+``SlidingWindower``/``TumblingWindower`` with a numeric fold
+(pysrc/bytewax/operators/windowing.py:1046-1190, 1692-1714).  Each
+``ingest`` is one activation of src/operators.rs:755-806; ``advance`` returns
+what that operator would have given downstream, split like ``WindowOut``
+(windowing.py:1193-1222): closed windows (``down`` + ``meta``) and ``late``.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+from . import _native as N
+
+_NP_VAL = {"u64": np.uint64, "i64": np.int64, "f32": np.float32, "f64": np.float64}
+
+
+class Context:
+    """One rank == one GPU (``bw_ctx``)."""
+
+    def __init__(self, device: int = 0, rank: int = 0, world: int = 1, nccl_id: Optional[bytes] = None):
+        self.lib = N.load()
+        self.rank, self.world, self.device = rank, world, device
+        h = C.c_void_p()
+        idbuf = C.create_string_buffer(nccl_id, 128) if nccl_id is not None else None
+        N.check(self.lib.bw_ctx_create(device, rank, world, idbuf, C.byref(h)))
+        self.h = h
+
+    @staticmethod
+    def new_nccl_id() -> bytes:
+        lib = N.load()
+        buf = C.create_string_buffer(128)
+        N.check(lib.bw_nccl_unique_id(buf))
+        return buf.raw
+
+    def close(self):
+        if self.h:
+            self.lib.bw_ctx_destroy(self.h)
+            self.h = None
+
+    # plain device memory (tests / bench)
+    def dev_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        N.check(self.lib.bw_dev_alloc(self.h, nbytes, C.byref(p)), self.h)
+        return p.value
+
+    def dev_free(self, ptr: int):
+        N.check(self.lib.bw_dev_free(self.h, C.c_void_p(ptr)), self.h)
+
+    def h2d(self, dptr: int, arr: np.ndarray):
+        arr = np.ascontiguousarray(arr)
+        N.check(self.lib.bw_memcpy(self.h, C.c_void_p(dptr), arr.ctypes.data_as(C.c_void_p), arr.nbytes, 0), self.h)
+
+    def d2h(self, arr: np.ndarray, dptr: int):
+        N.check(self.lib.bw_memcpy(self.h, arr.ctypes.data_as(C.c_void_p), C.c_void_p(dptr), arr.nbytes, 1), self.h)
+
+    def flush_l2(self):
+        N.check(self.lib.bw_flush_l2(self.h), self.h)
+
+
+@dataclass
+class Emitted:
+    """Rows of one ``advance``/``eof`` in the reference's downstream order."""
+
+    closed_key: np.ndarray
+    closed_window_id: np.ndarray
+    closed_acc: np.ndarray  # typed per reduction / dtype
+    closed_count: np.ndarray
+    closed_epoch: np.ndarray
+    late_key: np.ndarray
+    late_window_id: np.ndarray
+    late_val: np.ndarray
+    late_ts_us: np.ndarray
+    late_epoch: np.ndarray
+
+    def down(self, mean: bool = False) -> List[Tuple[int, Tuple[int, object]]]:
+        """``(key, (window_id, acc))`` like ``WindowOut.down`` (windowing.py:1196-1200)."""
+        if mean:
+            return [
+                (int(k), (int(w), [float(a), int(c)]))
+                for k, w, a, c in zip(self.closed_key, self.closed_window_id, self.closed_acc, self.closed_count)
+            ]
+        return [(int(k), (int(w), a.item())) for k, w, a in zip(self.closed_key, self.closed_window_id, self.closed_acc)]
+
+    def late(self) -> List[Tuple[int, Tuple[int, object]]]:
+        return [(int(k), (int(w), v.item())) for k, w, v in zip(self.late_key, self.late_window_id, self.late_val)]
+
+
+class WindowFold:
+    def __init__(
+        self,
+        ctx: Context,
+        reduction: str = "count",
+        length_us: int = 60_000_000,
+        offset_us: Optional[int] = None,
+        align_to_us: int = 1_640_995_200_000_000,
+        wait_us: int = 0,
+        val_dtype: str = "u64",
+        ts_from_value: bool = False,
+        ordered: bool = False,
+        emit_order: int = N.ORDER_REFERENCE,
+        capacity_hint: int = 1 << 16,
+        max_batch_rows: int = 1 << 20,
+        max_emit_rows: int = 1 << 20,
+        max_late_rows: int = 1 << 16,
+        ring_slots: int = 3,
+        exchange: int = N.XCHG_P2P,
+    ):
+        self.ctx, self.lib = ctx, ctx.lib
+        self.reduction, self.val_dtype, self.ts_from_value = reduction, val_dtype, ts_from_value
+        s = N.BwFoldSpec()
+        s.struct_size = C.sizeof(N.BwFoldSpec)
+        s.reduction = N.RED[reduction]
+        s.val_dtype = N.VAL[val_dtype]
+        s.ts_source = N.TS_FROM_VALUE if ts_from_value else N.TS_COLUMN
+        s.length_us = length_us
+        s.offset_us = offset_us if offset_us is not None else length_us
+        s.align_to_us = align_to_us
+        s.wait_us = N.BW_WAIT_FOREVER if wait_us is None else wait_us
+        s.ordered = int(ordered)
+        s.emit_order = emit_order
+        s.exchange = exchange
+        s.ring_slots = ring_slots
+        s.capacity_hint = capacity_hint
+        s.max_batch_rows = max_batch_rows
+        s.max_emit_rows = max_emit_rows
+        s.max_late_rows = max_late_rows
+        self.spec = s
+        self.has_ts = not ts_from_value
+        self.has_vals = not (reduction == "count" and self.has_ts)
+        h = C.c_void_p()
+        N.check(self.lib.bw_fold_create(ctx.h, C.byref(s), C.byref(h)), ctx.h)
+        self.h = h
+        self._epoch = 0
+
+    # -- ingest ------------------------------------------------------------
+    def acquire(self, rows: Optional[int] = None) -> N.BwBatch:
+        b = N.BwBatch()
+        n = self.spec.max_batch_rows if rows is None else rows
+        N.check(self.lib.bw_ingest_acquire(self.h, n, C.byref(b)), self.ctx.h)
+        return b
+
+    def slot_arrays(self, b: N.BwBatch):
+        """numpy views on a borrowed pinned slot."""
+        cap = int(b.capacity)
+        keys = np.ctypeslib.as_array(b.keys, shape=(cap,))
+        vals = None
+        if b.vals:
+            vals = np.ctypeslib.as_array(C.cast(b.vals, C.POINTER(C.c_uint8)), shape=(cap * np.dtype(_NP_VAL[self.val_dtype]).itemsize,)).view(_NP_VAL[self.val_dtype])
+        ts = np.ctypeslib.as_array(b.ts_us, shape=(cap,)) if b.ts_us else None
+        return keys, vals, ts
+
+    def commit(self, b: N.BwBatch, rows: int, epoch: Optional[int] = None):
+        if epoch is None:
+            self._epoch += 1
+            epoch = self._epoch
+        N.check(self.lib.bw_ingest_commit(self.h, C.byref(b), rows, epoch), self.ctx.h)
+
+    def ingest(self, keys, vals=None, ts=None, epoch: Optional[int] = None):
+        """One activation from host arrays (pinned slot -> async H2D -> kernels)."""
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        n = keys.shape[0]
+        b = self.acquire(n)
+        k, v, t = self.slot_arrays(b)
+        k[:n] = keys
+        if self.has_vals:
+            if vals is None:
+                raise ValueError("this fold needs a value column")
+            v[:n] = np.asarray(vals).astype(_NP_VAL[self.val_dtype], copy=False)
+        if self.has_ts:
+            if ts is None:
+                raise ValueError("this fold needs a ts_us column")
+            t[:n] = np.asarray(ts, dtype=np.int64)
+        self.commit(b, n, epoch)
+
+    def ingest_device(self, d_keys: int, d_vals: Optional[int], d_ts: Optional[int], rows: int, epoch: Optional[int] = None):
+        if epoch is None:
+            self._epoch += 1
+            epoch = self._epoch
+        N.check(
+            self.lib.bw_ingest_device(self.h, C.c_void_p(d_keys), C.c_void_p(d_vals or 0), C.c_void_p(d_ts or 0), rows, epoch),
+            self.ctx.h,
+        )
+
+    def gen_c1(self, d_keys: int, d_vals: int, start: int, rows: int, n_keys: int):
+        N.check(self.lib.bw_gen_c1(self.h, C.c_void_p(d_keys), C.c_void_p(d_vals), start, rows, n_keys), self.ctx.h)
+
+    # -- results -----------------------------------------------------------
+    def _acc_dtype(self):
+        if self.reduction == "count":
+            return np.uint64
+        if self.reduction == "mean":
+            return np.float64
+        if self.val_dtype in ("f32", "f64"):
+            return np.float64
+        return np.int64 if self.val_dtype == "i64" else np.uint64
+
+    def _wrap(self, e: N.BwEmit) -> Emitted:
+        nc, nl = int(e.n_closed), int(e.n_late)
+
+        def arr(ptr, n, dt):
+            if n == 0:
+                return np.zeros(0, dtype=dt)
+            return np.ctypeslib.as_array(ptr, shape=(n,)).view(dt).copy()
+
+        late_dt = np.float64 if self.val_dtype in ("f32", "f64") else (np.int64 if self.val_dtype == "i64" else np.uint64)
+        return Emitted(
+            arr(e.closed_key, nc, np.uint64), arr(e.closed_window_id, nc, np.int64), arr(e.closed_acc, nc, self._acc_dtype()),
+            arr(e.closed_count, nc, np.uint64), arr(e.closed_epoch, nc, np.uint64),
+            arr(e.late_key, nl, np.uint64), arr(e.late_window_id, nl, np.int64), arr(e.late_val, nl, late_dt),
+            arr(e.late_ts_us, nl, np.int64), arr(e.late_epoch, nl, np.uint64),
+        )
+
+    def advance(self) -> Emitted:
+        e = N.BwEmit()
+        N.check(self.lib.bw_advance(self.h, 0, 0, C.byref(e)), self.ctx.h)
+        return self._wrap(e)
+
+    def eof(self) -> Emitted:
+        e = N.BwEmit()
+        N.check(self.lib.bw_eof(self.h, C.byref(e)), self.ctx.h)
+        return self._wrap(e)
+
+    def window_bounds(self, window_id: int) -> Tuple[int, int]:
+        o, c = C.c_int64(), C.c_int64()
+        self.lib.bw_window_bounds(C.byref(self.spec), window_id, C.byref(o), C.byref(c))
+        return o.value, c.value
+
+    def stats(self) -> N.BwStats:
+        st = N.BwStats()
+        N.check(self.lib.bw_fold_stats(self.h, C.byref(st)), self.ctx.h)
+        return st
+
+    def reset_timers(self):
+        N.check(self.lib.bw_fold_reset_timers(self.h), self.ctx.h)
+
+    def time_begin(self):
+        N.check(self.lib.bw_fold_time_begin(self.h), self.ctx.h)
+
+    def time_end(self) -> float:
+        ms = C.c_float()
+        N.check(self.lib.bw_fold_time_end(self.h, C.byref(ms)), self.ctx.h)
+        return ms.value
+
+    def sync(self):
+        N.check(self.lib.bw_fold_sync(self.h), self.ctx.h)
+
+    def close(self):
+        if self.h:
+            self.lib.bw_fold_destroy(self.h)
+            self.h = None

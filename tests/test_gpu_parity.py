@@ -1,0 +1,268 @@
+"""Parity of the CUDA path (through the C ABI) with the oracles.  Needs a B200: -m gpu."""
+
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import coracle, pyoracle as po  # noqa: E402  (checker only)
+
+REL_TOL = 1e-6  # north_star: floating folds within 1e-6 relative
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from bytewax_b200 import gpu
+
+    c = gpu.Context(0)
+    yield c
+    c.close()
+
+
+def _is_float(case):
+    return any(isinstance(v, float) for b in case["batches"] for v in b[2])
+
+
+def _make_fold(ctx, s, is_float, **kw):
+    from bytewax_b200 import gpu
+
+    return gpu.WindowFold(
+        ctx, s["reduction"], s["length_us"], s["offset_us"], s["align_us"], s["wait_us"],
+        val_dtype="f64" if is_float else "i64", ordered=s["ordered"],
+        capacity_hint=kw.pop("capacity_hint", 4096), max_batch_rows=kw.pop("max_batch_rows", 1 << 16),
+        max_emit_rows=kw.pop("max_emit_rows", 1 << 18), max_late_rows=kw.pop("max_late_rows", 1 << 18), **kw)
+
+
+def _cmp_vals(red, got, want, is_float, where):
+    if red == "mean":
+        assert got[1] == want[1], where
+        assert got[0] == pytest.approx(want[0], rel=REL_TOL, abs=1e-9), where
+    elif is_float and red == "sum":
+        assert got == pytest.approx(want, rel=REL_TOL, abs=1e-9), where
+    else:
+        assert got == want, where
+
+
+def _check_activation(fold, em, act, spec, is_float, where):
+    red = spec["reduction"]
+    want_e = [(k, w, p) for k, w, t, p in act if t == "E"]
+    want_l = [(k, w, p) for k, w, t, p in act if t == "L"]
+    want_m = [(k, w, p) for k, w, t, p in act if t == "M"]
+    got_e = em.down(mean=(red == "mean"))
+    assert [(k, w) for k, (w, _) in got_e] == [(k, w) for k, w, _ in want_e], where
+    for (k, (w, a)), (_, _, p) in zip(got_e, want_e):
+        _cmp_vals(red, a, p, is_float, (where, k, w))
+    assert [(k, w, v) for k, (w, v) in em.late()] == want_l, where
+    # meta stream == window bounds of the closed rows, same order (windowing.py:1087-1093)
+    assert [[k, w, list(fold.window_bounds(w))] for k, (w, _) in got_e] == [[k, w, p] for k, w, p in want_m], where
+
+
+def test_golden_cases_per_activation(ctx, golden_dir):
+    with open(os.path.join(golden_dir, "window_fold_cases.json")) as f:
+        cases = json.load(f)
+    for name, case in cases.items():
+        s = case["spec"]
+        is_float = _is_float(case)
+        fold = _make_fold(ctx, s, is_float)
+        for i, (keys, ts, vals) in enumerate(case["batches"]):
+            fold.ingest(keys, vals, ts)
+            _check_activation(fold, fold.advance(), case["acts"][i], s, is_float, (name, i))
+        _check_activation(fold, fold.eof(), case["acts"][-1], s, is_float, (name, "eof"))
+        fold.close()
+
+
+def test_golden_cases_single_advance(ctx, golden_dir):
+    """All activations committed back to back, rows collected once: same rows, grouped by epoch."""
+    with open(os.path.join(golden_dir, "window_fold_cases.json")) as f:
+        cases = json.load(f)
+    for name in ("tumbling_count_lates", "sliding_sum_lates", "c1_shape_small", "discard_resets_watermark",
+                 "ordered_count_wait", "sliding_count_indivisible_negative"):
+        case = cases[name]
+        s = case["spec"]
+        fold = _make_fold(ctx, s, _is_float(case))
+        for keys, ts, vals in case["batches"]:
+            fold.ingest(keys, vals, ts)
+        em = fold.advance()
+        want = [(i + 1, k, w) for i, act in enumerate(case["acts"][:-1]) for k, w, t, _ in act if t == "E"]
+        assert list(zip(em.closed_epoch.tolist(), em.closed_key.tolist(), em.closed_window_id.tolist())) == want, name
+        _check_activation(fold, fold.eof(), case["acts"][-1], s, _is_float(case), (name, "eof"))
+        fold.close()
+
+
+def _random_batches(seed, nb, n, n_keys, span_us, jitter_us, start):
+    rnd = np.random.default_rng(seed)
+    out = []
+    for b in range(nb):
+        base = start + b * span_us + (np.arange(n) * span_us) // n
+        ts = base + rnd.integers(-jitter_us, jitter_us + 1, n) if jitter_us else base
+        out.append((rnd.integers(0, n_keys, n).astype(np.uint64), ts.astype(np.int64), rnd.integers(-1000, 1000, n)))
+    return out
+
+
+@pytest.mark.parametrize("red,length,offset,wait,jitter,ordered", [
+    ("count", 10, None, 0, 0, False),      # in order: fast path only
+    ("count", 10, None, 3, 2, False),      # disorder inside the wait: fast path
+    ("count", 10, None, 0, 6, False),      # late items: exact path
+    ("sum", 10, 5, 1, 4, False),           # sliding + late
+    ("max", 7, None, 2, 5, False),
+    ("min", 60, 10, 0, 3, False),          # 6 windows per item
+    ("count", 10, 3, 2, 2, True),          # ordered, indivisible offset
+    ("sum", 10, None, None, 30, False),    # wait forever: everything closes at EOF
+])
+def test_against_c_oracle_medium(ctx, red, length, offset, wait, jitter, ordered):
+    S = 1_000_000
+    spec = dict(reduction=red, length_us=length * S, offset_us=offset * S if offset else None,
+                align_us=1_640_995_200_000_000, wait_us=None if wait is None else wait * S, ordered=ordered)
+    batches = _random_batches(hash((red, length, jitter)) & 0xFFFF, 6, 50_000, 3000, 20 * S, jitter * S, spec["align_us"] - 5 * S)
+    orc = coracle.COracle(red, spec["length_us"], spec["offset_us"], spec["align_us"],
+                          (1 << 62) if wait is None else wait * S, ordered)
+    fold = _make_fold(ctx, spec, False, capacity_hint=8192, max_batch_rows=1 << 16, max_emit_rows=1 << 20, max_late_rows=1 << 21)
+    for keys, ts, vals in batches:
+        orc.on_batch(keys, ts, vals)
+        fold.ingest(keys, vals, ts)
+    orc.on_eof()
+    em, em_eof = fold.advance(), fold.eof()
+    ck, cw, ca, cc, cact = orc.closed()
+    lk, lw, lv, lts, lact = orc.late()
+    got = np.concatenate
+    assert got([em.closed_key, em_eof.closed_key]).tolist() == ck.tolist()
+    assert got([em.closed_window_id, em_eof.closed_window_id]).tolist() == cw.tolist()
+    assert got([em.closed_acc.astype(np.int64), em_eof.closed_acc.astype(np.int64)]).tolist() == ca.tolist()
+    assert em.closed_epoch.tolist() == (cact[: len(em.closed_epoch)] + 1).tolist()
+    assert em.late_key.tolist() == lk.tolist() and em.late_window_id.tolist() == lw.tolist()
+    assert em.late_val.astype(np.int64).tolist() == lv.tolist() and em.late_ts_us.tolist() == lts.tolist()
+    st = fold.stats()
+    if jitter > (wait if wait is not None else 10**9):
+        assert st.slow_batches > 0
+    fold.close()
+    orc.close()
+
+
+def test_float_sum_and_mean_tolerance(ctx):
+    S = 1_000_000
+    rnd = np.random.default_rng(5)
+    for red in ("sum", "mean", "min", "max"):
+        for dtype in ("f32", "f64"):
+            from bytewax_b200 import gpu
+
+            n = 40_000
+            keys = rnd.integers(0, 500, n).astype(np.uint64)
+            ts = (1_640_995_200_000_000 + np.arange(n) * 1000).astype(np.int64)
+            vals = rnd.random(n).astype(np.float32 if dtype == "f32" else np.float64)
+            fold = gpu.WindowFold(ctx, red, 10 * S, None, wait_us=0, val_dtype=dtype, capacity_hint=2048,
+                                  max_batch_rows=1 << 16, max_emit_rows=1 << 16)
+            orc = coracle.COracle(red, 10 * S, is_float=True)
+            for lo in range(0, n, 10_000):
+                sl = slice(lo, lo + 10_000)
+                fold.ingest(keys[sl], vals[sl], ts[sl])
+                orc.on_batch(keys[sl], ts[sl], vals[sl].astype(np.float64))
+            orc.on_eof()
+            em, em2 = fold.advance(), fold.eof()
+            ck, cw, ca, cc, _ = orc.closed()
+            gk = np.concatenate([em.closed_key, em2.closed_key])
+            ga = np.concatenate([em.closed_acc, em2.closed_acc])
+            gc = np.concatenate([em.closed_count, em2.closed_count])
+            assert gk.tolist() == ck.tolist()
+            if red in ("min", "max"):
+                assert ga.tolist() == ca.tolist()  # exact: no rounding in min/max
+            else:
+                np.testing.assert_allclose(ga, ca, rtol=REL_TOL)
+            if red == "mean":
+                assert gc.tolist() == cc.tolist()
+            fold.close()
+            orc.close()
+
+
+def test_edge_cases(ctx):
+    from bytewax_b200 import gpu
+
+    S = 1_000_000
+    A = 1_640_995_200_000_000
+    fold = gpu.WindowFold(ctx, "count", 10 * S, None, A, 0, capacity_hint=64, max_batch_rows=1024)
+    # empty activation
+    fold.ingest(np.zeros(0, np.uint64), None, np.zeros(0, np.int64))
+    assert fold.advance().closed_key.size == 0
+    # key == 2^64-1 (the table's empty sentinel), key 0, 20-digit keys, negative windows
+    keys = np.array([2**64 - 1, 0, 2**64 - 1, 10**19, 10**19 + 5, 9, 10, 100, 99], dtype=np.uint64)
+    ts = np.array([A - 25 * S] * 9, dtype=np.int64)
+    fold.ingest(keys, None, ts)
+    em = fold.eof()
+    want = sorted(set(keys.tolist()), key=str)
+    assert em.closed_key.tolist() == want
+    assert em.closed_window_id.tolist() == [-3] * len(want)
+    assert dict(zip(em.closed_key.tolist(), em.closed_acc.tolist()))[2**64 - 1] == 2
+    fold.close()
+    # one key, many windows inside one activation; first-opened order != id order
+    fold = gpu.WindowFold(ctx, "count", 10 * S, None, A, 50 * S, capacity_hint=64, max_batch_rows=1024)
+    ts = np.array([A + 31 * S, A + 5 * S, A + 12 * S, A + 33 * S, A + 95 * S], dtype=np.int64)
+    fold.ingest(np.full(5, 7, np.uint64), None, ts)
+    em = fold.advance()
+    assert em.closed_window_id.tolist() == [3, 0, 1]  # closed by wm = 45 s, in first-opened order
+    assert em.closed_acc.tolist() == [2, 1, 1]
+    assert fold.eof().closed_window_id.tolist() == [9]
+    fold.close()
+
+
+def test_errors_are_loud(ctx):
+    from bytewax_b200 import _native as N, gpu
+
+    with pytest.raises(N.BwError) as e:
+        gpu.WindowFold(ctx, "count", 10, 20)  # offset > length
+    assert e.value.status == 4
+    fold = gpu.WindowFold(ctx, "count", 10_000_000, capacity_hint=16, max_batch_rows=1 << 16, max_emit_rows=8)
+    keys = np.arange(60_000, dtype=np.uint64)
+    fold.ingest(keys, None, np.full(60_000, 1_640_995_200_000_000, np.int64))
+    with pytest.raises(N.BwError) as e:
+        fold.advance()
+    assert e.value.status == 3  # table full
+    fold.close()
+
+
+def test_c1_properties_and_sampled_parity(ctx):
+    """Config C1 at 2^24 rows x 4 batches: exact multiset vs the C oracle at 2M rows,
+    then size-independent checks on the rest (sum of counts == N, per-window totals)."""
+    from bytewax_b200 import gpu
+
+    A = 1_640_995_200_000_000
+    n_keys, B, nb = 100_000, 1 << 22, 6
+    L = 5_000_000  # 5 s windows -> a window closes every ~1.2 batches
+    fold = gpu.WindowFold(ctx, "count", L, None, A, 0, val_dtype="u64", ts_from_value=True, capacity_hint=n_keys,
+                          max_batch_rows=B, max_emit_rows=1 << 23)
+    dk, dv = ctx.dev_alloc(B * 8), ctx.dev_alloc(B * 8)
+    orc = coracle.COracle("count", L, align_us=A)
+    hk, hv = np.empty(B, np.uint64), np.empty(B, np.uint64)
+    rows_got = []
+    for b in range(nb):
+        fold.gen_c1(dk, dv, b * B, B, n_keys)
+        fold.ingest_device(dk, dv, None, B)
+        if b < 1:
+            fold.sync()
+            ctx.d2h(hk, dk)
+            ctx.d2h(hv, dv)
+            k2, t2, v2 = coracle.gen_c1(b * B, B, n_keys, A)
+            assert hk.tolist() == k2.tolist() and hv.tolist() == v2.tolist()
+            orc.on_batch(k2, t2)
+        em = fold.advance()
+        rows_got.append(em)
+        if b < 1:
+            ck, cw, ca, _, _ = orc.closed()
+            assert em.closed_key.tolist() == ck.tolist() and em.closed_window_id.tolist() == cw.tolist()
+            assert em.closed_acc.tolist() == ca.tolist()
+    rows_got.append(fold.eof())
+    total = sum(int(e.closed_acc.sum()) for e in rows_got)
+    assert total == nb * B
+    wid = np.concatenate([e.closed_window_id for e in rows_got])
+    acc = np.concatenate([e.closed_acc for e in rows_got])
+    per_window = np.bincount(wid, weights=acc).astype(np.int64)
+    nfull = (nb * B) // L
+    assert (per_window[:nfull] == L).all() and per_window.sum() == nb * B
+    st = fold.stats()
+    assert st.slow_batches == 0 and st.fold_launches == nb
+    ctx.dev_free(dk)
+    ctx.dev_free(dv)
+    fold.close()
+    orc.close()
