@@ -12,7 +12,6 @@
 #include "bw_common.cuh"
 #include "bw_fold.cuh"
 
-#define BW_TOMB_WID (INT64_MIN + 1)
 
 __device__ __forceinline__ u64 bw_warp_reserve(unsigned long long* ctr, u32 n) {
   // opportunistic warp aggregation: one atomic per converged group
@@ -68,200 +67,175 @@ __device__ __forceinline__ u64 bw_finish_acc(const FoldParams& p, u64 acc) {
   return acc;
 }
 
-struct PaneRef {
+#define BW_MAX_PANES 64  // live panes per key that K4 can re-rank (beyond: BW_ERR_CAPACITY)
+
+struct PaneRec {
   i64 q;
   u64 acc, cnt, seq;
-  u32 node;  // 0 == the inline pane
-  bool valid;
+  u32 born;  // 6-bit creation tag, or BW_TAG_STALE
+  bool dead;
 };
 
-__device__ __forceinline__ PaneRef bw_pane_inline(const Table& t, u64 s) {
-  PaneRef r;
-  i64 tag = t.hot[s].widtag;
-  r.valid = (tag != BW_EMPTY_WIDTAG);
-  r.q = bw_widtag_q(tag);
-  r.acc = t.hot[s].acc;
-  r.cnt = t.cold[s].acc2;
-  r.seq = t.cold[s].open_seq;
-  r.node = 0;
-  return r;
-}
-__device__ __forceinline__ PaneRef bw_pane_node(const Table& t, u32 n) {
-  PaneRef r;
-  r.valid = true;
-  r.q = t.nodes[n].wid;
-  r.acc = t.nodes[n].acc;
-  r.cnt = t.node_acc2[n];
-  r.seq = t.nodes[n].open_seq;
-  r.node = n;
-  return r;
-}
-
-// Close everything the key's watermark allows; keep the newest pane inline.
+// Close everything the key's watermark allows, then put the newest pane in
+// the hot slot, the second newest in the cold slot and the rest on the list.
 __device__ void bw_close_key(const Table& t, const FoldParams& p, const EmitBufs& e, u64 s, bool eof, u64 epoch) {
   HotSlot* hs = t.hot + s;
   ColdSlot* cs = t.cold + s;
-  i64 tag = hs->widtag;
-  if (tag == BW_EMPTY_WIDTAG) return;
+  AuxSlot* ax = t.aux + s;
+  if (hs->wt0 == BW_EMPTY_WIDTAG) return;
   const u64 key = hs->key;
-  const i64 mts = hs->max_ts;
   i64 wm;
   if (eof) {
     wm = INT64_MAX;
   } else if (!p.track_wm) {
     wm = INT64_MIN;
   } else {
-    wm = bw_sub_sat(mts, p.wait_us);
+    wm = bw_sub_sat(hs->max_ts, p.wait_us);
     if (wm < BW_UTC_MIN_US_DEV) wm = BW_UTC_MIN_US_DEV;
+  }
+  // gather
+  PaneRec P[BW_MAX_PANES];
+  u32 nodes[BW_MAX_PANES];
+  int n = 0, nn = 0;
+  P[n++] = PaneRec{bw_widtag_q(hs->wt0), hs->acc0, ax->cnt0, cs->seq0, (u32)hs->wt0 & 0x7Fu, false};
+  if (cs->wt1 != BW_EMPTY_WIDTAG)
+    P[n++] = PaneRec{bw_widtag_q(cs->wt1), cs->acc1, ax->cnt1, cs->seq1, (u32)cs->wt1 & 0x7Fu, false};
+  for (u32 nd = ax->spill_head; nd; nd = t.nodes[nd].next) {
+    if (n >= BW_MAX_PANES) {
+      bw_raise(t.ctr, 3u);
+      return;
+    }
+    nodes[nn++] = nd;
+    P[n++] = PaneRec{t.nodes[nd].wid, t.nodes[nd].acc, t.node_acc2[nd], t.nodes[nd].open_seq, BW_TAG_STALE, false};
   }
   const i64 a = p.panes_per_offset, b = p.panes_per_window;
   const bool ordered_seq = p.ordered != 0;
-  bool inline_alive = true;
-
   if (a == 1 && b == 1) {
     // tumbling: window id == pane id; a closed pane is emitted and dropped
-    PaneRef in = bw_pane_inline(t, s);
-    if (wm >= bw_pane_release(in.q, p)) {
-      bw_emit_closed(e, t.ctr, key, in.q, bw_finish_acc(p, in.acc), in.cnt,
-                     ordered_seq ? (u64)(in.q + (1LL << 62)) : in.seq, epoch);
-      inline_alive = false;
-    }
-    for (u32 n = cs->spill_head; n; n = t.nodes[n].next) {
-      PaneRef r = bw_pane_node(t, n);
-      if (wm >= bw_pane_release(r.q, p)) {
-        bw_emit_closed(e, t.ctr, key, r.q, bw_finish_acc(p, r.acc), r.cnt,
-                       ordered_seq ? (u64)(r.q + (1LL << 62)) : r.seq, epoch);
-        t.nodes[n].wid = BW_TOMB_WID;
+    for (int i = 0; i < n; ++i)
+      if (wm >= bw_pane_release(P[i].q, p)) {
+        bw_emit_closed(e, t.ctr, key, P[i].q, bw_finish_acc(p, P[i].acc), P[i].cnt,
+                       ordered_seq ? (u64)(P[i].q + (1LL << 62)) : P[i].seq, epoch);
+        P[i].dead = true;
       }
-    }
   } else {
-    // sliding: window w = panes [w*a, w*a + b); emit each newly closable
-    // window once, from its smallest live pane; then drop dead panes.
-    i64 c_new;  // largest closable window id
-    if (eof) {
-      c_new = INT64_MAX;
-    } else if (wm == INT64_MIN) {
-      c_new = INT64_MIN;
-    } else {
-      c_new = bw_floordiv(wm - p.align_us - p.length_us, p.offset_us);
-    }
-    const i64 c_prev = cs->closed_upto;  // windows <= c_prev were already emitted
+    // sliding: window w = panes [w*a, w*a + b); emit each newly closable window
+    // once (from its smallest live pane), then drop panes whose last window closed
+    i64 c_new;
+    if (eof) c_new = INT64_MAX;
+    else if (wm == INT64_MIN) c_new = INT64_MIN;
+    else c_new = bw_floordiv(wm - p.align_us - p.length_us, p.offset_us);
+    const i64 c_prev = ax->closed_upto;
     if (c_new > c_prev) {
-      // outer walk over panes P
-      PaneRef P = bw_pane_inline(t, s);
-      u32 next = cs->spill_head;
-      while (true) {
-        if (P.valid) {
-          i64 w_lo = bw_floordiv(P.q - b + a, a);  // ceil((q - b + 1)/a)
-          i64 w_hi = bw_floordiv(P.q, a);
-          if (w_lo <= c_prev) w_lo = c_prev + 1;
-          if (w_hi > c_new) w_hi = c_new;
-          for (i64 w = w_lo; w <= w_hi; ++w) {
-            const i64 q0 = w * a, q1 = w * a + b;  // pane range [q0, q1)
-            // is P the smallest live pane of w?  combine all panes of w on the way
-            bool smallest = true;
-            u64 acc = p.acc_identity, cnt = 0, seq = ~0ULL;
-            PaneRef R = bw_pane_inline(t, s);
-            u32 rn = cs->spill_head;
-            while (true) {
-              if (R.valid && R.q >= q0 && R.q < q1) {
-                if (R.q < P.q) {
-                  smallest = false;
-                  break;
-                }
-                acc = bw_combine(p.op, acc, R.acc);
-                cnt += R.cnt;
-                seq = R.seq < seq ? R.seq : seq;
-              }
-              if (!rn) break;
-              R = bw_pane_node(t, rn);
-              rn = t.nodes[rn].next;
+      for (int i = 0; i < n; ++i) {
+        i64 w_lo = bw_floordiv(P[i].q - b + a, a);  // ceil((q - b + 1) / a)
+        i64 w_hi = bw_floordiv(P[i].q, a);
+        if (w_lo <= c_prev) w_lo = c_prev + 1;
+        if (w_hi > c_new) w_hi = c_new;
+        for (i64 w = w_lo; w <= w_hi; ++w) {
+          const i64 q0 = w * a, q1 = w * a + b;
+          bool smallest = true;
+          u64 acc = p.acc_identity, cnt = 0, seq = ~0ULL;
+          for (int j = 0; j < n; ++j) {
+            if (P[j].q < q0 || P[j].q >= q1) continue;
+            if (P[j].q < P[i].q) {
+              smallest = false;
+              break;
             }
-            if (smallest)
-              bw_emit_closed(e, t.ctr, key, w, bw_finish_acc(p, acc), cnt,
-                             ordered_seq ? (u64)(w + (1LL << 62)) : seq, epoch);
+            acc = bw_combine(p.op, acc, P[j].acc);
+            cnt += P[j].cnt;
+            seq = P[j].seq < seq ? P[j].seq : seq;
           }
+          if (smallest)
+            bw_emit_closed(e, t.ctr, key, w, bw_finish_acc(p, acc), cnt, ordered_seq ? (u64)(w + (1LL << 62)) : seq,
+                           epoch);
         }
-        if (!next) break;
-        P = bw_pane_node(t, next);
-        next = t.nodes[next].next;
       }
-      cs->closed_upto = c_new;
+      ax->closed_upto = c_new;
     }
-    // drop panes whose last window is closed
-    PaneRef in = bw_pane_inline(t, s);
-    if (wm >= bw_pane_release(in.q, p)) inline_alive = false;
-    for (u32 n = cs->spill_head; n; n = t.nodes[n].next)
-      if (wm >= bw_pane_release(t.nodes[n].wid, p)) t.nodes[n].wid = BW_TOMB_WID;
+    for (int i = 0; i < n; ++i)
+      if (wm >= bw_pane_release(P[i].q, p)) P[i].dead = true;
   }
-
-  // rebuild: unlink dead nodes, find newest / oldest survivors
-  u32 best = 0;
-  i64 best_q = INT64_MIN, min_q = INT64_MAX;
-  u32 prev = 0;
-  for (u32 n = cs->spill_head; n;) {
-    u32 nx = t.nodes[n].next;
-    if (t.nodes[n].wid == BW_TOMB_WID) {
-      if (prev) t.nodes[prev].next = nx; else cs->spill_head = nx;
-      int top = atomicAdd(&t.ctr->free_top, 1);
-      t.free_stack[top] = n;
-    } else {
-      i64 q = t.nodes[n].wid;
-      if (q > best_q) { best_q = q; best = n; }
-      if (q < min_q) min_q = q;
-      prev = n;
+  // survivors, newest first (insertion sort of indices)
+  int idx[BW_MAX_PANES];
+  int m = 0;
+  for (int i = 0; i < n; ++i) {
+    if (P[i].dead) continue;
+    int j = m++;
+    while (j > 0 && P[idx[j - 1]].q < P[i].q) {
+      idx[j] = idx[j - 1];
+      --j;
     }
-    n = nx;
+    idx[j] = i;
   }
-  i64 in_q = bw_widtag_q(tag);
-  if (!inline_alive && !best) {
+  if (m == 0) {
     // no panes left: the reference discards the whole logic, watermark included
+    // (windowing.py:1110-1113 -> src/operators.rs:796-799)
     hs->max_ts = INT64_MIN;
-    hs->widtag = BW_EMPTY_WIDTAG;
-    hs->acc = p.acc_identity;
-    cs->open_seq = ~0ULL;
-    cs->acc2 = 0;
-    cs->closed_upto = INT64_MIN;
-    return;
+    hs->wt0 = BW_EMPTY_WIDTAG;
+    hs->acc0 = p.acc_identity;
+    ax->closed_upto = INT64_MIN;
+  } else {
+    const PaneRec& r0 = P[idx[0]];
+    const u64 delta = (u64)(r0.q - P[idx[m - 1]].q);
+    // K4 runs after the batch that created a pane, so its open_seq is final: mark stale
+    hs->wt0 = bw_pack_widtag(r0.q, delta > 255 ? 255u : (u32)delta, BW_TAG_STALE);
+    hs->acc0 = r0.acc;
+    ax->cnt0 = r0.cnt;
+    cs->seq0 = r0.seq;
   }
-  if (!inline_alive || best_q > in_q) {
-    // move the newest node into the inline position (swap when inline is alive)
-    PaneNode nd = t.nodes[best];
-    u64 nd_cnt = t.node_acc2[best];
-    if (inline_alive) {
-      t.nodes[best].wid = in_q;
-      t.nodes[best].acc = hs->acc;
-      t.nodes[best].open_seq = cs->open_seq;
-      t.nodes[best].born = 0xFFFFFFFFu;  // never "fresh" again
-      t.node_acc2[best] = cs->acc2;
-      if (in_q < min_q) min_q = in_q;
+  if (m >= 2) {
+    const PaneRec& r1 = P[idx[1]];
+    cs->wt1 = bw_pack_widtag(r1.q, 0, BW_TAG_STALE);
+    cs->acc1 = r1.acc;
+    ax->cnt1 = r1.cnt;
+    cs->seq1 = r1.seq;
+  } else {
+    cs->wt1 = BW_EMPTY_WIDTAG;
+    cs->acc1 = p.acc_identity;
+    ax->cnt1 = 0;
+    cs->seq1 = ~0ULL;
+  }
+  if (m == 0) {
+    ax->cnt0 = 0;
+    cs->seq0 = ~0ULL;
+  }
+  // the rest goes back on the list, reusing node storage
+  u32 head = 0;
+  int used = 0;
+  for (int r = m - 1; r >= 2; --r) {
+    u32 nd;
+    if (used < nn) {
+      nd = nodes[used++];
     } else {
-      // unlink `best`
-      u32 pv = 0;
-      for (u32 n = cs->spill_head; n; n = t.nodes[n].next) {
-        if (n == best) {
-          if (pv) t.nodes[pv].next = t.nodes[n].next; else cs->spill_head = t.nodes[n].next;
+      int top = atomicSub(&t.ctr->free_top, 1);
+      if (top > 0) {
+        nd = t.free_stack[top - 1];
+      } else {
+        atomicAdd(&t.ctr->free_top, 1);
+        nd = atomicAdd(&t.ctr->pool_next, 1u);
+        if (nd >= t.pool_cap) {
+          bw_raise(t.ctr, 3u);
           break;
         }
-        pv = n;
       }
-      int top = atomicAdd(&t.ctr->free_top, 1);
-      t.free_stack[top] = best;
-      // min over the remaining nodes
-      min_q = INT64_MAX;
-      for (u32 n = cs->spill_head; n; n = t.nodes[n].next)
-        if (t.nodes[n].wid < min_q) min_q = t.nodes[n].wid;
     }
-    hs->acc = nd.acc;
-    cs->open_seq = nd.open_seq;
-    cs->acc2 = nd_cnt;
-    in_q = nd.wid;
+    const PaneRec& rr = P[idx[r]];
+    PaneNode v;
+    v.wid = rr.q;
+    v.acc = rr.acc;
+    v.open_seq = rr.seq;
+    v.next = head;
+    v.born = 0xFFFFFFFFu;
+    t.nodes[nd] = v;
+    t.node_acc2[nd] = rr.cnt;
+    head = nd;
   }
-  if (min_q > in_q) min_q = in_q;
-  u64 delta = (u64)(in_q - min_q);
-  // The born tag only matters inside the batch that created the pane (arrival-order
-  // minimum of open_seq); K4 runs after that batch, so the survivor is marked stale.
-  hs->widtag = bw_pack_widtag(in_q, delta > 255 ? 255u : (u32)delta, BW_TAG_STALE);
+  ax->spill_head = head;
+  for (; used < nn; ++used) {
+    int top = atomicAdd(&t.ctr->free_top, 1);
+    t.free_stack[top] = nodes[used];
+  }
 }
 
 __global__ void k_close_dirty(Table t, FoldParams p, EmitBufs e, u64 epoch) {

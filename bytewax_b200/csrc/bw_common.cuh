@@ -32,22 +32,29 @@ __host__ __device__ __forceinline__ u32 bw_route_hash(u64 h, u32 world) {
 // State layout in HBM (DESIGN.md "Data layout").
 //
 // One 32-byte HOT slot per key == exactly one L2 sector: everything the
-// steady-state fold touches.  One 32-byte COLD slot per key for what only
-// pane creation / close needs.  Extra live panes of a key hang off the cold
-// slot as a short linked list of 32-byte nodes.
+// steady-state fold touches (key, running max ts, newest pane).  One 32-byte
+// COLD slot per key holds the second pane (the one a key is moving out of or
+// into inside an activation) plus both panes' open sequence numbers.  One
+// 32-byte AUX slot per key for counts (MEAN), sliding bookkeeping and the head
+// of a short linked list of 32-byte nodes for any further live panes.
 // ---------------------------------------------------------------------------
 struct __align__(32) HotSlot {
   u64 key;      // BW_EMPTY_KEY when free
   i64 max_ts;   // max event ts seen since the key was (re)created; INT64_MIN when none
-  i64 widtag;   // inline pane: (pane_id << 16) | older_delta << 8 | dirty << 7 | born & 63
-  u64 acc;      // inline pane accumulator (bits)
+  i64 wt0;      // pane 0 (newest after K4): (pane_id << 16) | older_delta << 8 | dirty << 7 | stale << 6 | born & 63
+  u64 acc0;     // pane 0 accumulator (bits)
 };
 struct __align__(32) ColdSlot {
-  u64 open_seq;    // arrival sequence (batch << 32 | index) that opened the inline pane
-  u64 acc2;        // inline pane value count (MEAN divisor / row count)
-  u32 spill_head;  // first extra pane node, 0 == none
-  u32 lock;        // structural lock for the node list
-  i64 closed_upto; // sliding windows: window ids <= this were already emitted for this key incarnation
+  i64 wt1;      // pane 1 (second newest after K4), same packing (delta / dirty unused)
+  u64 acc1;
+  u64 seq0;     // arrival sequence (batch << 32 | index) of the event that opened pane 0
+  u64 seq1;     // ... pane 1
+};
+struct __align__(32) AuxSlot {
+  u64 cnt0, cnt1;   // value counts of panes 0 / 1 (MEAN divisor)
+  u32 spill_head;   // further panes: linked list of PaneNode, 0 == none
+  u32 lock;         // structural lock for the node list
+  i64 closed_upto;  // sliding windows: window ids <= this were already emitted for this key incarnation
 };
 struct __align__(32) PaneNode {
   i64 wid;
@@ -114,6 +121,7 @@ struct FoldParams {
 struct Table {
   HotSlot* hot;
   ColdSlot* cold;
+  AuxSlot* aux;
   PaneNode* nodes;
   u64* node_acc2;
   u32* free_stack;
@@ -166,21 +174,27 @@ struct EmitBufs {
 // PTX helpers
 // ---------------------------------------------------------------------------
 // One 32-byte sector in one instruction (LDG.E.256), L2-coherent.
-__device__ __forceinline__ void bw_ld_slot(const HotSlot* p, u64& key, i64& max_ts, i64& widtag, u64& acc) {
+__device__ __forceinline__ void bw_ld_slot(const void* p, u64& a, i64& b, i64& c, u64& d) {
   asm volatile("ld.global.relaxed.gpu.v4.u64 {%0,%1,%2,%3}, [%4];"
-               : "=l"(key), "=l"(max_ts), "=l"(widtag), "=l"(acc)
+               : "=l"(a), "=l"(b), "=l"(c), "=l"(d)
                : "l"(p)
                : "memory");
 }
-// streaming 8-byte load that does not pollute L1
+// Streaming loads of the input columns: read once, so keep them out of L1 and
+// mark them first-to-evict in L2 -- the 126 MB L2 is reserved for the key table.
+__device__ __forceinline__ u64 bw_evict_first_policy() {
+  u64 pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
 __device__ __forceinline__ u64 bw_ld_stream_u64(const u64* p) {
   u64 v;
-  asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(bw_evict_first_policy()));
   return v;
 }
 __device__ __forceinline__ u32 bw_ld_stream_u32(const u32* p) {
   u32 v;
-  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(bw_evict_first_policy()));
   return v;
 }
 __device__ __forceinline__ void bw_red_add_u64(u64* p, u64 v) {
@@ -232,6 +246,14 @@ __host__ __device__ __forceinline__ i64 bw_floordiv(i64 a, i64 b) {
 // last window = floor(q / a); close = align + w*offset + length.
 __device__ __forceinline__ i64 bw_pane_release(i64 q, const FoldParams& p) {
   i64 w = (p.panes_per_offset == 1) ? q : bw_floordiv(q, p.panes_per_offset);
+  return p.align_us + w * p.offset_us + p.length_us;
+}
+// Earliest time any window covering pane q can close == close time of the first
+// window covering it: first window = ceil((q - b + 1) / a).
+__device__ __forceinline__ i64 bw_pane_first_close(i64 q, const FoldParams& p) {
+  i64 w = (p.panes_per_window == 1 && p.panes_per_offset == 1)
+              ? q
+              : bw_floordiv(q - p.panes_per_window + p.panes_per_offset, p.panes_per_offset);
   return p.align_us + w * p.offset_us + p.length_us;
 }
 // saturating ts - wait (the reference's OverflowError branch, windowing.py:281-285)

@@ -2,28 +2,39 @@
 //
 // Replaces the per-key `on_batch` loop of src/operators.rs:755-806 running
 // `_WindowLogic.on_batch` (pysrc/bytewax/operators/windowing.py:1115-1133) for
-// numeric folds.  One thread per event; one 32-byte sector read and one or two
-// fire-and-forget L2 reductions per event in the steady state.
+// numeric folds.  One thread per event.
+//
+// Steady state (key known, event falls in the key's newest pane): ONE 32-byte
+// sector read (LDG.256) and one or two fire-and-forget L2 reductions.  Every
+// other case (second probe, new key, second pane, further panes) is pushed to
+// a block-local queue and drained by full warps afterwards, so the rare,
+// latency-bound paths never hold the fast lanes of a warp hostage.
 #pragma once
 #include "bw_common.cuh"
 
-
 // Block-local staging of the rare global appends (dirty-key list, new-key
-// count): one global atomic per block per tile instead of one per event, so
-// the single list cursor in L2 never serialises the fold.
+// count) and of the deferred events.
 #define BW_SINK_CAP 1024
+#define BW_FOLD_THREADS 256
+#define BW_FOLD_UNROLL 4
+#define BW_FOLD_WARPS (BW_FOLD_THREADS / 32)
+#define BW_WARP_DEFER_CAP (32 * BW_FOLD_UNROLL)
 struct BlockSinks {
   u32 n_dirty;
   u32 n_new_keys;
   u32 dirty[BW_SINK_CAP];
+  // per-warp queues of deferred events (arrival index within the batch)
+  u32 n_defer[BW_FOLD_WARPS];
+  u32 dq_g[BW_FOLD_WARPS][BW_WARP_DEFER_CAP];
 };
 __device__ __forceinline__ void bw_sinks_init(BlockSinks* sk) {
   if (threadIdx.x == 0) {
     sk->n_dirty = 0;
     sk->n_new_keys = 0;
   }
+  if (threadIdx.x < BW_FOLD_WARPS) sk->n_defer[threadIdx.x] = 0;
 }
-// call by all threads of the block, between __syncthreads()
+// call by all threads of the block, after a __syncthreads()
 __device__ __forceinline__ void bw_sinks_flush(BlockSinks* sk, const Table& t) {
   __shared__ u32 base;
   u32 n = sk->n_dirty < BW_SINK_CAP ? sk->n_dirty : BW_SINK_CAP;
@@ -52,35 +63,59 @@ __device__ __forceinline__ i64 bw_ld_i64_coherent(const i64* p) {
   return v;
 }
 
-// Find (or create) the slot of `key`.  Returns the slot index, or ~0 on a full table.
-__device__ __forceinline__ u64 bw_find_slot(const Table& t, BlockSinks* sk, u64 key, u64 h, i64& max_ts,
-                                            i64& widtag) {
-  u64 s = (key == BW_EMPTY_KEY) ? (t.mask + 1) : (h & t.mask);
-  for (u64 probe = 0; probe <= t.mask; ++probe) {
-    HotSlot* hs = t.hot + s;
-    u64 k, acc_unused;
-    bw_ld_slot(hs, k, max_ts, widtag, acc_unused);
-    if (k == key) return s;
-    if (k == BW_EMPTY_KEY) {
-      u64 old = atomicCAS((unsigned long long*)&hs->key, (unsigned long long)BW_EMPTY_KEY, (unsigned long long)key);
-      if (old == BW_EMPTY_KEY) {
-        // a free slot is always in the reset state; nobody else touches it before the key is set
-        atomicAdd(&sk->n_new_keys, 1u);
-        return s;
+__device__ __forceinline__ u64 bw_home_slot(const Table& t, u64 key) {
+  return (key == BW_EMPTY_KEY) ? (t.mask + 1) : (bw_mix64(key) & t.mask);
+}
+
+// Find (or create) the slot of `key`, starting at its home slot.  Four
+// consecutive slots are fetched per round trip (independent LDG.256s), so a
+// linear-probe chain costs ceil(len / 4) L2 latencies.  Returns ~0 on a full table.
+#define BW_PROBE_WIDTH 4
+__device__ __forceinline__ u64 bw_find_slot(const Table& t, BlockSinks* sk, u64 key, i64& max_ts, i64& wt0) {
+  u64 s = bw_home_slot(t, key);
+  if (key == BW_EMPTY_KEY) {  // alias slot: always "found"
+    u64 k, a;
+    bw_ld_slot(t.hot + s, k, max_ts, wt0, a);
+    return s;
+  }
+  for (u64 probe = 0; probe <= t.mask; probe += BW_PROBE_WIDTH) {
+    u64 k[BW_PROBE_WIDTH], a[BW_PROBE_WIDTH];
+    i64 m[BW_PROBE_WIDTH], w[BW_PROBE_WIDTH];
+#pragma unroll
+    for (int j = 0; j < BW_PROBE_WIDTH; ++j) bw_ld_slot(t.hot + ((s + j) & t.mask), k[j], m[j], w[j], a[j]);
+#pragma unroll
+    for (int j = 0; j < BW_PROBE_WIDTH; ++j) {
+      const u64 sj = (s + j) & t.mask;
+      if (k[j] == key) {
+        max_ts = m[j];
+        wt0 = w[j];
+        return sj;
       }
-      if (old == key) {
-        bw_ld_slot(hs, k, max_ts, widtag, acc_unused);
-        return s;
+      if (k[j] == BW_EMPTY_KEY) {
+        HotSlot* hs = t.hot + sj;
+        u64 old = atomicCAS((unsigned long long*)&hs->key, (unsigned long long)BW_EMPTY_KEY, (unsigned long long)key);
+        if (old == BW_EMPTY_KEY) {
+          // a free slot is always in the reset state; nobody else touches it before the key is set
+          atomicAdd(&sk->n_new_keys, 1u);
+          max_ts = m[j];
+          wt0 = w[j];
+          return sj;
+        }
+        if (old == key) {
+          u64 kk, aa;
+          bw_ld_slot(hs, kk, max_ts, wt0, aa);
+          return sj;
+        }
+        // another key took it: keep probing past it
       }
     }
-    s = (s + 1) & t.mask;
+    s = (s + BW_PROBE_WIDTH) & t.mask;
   }
   return ~0ULL;
 }
 
 __device__ __forceinline__ void bw_mark_dirty(const Table& t, BlockSinks* sk, u64 s) {
-  unsigned long long old =
-      atomicOr((unsigned long long*)&t.hot[s].widtag, (unsigned long long)BW_TAG_DIRTY);
+  unsigned long long old = atomicOr((unsigned long long*)&t.hot[s].wt0, (unsigned long long)BW_TAG_DIRTY);
   if (!(old & (unsigned long long)BW_TAG_DIRTY)) {
     u32 i = atomicAdd(&sk->n_dirty, 1u);
     if (i < BW_SINK_CAP) {
@@ -92,12 +127,12 @@ __device__ __forceinline__ void bw_mark_dirty(const Table& t, BlockSinks* sk, u6
   }
 }
 
-// Find or create the extra pane node (key slot s, pane q).  Returns node index or 0 on failure.
+// Find or create the overflow pane node (key slot s, pane q).  Returns node index or 0 on failure.
 __device__ __noinline__ u32 bw_spill_node(const Table& t, const FoldParams& p, u64 s, i64 q, u32 batch_no,
                                          bool& created) {
-  ColdSlot* cs = t.cold + s;
+  AuxSlot* ax = t.aux + s;
   created = false;
-  u32 n = bw_ld_u32_coherent(&cs->spill_head);
+  u32 n = bw_ld_u32_coherent(&ax->spill_head);
   while (n) {
     if (bw_ld_i64_coherent(&t.nodes[n].wid) == q) return n;
     n = bw_ld_u32_coherent(&t.nodes[n].next);
@@ -105,9 +140,9 @@ __device__ __noinline__ u32 bw_spill_node(const Table& t, const FoldParams& p, u
   u32 result = 0;
   bool done = false;
   while (!done) {
-    if (atomicCAS(&cs->lock, 0u, 1u) == 0u) {
+    if (atomicCAS(&ax->lock, 0u, 1u) == 0u) {
       __threadfence();
-      u32 head = bw_ld_u32_coherent(&cs->spill_head);
+      u32 head = bw_ld_u32_coherent(&ax->spill_head);
       n = head;
       while (n) {
         if (bw_ld_i64_coherent(&t.nodes[n].wid) == q) break;
@@ -135,66 +170,105 @@ __device__ __noinline__ u32 bw_spill_node(const Table& t, const FoldParams& p, u
           t.nodes[n] = nd;
           t.node_acc2[n] = 0;
           __threadfence();
-          atomicExch(&cs->spill_head, n);
+          atomicExch(&ax->spill_head, n);
           created = true;
         }
       }
       result = n;
       __threadfence();
-      atomicExch(&cs->lock, 0u);
+      atomicExch(&ax->lock, 0u);
       done = true;
     }
   }
   return result;
 }
 
-// Fold one non-late event.  `seq` = (batch_no << 32) | arrival index.
-__device__ __forceinline__ void bw_fold_event(const Table& t, const FoldParams& p, BlockSinks* sk, u64 key, i64 ts,
-                                              u64 operand, u64 seq, u32 batch_no) {
+// Watermark tracking + "this key may have something to close / re-rank" marking.
+__device__ __forceinline__ void bw_after_fold(const Table& t, const FoldParams& p, BlockSinks* sk, u64 s, i64 ts,
+                                              i64 mts, i64 tag0, bool created) {
+  HotSlot* hs = t.hot + s;
+  if (p.track_wm) {
+    if (ts > mts) bw_red_max_s64(&hs->max_ts, ts);
+    if (!(tag0 & BW_TAG_DIRTY)) {
+      bool mark = created;
+      if (!mark) {
+        u32 delta = bw_widtag_delta(tag0);
+        mark = (delta == 255u) || (bw_sub_sat(ts, p.wait_us) >= bw_pane_first_close(bw_widtag_q(tag0) - (i64)delta, p));
+      }
+      if (mark) bw_mark_dirty(t, sk, s);
+    }
+  } else if (created && !(tag0 & BW_TAG_DIRTY)) {
+    bw_mark_dirty(t, sk, s);  // keep the newest panes in the direct slots for the next batch
+  }
+}
+
+// General path: any event (new key, displaced key, second / further pane).
+// `seq` = (batch_no << 32) | arrival index.
+__device__ __noinline__ void bw_fold_event(const Table& t, const FoldParams& p, BlockSinks* sk, u64 key, i64 ts,
+                                           u64 operand, u64 seq, u32 batch_no) {
   i64 q = bw_pane_of(ts, p);
   if (q <= -BW_WID_LIMIT || q >= BW_WID_LIMIT) {
     bw_raise(t.ctr, 6u /*BW_ERR_RANGE*/);
     return;
   }
-  i64 mts, tag;
-  u64 s = bw_find_slot(t, sk, key, bw_mix64(key), mts, tag);
+  i64 mts, tag0;
+  u64 s = bw_find_slot(t, sk, key, mts, tag0);
   if (s == ~0ULL) {
     bw_raise(t.ctr, 3u);
     return;
   }
   HotSlot* hs = t.hot + s;
-  if (tag == BW_EMPTY_WIDTAG) {
-    i64 mine = bw_pack_widtag(q, 0, batch_no & 63u);
-    i64 old = (i64)atomicCAS((unsigned long long*)&hs->widtag, (unsigned long long)BW_EMPTY_WIDTAG,
-                             (unsigned long long)mine);
-    tag = (old == BW_EMPTY_WIDTAG) ? mine : old;
+  ColdSlot* cs = t.cold + s;
+  const u32 born = batch_no & 63u;
+  if (tag0 == BW_EMPTY_WIDTAG) {
+    i64 mine = bw_pack_widtag(q, 0, born);
+    i64 old = (i64)atomicCAS((unsigned long long*)&hs->wt0, (unsigned long long)BW_EMPTY_WIDTAG, (unsigned long long)mine);
+    tag0 = (old == BW_EMPTY_WIDTAG) ? mine : old;
   }
   bool created = false;
-  if (bw_widtag_q(tag) == q) {
-    bw_apply(p.op, &hs->acc, operand);
-    if (p.need_count) bw_red_add_u64(&t.cold[s].acc2, 1ULL);
-    if (((u32)tag & 0x7Fu) == (batch_no & 63u)) bw_red_min_u64(&t.cold[s].open_seq, seq);
+  if (bw_widtag_q(tag0) == q) {
+    bw_apply(p.op, &hs->acc0, operand);
+    if (p.need_count) bw_red_add_u64(&t.aux[s].cnt0, 1ULL);
+    if (((u32)tag0 & 0x7Fu) == born) bw_red_min_u64(&cs->seq0, seq);
   } else {
-    u32 n = bw_spill_node(t, p, s, q, batch_no, created);
-    if (!n) return;
-    bw_apply(p.op, &t.nodes[n].acc, operand);
-    if (p.need_count) bw_red_add_u64(&t.node_acc2[n], 1ULL);
-    if (t.nodes[n].born == batch_no) bw_red_min_u64(&t.nodes[n].open_seq, seq);
-  }
-  if (p.track_wm) {
-    if (ts > mts) bw_red_max_s64(&hs->max_ts, ts);
-    if (!(tag & BW_TAG_DIRTY)) {
-      bool mark = created;
-      if (!mark) {
-        u32 delta = bw_widtag_delta(tag);
-        mark = (delta == 255u) ||
-               (bw_sub_sat(ts, p.wait_us) >= bw_pane_release(bw_widtag_q(tag) - (i64)delta, p));
+    i64 tag1 = bw_ld_i64_coherent(&cs->wt1);
+    if (tag1 == BW_EMPTY_WIDTAG) {
+      i64 mine = bw_pack_widtag(q, 0, born);
+      i64 old = (i64)atomicCAS((unsigned long long*)&cs->wt1, (unsigned long long)BW_EMPTY_WIDTAG, (unsigned long long)mine);
+      if (old == BW_EMPTY_WIDTAG) {
+        tag1 = mine;
+        created = true;
+      } else {
+        tag1 = old;
       }
-      if (mark) bw_mark_dirty(t, sk, s);
     }
-  } else if (created) {
-    // keep the newest pane inline for the next batch
-    if (!(tag & BW_TAG_DIRTY)) bw_mark_dirty(t, sk, s);
+    if (bw_widtag_q(tag1) == q) {
+      bw_apply(p.op, &cs->acc1, operand);
+      if (p.need_count) bw_red_add_u64(&t.aux[s].cnt1, 1ULL);
+      if (((u32)tag1 & 0x7Fu) == born) bw_red_min_u64(&cs->seq1, seq);
+    } else {
+      u32 n = bw_spill_node(t, p, s, q, batch_no, created);
+      if (!n) return;
+      bw_apply(p.op, &t.nodes[n].acc, operand);
+      if (p.need_count) bw_red_add_u64(&t.node_acc2[n], 1ULL);
+      if (t.nodes[n].born == batch_no) bw_red_min_u64(&t.nodes[n].open_seq, seq);
+    }
+  }
+  bw_after_fold(t, p, sk, s, ts, mts, tag0, created);
+}
+
+// raw value bits -> accumulator operand
+__device__ __forceinline__ void bw_operand(const FoldParams& p, u64 raw, u64& operand) {
+  if (p.val_dtype >= 2) {
+    double d = (p.val_dtype == 2) ? (double)__uint_as_float((u32)raw) : __longlong_as_double((i64)raw);
+    u64 b = (u64)__double_as_longlong(d);
+    operand = (p.op == BW_OP_ADD_F64) ? b : bw_f64_to_ordered(b);
+  } else {
+    operand = raw;
+    if (p.op == BW_OP_ADD_F64) {  // MEAN over integers accumulates in f64
+      double d = (p.val_dtype == 1) ? (double)(i64)raw : (double)raw;
+      operand = (u64)__double_as_longlong(d);
+    }
   }
 }
 
@@ -239,14 +313,10 @@ __device__ __forceinline__ bool bw_locate(const BatchView& bv, const u64* seg_st
   return true;
 }
 
-#define BW_FOLD_THREADS 256
-#define BW_FOLD_UNROLL 4
-
-// Fast path: every event of the batch is provably on time (prepass verdict), or
-// the clock never advances on data (wait == forever).
-__global__ void __launch_bounds__(BW_FOLD_THREADS)
-k_fold(BatchView bv, Table t, FoldParams p, u32 batch_no, int check_clean) {
-  if (check_clean && t.ctr->batch_clean == 0u) return;
+// The fold kernel.  Launched only for batches the prepass proved free of late
+// items (or when the clock never advances on data, wait == forever).
+__global__ void __launch_bounds__(BW_FOLD_THREADS, 4)
+k_fold(BatchView bv, Table t, FoldParams p, u32 batch_no) {
   __shared__ u64 seg_start[BW_MAX_WORLD + 1];
   __shared__ BlockSinks sinks;
   bw_sinks_init(&sinks);
@@ -261,30 +331,90 @@ k_fold(BatchView bv, Table t, FoldParams p, u32 batch_no, int check_clean) {
   __syncthreads();
   const u64 total = seg_start[bv.nseg];
   const u64 tile = (u64)BW_FOLD_THREADS * BW_FOLD_UNROLL;
+  const u32 born = batch_no & 63u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  u32 iter = 0;
   for (u64 base = (u64)blockIdx.x * tile; base < total; base += (u64)gridDim.x * tile) {
-    u64 key[BW_FOLD_UNROLL], operand[BW_FOLD_UNROLL], raw;
-    i64 ts[BW_FOLD_UNROLL];
-    bool ok[BW_FOLD_UNROLL];
+    // a warp owns BW_FOLD_UNROLL runs of 32 consecutive events
+    const u64 wbase = base + (u64)warp * (32 * BW_FOLD_UNROLL);
+    u64 key[BW_FOLD_UNROLL], raw[BW_FOLD_UNROLL];
+    // phase A: stream the events in, then issue every home-slot read before using any
 #pragma unroll
     for (int u = 0; u < BW_FOLD_UNROLL; ++u) {
-      u64 g = base + (u64)u * BW_FOLD_THREADS + threadIdx.x;
-      ok[u] = g < total;
-      if (ok[u]) {
+      const u64 g = wbase + (u64)u * 32 + lane;
+      key[u] = 0;
+      raw[u] = 0;
+      if (g < total) {
         int seg = 0;
         u64 off = g;
         if (bv.nseg > 1) bw_locate(bv, seg_start, g, seg, off);
-        bw_load_event(bv, seg, off, p, key[u], ts[u], operand[u], raw);
+        key[u] = bw_ld_stream_u64(bv.keys[seg] + off);
+        if (p.ts_from_value || bv.vals[seg]) {
+          raw[u] = (p.val_dtype == 2) ? (u64)bw_ld_stream_u32((const u32*)bv.vals[seg] + off)
+                                      : bw_ld_stream_u64((const u64*)bv.vals[seg] + off);
+        }
       }
     }
+    u64 k0[BW_FOLD_UNROLL], a0[BW_FOLD_UNROLL];
+    i64 mts[BW_FOLD_UNROLL], tag0[BW_FOLD_UNROLL];
+    u32 slot[BW_FOLD_UNROLL];
 #pragma unroll
     for (int u = 0; u < BW_FOLD_UNROLL; ++u) {
-      if (ok[u]) {
-        u64 g = base + (u64)u * BW_FOLD_THREADS + threadIdx.x;
-        bw_fold_event(t, p, &sinks, key[u], ts[u], operand[u], ((u64)batch_no << 32) | g, batch_no);
+      slot[u] = (u32)bw_home_slot(t, key[u]);
+      bw_ld_slot(t.hot + slot[u], k0[u], mts[u], tag0[u], a0[u]);
+    }
+    // phase B: steady-state events finish here; everything else goes to the warp's queue
+#pragma unroll
+    for (int u = 0; u < BW_FOLD_UNROLL; ++u) {
+      const u64 g = wbase + (u64)u * 32 + lane;
+      if (g >= total) continue;
+      i64 ts;
+      if (p.ts_from_value) {
+        ts = p.align_us + (i64)raw[u];
+      } else {
+        int seg = 0;
+        u64 off = g;
+        if (bv.nseg > 1) bw_locate(bv, seg_start, g, seg, off);
+        ts = (i64)bw_ld_stream_u64((const u64*)bv.ts[seg] + off);
+      }
+      const i64 q = bw_pane_of(ts, p);
+      const bool fast = (k0[u] == key[u]) && (tag0[u] != BW_EMPTY_WIDTAG) && (bw_widtag_q(tag0[u]) == q) &&
+                        (q > -BW_WID_LIMIT) && (q < BW_WID_LIMIT);
+      if (fast) {
+        u64 operand;
+        bw_operand(p, raw[u], operand);
+        HotSlot* hs = t.hot + slot[u];
+        bw_apply(p.op, &hs->acc0, operand);
+        if (p.need_count) bw_red_add_u64(&t.aux[slot[u]].cnt0, 1ULL);
+        if (((u32)tag0[u] & 0x7Fu) == born) bw_red_min_u64(&t.cold[slot[u]].seq0, ((u64)batch_no << 32) | g);
+        bw_after_fold(t, p, &sinks, slot[u], ts, mts[u], tag0[u], false);
+      } else {
+        u32 i = atomicAdd(&sinks.n_defer[warp], 1u);
+        sinks.dq_g[warp][i] = (u32)g;
       }
     }
-    __syncthreads();
-    if (sinks.n_dirty > BW_SINK_CAP / 2) bw_sinks_flush(&sinks, t);  // uniform: read after the barrier
+    __syncwarp();
+    // phase C: the warp drains its own queue with dense lanes (no block barrier)
+    const u32 nd = sinks.n_defer[warp];
+    for (u32 i = lane; i < nd; i += 32) {
+      const u64 g = sinks.dq_g[warp][i];
+      int seg = 0;
+      u64 off = g;
+      if (bv.nseg > 1) bw_locate(bv, seg_start, g, seg, off);
+      u64 kk, op, rw;
+      i64 ts;
+      bw_load_event(bv, seg, off, p, kk, ts, op, rw);
+      bw_fold_event(t, p, &sinks, kk, ts, op, ((u64)batch_no << 32) | g, batch_no);
+    }
+    __syncwarp();
+    if (lane == 0) sinks.n_defer[warp] = 0;
+    __syncwarp();
+    // the staged dirty list is flushed block-wide now and then (it overflows safely
+    // to direct appends, so this is only about keeping the global cursor cold)
+    if ((++iter & 7u) == 0u) {
+      __syncthreads();
+      if (sinks.n_dirty > BW_SINK_CAP / 4) bw_sinks_flush(&sinks, t);  // uniform: read after the barrier
+    }
   }
   __syncthreads();
   bw_sinks_flush(&sinks, t);

@@ -159,16 +159,22 @@ __global__ void k_init_table(Table t, u64 acc_identity) {
     HotSlot h;
     h.key = BW_EMPTY_KEY;
     h.max_ts = INT64_MIN;
-    h.widtag = BW_EMPTY_WIDTAG;
-    h.acc = acc_identity;
+    h.wt0 = BW_EMPTY_WIDTAG;
+    h.acc0 = acc_identity;
     t.hot[s] = h;
     ColdSlot c;
-    c.open_seq = ~0ULL;
-    c.acc2 = 0;
-    c.spill_head = 0;
-    c.lock = 0;
-    c.closed_upto = INT64_MIN;
+    c.wt1 = BW_EMPTY_WIDTAG;
+    c.acc1 = acc_identity;
+    c.seq0 = ~0ULL;
+    c.seq1 = ~0ULL;
     t.cold[s] = c;
+    AuxSlot x;
+    x.cnt0 = 0;
+    x.cnt1 = 0;
+    x.spill_head = 0;
+    x.lock = 0;
+    x.closed_upto = INT64_MIN;
+    t.aux[s] = x;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     Counters z;
@@ -319,9 +325,17 @@ static bw_status fold_alloc(bw_fold* f) {
   while (cap < 2 * std::max<u64>(s.capacity_hint, 1)) cap <<= 1;
   if (cap > (1ULL << 31)) FAIL(f, BW_ERR_SPEC, "capacity_hint too large");
   f->t.mask = cap - 1;
-  f->t.pool_cap = (u32)std::min<u64>(2 * cap + 1024, 0xFFFFFFF0ULL);
+  {
+    // overflow pane nodes: panes a key can hold beyond its two direct slots
+    const i64 per_window = f->p.panes_per_window;
+    u64 expect = 32;  // wait == forever: nothing closes before EOF
+    if (f->p.track_wm) expect = (u64)std::min<i64>(per_window + f->p.wait_us / f->p.pane_us + 4, 1 << 20);
+    u64 want = std::max<u64>(2 * cap, std::max<u64>(s.capacity_hint, 1024) * expect) + 1024;
+    f->t.pool_cap = (u32)std::min<u64>(want, 0x7FFFFFF0ULL);
+  }
   CU(ctx, dmalloc(&f->t.hot, cap + 1));
   CU(ctx, dmalloc(&f->t.cold, cap + 1));
+  CU(ctx, dmalloc(&f->t.aux, cap + 1));
   CU(ctx, dmalloc(&f->t.nodes, f->t.pool_cap));
   CU(ctx, dmalloc(&f->t.node_acc2, f->t.pool_cap));
   CU(ctx, dmalloc(&f->t.free_stack, f->t.pool_cap));
@@ -358,6 +372,24 @@ static bw_status fold_alloc(bw_fold* f) {
   CU(ctx, cudaEventCreateWithFlags(&f->ev_in, cudaEventDisableTiming));
   CU(ctx, cudaEventCreateWithFlags(&f->ev_pre, cudaEventDisableTiming));
   CU(ctx, cudaEventCreateWithFlags(&f->ev_h2d, cudaEventDisableTiming));
+  // Pin the hot slots (one sector per key) in L2: persisting access window on the compute stream.
+  {
+    cudaDeviceProp prop;
+    CU(ctx, cudaGetDeviceProperties(&prop, ctx->device));
+    const size_t hot_bytes = (cap + 1) * sizeof(HotSlot);
+    if (prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
+      const size_t persist = std::min<size_t>(hot_bytes, (size_t)prop.persistingL2CacheMaxSize);
+      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist);
+      cudaStreamAttrValue av;
+      memset(&av, 0, sizeof av);
+      av.accessPolicyWindow.base_ptr = f->t.hot;
+      av.accessPolicyWindow.num_bytes = std::min<size_t>(hot_bytes, (size_t)prop.accessPolicyMaxWindowSize);
+      av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)persist / (double)av.accessPolicyWindow.num_bytes);
+      av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      av.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+      if (cudaStreamSetAttribute(f->s_compute, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) cudaGetLastError();
+    }
+  }
   int occ = 0;
   CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fold, BW_FOLD_THREADS, 0));
   if (occ < 1) occ = 1;
@@ -487,7 +519,7 @@ bw_status bw_fold_create(bw_ctx* ctx, const bw_fold_spec* spec, bw_fold** out) {
   }
   f->val_bytes = spec->val_dtype == BW_VAL_F32 ? 4 : 8;
   f->has_ts = spec->ts_source == BW_TS_COLUMN;
-  f->has_vals = !(spec->reduction == BW_RED_COUNT && f->has_ts);
+  f->has_vals = true;  // the late stream carries the original value, even for counts
   bw_status st = fold_alloc(f);
   if (st != BW_OK) return st;
   if (ctx->world > 1) {
@@ -505,7 +537,7 @@ void bw_fold_destroy(bw_fold* f) {
   cudaDeviceSynchronize();
   for (int r = 0; r < f->ctx->world; ++r)
     if (f->peer_base[r] && r != f->ctx->rank && f->spec.exchange == BW_XCHG_P2P) cudaIpcCloseMemHandle(f->peer_base[r]);
-  void* dev[] = {f->t.hot, f->t.cold, f->t.nodes, f->t.node_acc2, f->t.free_stack, f->t.dirty, f->d_ctr, f->e.c_key,
+  void* dev[] = {f->t.hot, f->t.cold, f->t.aux, f->t.nodes, f->t.node_acc2, f->t.free_stack, f->t.dirty, f->d_ctr, f->e.c_key,
                  f->e.c_wid, f->e.c_acc, f->e.c_count, f->e.c_seq, f->e.c_epoch, f->e.l_key, f->e.l_wid, f->e.l_val,
                  f->e.l_ts, f->e.l_seq, f->e.l_epoch, f->d_rmin, f->d_rmax, f->d_rbad, f->d_verdict, f->d_kflat,
                  f->d_ksorted, f->d_tsflat, f->d_tssorted, f->d_prefmax, f->d_idx, f->d_idxsorted, f->d_late, f->d_cub,
@@ -600,25 +632,26 @@ static bw_status exchange(bw_fold* f, const u64* d_keys, const void* d_vals, con
   XLayout L = xlayout(f);
   PartIn in;
   in.keys = d_keys;
-  in.vals = f->has_vals ? d_vals : nullptr;
+  in.vals = d_vals;
   in.ts = f->has_ts ? d_ts : nullptr;
   in.n = rows;
-  in.val_bytes = f->has_vals ? f->val_bytes : 0;
+  in.val_bytes = d_vals ? f->val_bytes : 0;
   in.world = W;
   PartOut po;
   memset(&po, 0, sizeof po);
   po.region_cap = f->region_cap;
   const bool p2p = f->spec.exchange == BW_XCHG_P2P;
+  const bool hv = d_vals != nullptr;  // counts may come without a value column
   for (int d = 0; d < W; ++d) {
     if (p2p) {
       char* base = (char*)f->peer_base[d];
       po.keys[d] = (u64*)(base + L.keys_off[buf]) + (size_t)R * f->region_cap;
-      po.vals[d] = f->has_vals ? (void*)(base + L.vals_off[buf] + (size_t)R * f->region_cap * f->val_bytes) : nullptr;
+      po.vals[d] = hv ? (void*)(base + L.vals_off[buf] + (size_t)R * f->region_cap * f->val_bytes) : nullptr;
       po.ts[d] = f->has_ts ? (i64*)(base + L.ts_off[buf]) + (size_t)R * f->region_cap : nullptr;
       po.counts[d] = (u64*)(base + L.counts_off[buf]) + R;
     } else {
       po.keys[d] = f->send_keys + (size_t)d * f->region_cap;
-      po.vals[d] = f->has_vals ? (void*)((char*)f->send_vals + (size_t)d * f->region_cap * f->val_bytes) : nullptr;
+      po.vals[d] = hv ? (void*)((char*)f->send_vals + (size_t)d * f->region_cap * f->val_bytes) : nullptr;
       po.ts[d] = f->has_ts ? f->send_ts + (size_t)d * f->region_cap : nullptr;
       po.counts[d] = f->d_send_counts + d;
     }
@@ -649,7 +682,7 @@ static bw_status exchange(bw_fold* f, const u64* d_keys, const void* d_vals, con
       u64* rk = (u64*)(mine + L.keys_off[buf]) + (size_t)r * f->region_cap;
       NC(ctx, ncclSend(f->send_keys + (size_t)r * f->region_cap, nsend, ncclUint64, r, ctx->comm, s));
       NC(ctx, ncclRecv(rk, nrecv, ncclUint64, r, ctx->comm, s));
-      if (f->has_vals) {
+      if (hv) {
         char* rv = mine + L.vals_off[buf] + (size_t)r * f->region_cap * f->val_bytes;
         NC(ctx, ncclSend((char*)f->send_vals + (size_t)r * f->region_cap * f->val_bytes, nsend * f->val_bytes, ncclChar, r,
                          ctx->comm, s));
@@ -673,7 +706,7 @@ static bw_status exchange(bw_fold* f, const u64* d_keys, const void* d_vals, con
   bv->max_rows = f->max_recv_rows;
   for (int r = 0; r < W; ++r) {
     bv->keys[r] = (const u64*)(mine + L.keys_off[buf]) + (size_t)r * f->region_cap;
-    bv->vals[r] = f->has_vals ? (const void*)(mine + L.vals_off[buf] + (size_t)r * f->region_cap * f->val_bytes) : nullptr;
+    bv->vals[r] = hv ? (const void*)(mine + L.vals_off[buf] + (size_t)r * f->region_cap * f->val_bytes) : nullptr;
     bv->ts[r] = f->has_ts ? (const i64*)(mine + L.ts_off[buf]) + (size_t)r * f->region_cap : nullptr;
   }
   return BW_OK;
@@ -698,7 +731,7 @@ static bw_status run_batch(bw_fold* f, const u64* d_keys, const void* d_vals, co
   } else {
     bv.nseg = 1;
     bv.keys[0] = d_keys;
-    bv.vals[0] = f->has_vals ? d_vals : nullptr;
+    bv.vals[0] = d_vals;
     bv.ts[0] = f->has_ts ? d_ts : nullptr;
     bv.h_counts[0] = rows;
     bv.max_rows = rows;
@@ -729,7 +762,7 @@ static bw_status run_batch(bw_fold* f, const u64* d_keys, const void* d_vals, co
       }
       const u64 tile = (u64)BW_FOLD_THREADS * BW_FOLD_UNROLL;
       int grid = (int)std::min<u64>((max_total + tile - 1) / tile, (u64)f->fold_grid);
-      k_fold<<<grid, BW_FOLD_THREADS, 0, f->s_compute>>>(bv, f->t, f->p, batch_no, 0);
+      k_fold<<<grid, BW_FOLD_THREADS, 0, f->s_compute>>>(bv, f->t, f->p, batch_no);
       CU(ctx, cudaGetLastError());
       if (ep) CU(ctx, cudaEventRecord(ep->b, f->s_compute));
       f->st.kernel_launches++;
@@ -799,7 +832,8 @@ bw_status bw_ingest_device(bw_fold* f, const uint64_t* d_keys, const void* d_val
   bw_ctx* ctx = f->ctx;
   if (f->eof_done) FAIL(f, BW_ERR_STATE, "ingest after eof");
   if (rows > f->spec.max_batch_rows) FAIL(f, BW_ERR_SPEC, "ingest: rows > max_batch_rows");
-  if (rows && (!d_keys || (f->has_vals && !d_vals) || (f->has_ts && !d_ts_us))) FAIL(f, BW_ERR_SPEC, "ingest: missing column");
+  if (rows && (!d_keys || (!d_vals && (f->spec.reduction != BW_RED_COUNT || !f->has_ts)) || (f->has_ts && !d_ts_us)))
+    FAIL(f, BW_ERR_SPEC, "ingest: missing column");
   CU(ctx, cudaSetDevice(ctx->device));
   CU(ctx, cudaEventRecord(f->ev_in, f->s_compute));
   return run_batch(f, d_keys, d_vals, d_ts_us, rows, epoch);
@@ -834,7 +868,7 @@ static bw_status slow_path(bw_fold* f, const BatchView& bv, u64 total, u64 epoch
     size_t b1 = 0, b2 = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, b1, f->d_kflat, f->d_ksorted, f->d_idx, f->d_idxsorted, (int)cap, 0, 64, s);
     cub::DeviceScan::ExclusiveScanByKey(nullptr, b2, f->d_ksorted, f->d_tssorted, f->d_prefmax, MaxI64(), (i64)INT64_MIN,
-                                        (int)cap, cub::Equality(), s);
+                                        (int)cap, ::cuda::std::equal_to<>(), s);
     f->cub_bytes = std::max(b1, b2) + 256;
     CU(ctx, cudaMalloc(&f->d_cub, f->cub_bytes));
     f->slow_cap = cap;
@@ -846,7 +880,7 @@ static bw_status slow_path(bw_fold* f, const BatchView& bv, u64 total, u64 epoch
   k_gather_i64<<<grid, 256, 0, s>>>(f->d_tsflat, f->d_idxsorted, f->d_tssorted, total);
   tb = f->cub_bytes;
   CU(ctx, cub::DeviceScan::ExclusiveScanByKey(f->d_cub, tb, f->d_ksorted, f->d_tssorted, f->d_prefmax, MaxI64(),
-                                              (i64)INT64_MIN, (int)total, cub::Equality(), s));
+                                              (i64)INT64_MIN, (int)total, ::cuda::std::equal_to<>(), s));
   k_slow_classify<<<grid, 256, 0, s>>>(f->t, f->p, f->d_ksorted, f->d_idxsorted, f->d_tssorted, f->d_prefmax, f->d_late, total);
   k_slow_fold<<<f->fold_grid, BW_FOLD_THREADS, 0, s>>>(bv, f->t, f->p, f->e, f->d_late, batch_no, epoch_ord);
   CU(ctx, cudaGetLastError());

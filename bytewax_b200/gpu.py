@@ -134,7 +134,7 @@ class WindowFold:
         s.max_late_rows = max_late_rows
         self.spec = s
         self.has_ts = not ts_from_value
-        self.has_vals = not (reduction == "count" and self.has_ts)
+        self.has_vals = True
         h = C.c_void_p()
         N.check(self.lib.bw_fold_create(ctx.h, C.byref(s), C.byref(h)), ctx.h)
         self.h = h
@@ -172,8 +172,11 @@ class WindowFold:
         k[:n] = keys
         if self.has_vals:
             if vals is None:
-                raise ValueError("this fold needs a value column")
-            v[:n] = np.asarray(vals).astype(_NP_VAL[self.val_dtype], copy=False)
+                if self.reduction != "count":
+                    raise ValueError("this fold needs a value column")
+                v[:n] = 0
+            else:
+                v[:n] = np.asarray(vals).astype(_NP_VAL[self.val_dtype], copy=False)
         if self.has_ts:
             if ts is None:
                 raise ValueError("this fold needs a ts_us column")

@@ -134,7 +134,7 @@ typedef struct bw_fold bw_fold;
 /* A borrowed slot of the pinned ingest ring (valid until the matching commit). */
 typedef struct bw_batch {
   uint64_t* keys;  /* [capacity] */
-  void* vals;      /* [capacity] of val_dtype; NULL for BW_RED_COUNT w/ ts column */
+  void* vals;      /* [capacity] of val_dtype (counts carry it only into the late stream) */
   int64_t* ts_us;  /* [capacity]; NULL when ts_source == BW_TS_FROM_VALUE */
   uint64_t capacity;
   uint32_t slot;
