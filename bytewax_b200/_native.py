@@ -15,7 +15,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-LIB_PATH = os.path.join(HERE, "libbwgpu.so")
+LIB_PATH = os.environ.get("BWGPU_LIB") or os.path.join(HERE, "libbwgpu.so")
 CSRC = os.path.join(HERE, "csrc")
 
 BW_OK = 0

@@ -177,7 +177,12 @@ __device__ void bw_close_key(const Table& t, const FoldParams& p, const EmitBufs
     ax->closed_upto = INT64_MIN;
   } else {
     const PaneRec& r0 = P[idx[0]];
-    const u64 delta = (u64)(r0.q - P[idx[m - 1]].q);
+    // threshold (pane units) of the earliest window still covering the oldest pane,
+    // not yet emitted: T = a * max(ceil((q_old - b + 1) / a), closed_upto + 1)
+    i64 w_first = bw_floordiv(P[idx[m - 1]].q - b + a, a);
+    if (!(a == 1 && b == 1) && ax->closed_upto != INT64_MIN && w_first <= ax->closed_upto) w_first = ax->closed_upto + 1;
+    const i64 dq = r0.q - w_first * a;
+    const u64 delta = dq < 0 ? 0 : (u64)dq;
     // K4 runs after the batch that created a pane, so its open_seq is final: mark stale
     hs->wt0 = bw_pack_widtag(r0.q, delta > 255 ? 255u : (u32)delta, BW_TAG_STALE);
     hs->acc0 = r0.acc;

@@ -108,6 +108,16 @@ struct FoldParams {
   i64 panes_per_offset;  // a
   i64 panes_per_window;  // b
   double inv_pane;       // 1.0 / pane_us
+  // exact unsigned division by pane_us (round-up multiply-high): see bw_pane_of
+  u64 div_magic;
+  u32 div_shift;         // L - 1 where L = ceil(log2(pane_us)); pane_us == 1 handled apart
+  u32 div_is_one;
+  i64 div_bias;          // multiple of pane_us, makes (ts - align + bias) non-negative
+  i64 div_bias_q;        // bias / pane_us
+  // closability test in pane units: an event at pane q with remainder r proves every
+  // window w with w * panes_per_offset <= q - close_back - (r < wait_rem) closable
+  i64 close_back;        // length/pane + wait/pane
+  i64 wait_rem;          // wait % pane
   int op;                // BwOp of acc
   int reduction;         // bw_reduction
   int val_dtype;
@@ -228,14 +238,24 @@ __device__ __forceinline__ void bw_apply(int op, u64* acc, u64 operand) {
   }
 }
 
-// floor((ts - align) / pane) for any sign; exact (double estimate + integer fix-up).
+// floor((ts - align) / pane) for any sign, exact, no division: the dividend is
+// biased non-negative and divided by the invariant pane with a precomputed
+// round-up multiplier (q = (t + ((n - t) >> 1)) >> (L - 1), t = mulhi(n, m)).
+__device__ __forceinline__ i64 bw_pane_of_r(i64 ts, const FoldParams& p, i64& rem) {
+  const u64 n = (u64)(ts - p.align_us + p.div_bias);
+  u64 qq;
+  if (p.div_is_one) {
+    qq = n;
+  } else {
+    const u64 t = __umul64hi(n, p.div_magic);
+    qq = (t + ((n - t) >> 1)) >> p.div_shift;
+  }
+  rem = (i64)(n - qq * (u64)p.pane_us);
+  return (i64)qq - p.div_bias_q;
+}
 __device__ __forceinline__ i64 bw_pane_of(i64 ts, const FoldParams& p) {
-  i64 d = ts - p.align_us;
-  i64 q = (i64)floor((double)d * p.inv_pane);
-  i64 r = d - q * p.pane_us;
-  while (r < 0) { r += p.pane_us; --q; }
-  while (r >= p.pane_us) { r -= p.pane_us; ++q; }
-  return q;
+  i64 r;
+  return bw_pane_of_r(ts, p, r);
 }
 // host/device exact floor division
 __host__ __device__ __forceinline__ i64 bw_floordiv(i64 a, i64 b) {

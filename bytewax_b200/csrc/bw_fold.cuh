@@ -12,13 +12,32 @@
 #pragma once
 #include "bw_common.cuh"
 
+// Compile-time specialisation of the fold: the accumulator op, whether the
+// watermark is tracked and whether value counts are kept are template
+// constants in the hot kernel (one small instruction stream per fold type --
+// the generic kernel was 74 KB of SASS and stalled on instruction fetch);
+// -1 means "read it from FoldParams at run time" (exact slow path).
+template <int OP_, int WM_, int CNT_>
+struct FoldCfg {
+  __device__ __forceinline__ static int op(const FoldParams& p) { return OP_ >= 0 ? OP_ : p.op; }
+  __device__ __forceinline__ static bool wm(const FoldParams& p) { return WM_ >= 0 ? (WM_ != 0) : (p.track_wm != 0); }
+  __device__ __forceinline__ static bool cnt(const FoldParams& p) { return CNT_ >= 0 ? (CNT_ != 0) : (p.need_count != 0); }
+};
+typedef FoldCfg<-1, -1, -1> FoldCfgRuntime;
+
 // Block-local staging of the rare global appends (dirty-key list, new-key
 // count) and of the deferred events.
 #define BW_SINK_CAP 1024
 #define BW_FOLD_THREADS 256
+#ifndef BW_FOLD_UNROLL
 #define BW_FOLD_UNROLL 4
+#endif
+#ifndef BW_FOLD_MINB
+#define BW_FOLD_MINB 3
+#endif
 #define BW_FOLD_WARPS (BW_FOLD_THREADS / 32)
 #define BW_WARP_DEFER_CAP (32 * BW_FOLD_UNROLL)
+#define BW_NO_SLOT 0xFFFFFFFFu
 struct BlockSinks {
   u32 n_dirty;
   u32 n_new_keys;
@@ -26,6 +45,7 @@ struct BlockSinks {
   // per-warp queues of deferred events (arrival index within the batch)
   u32 n_defer[BW_FOLD_WARPS];
   u32 dq_g[BW_FOLD_WARPS][BW_WARP_DEFER_CAP];
+  u32 dq_slot[BW_FOLD_WARPS][BW_WARP_DEFER_CAP];  // slot of the key when already known, else BW_NO_SLOT
 };
 __device__ __forceinline__ void bw_sinks_init(BlockSinks* sk) {
   if (threadIdx.x == 0) {
@@ -114,7 +134,7 @@ __device__ __forceinline__ u64 bw_find_slot(const Table& t, BlockSinks* sk, u64 
   return ~0ULL;
 }
 
-__device__ __forceinline__ void bw_mark_dirty(const Table& t, BlockSinks* sk, u64 s) {
+__device__ __noinline__ void bw_mark_dirty(const Table& t, BlockSinks* sk, u64 s) {
   unsigned long long old = atomicOr((unsigned long long*)&t.hot[s].wt0, (unsigned long long)BW_TAG_DIRTY);
   if (!(old & (unsigned long long)BW_TAG_DIRTY)) {
     u32 i = atomicAdd(&sk->n_dirty, 1u);
@@ -184,16 +204,22 @@ __device__ __noinline__ u32 bw_spill_node(const Table& t, const FoldParams& p, u
 }
 
 // Watermark tracking + "this key may have something to close / re-rank" marking.
+// `q`, `rem` = pane and remainder of the event's own timestamp.  K4 leaves in
+// the tag's delta field d = q0 - T where T is the pane-unit threshold of the
+// key's earliest closable window; the event proves it closable iff
+// q - close_back - (rem < wait_rem) >= q0 - d.  255 == "always re-examine".
+template <class C>
 __device__ __forceinline__ void bw_after_fold(const Table& t, const FoldParams& p, BlockSinks* sk, u64 s, i64 ts,
-                                              i64 mts, i64 tag0, bool created) {
+                                              i64 mts, i64 tag0, bool created, i64 q, i64 rem) {
   HotSlot* hs = t.hot + s;
-  if (p.track_wm) {
+  if (C::wm(p)) {
     if (ts > mts) bw_red_max_s64(&hs->max_ts, ts);
     if (!(tag0 & BW_TAG_DIRTY)) {
       bool mark = created;
       if (!mark) {
-        u32 delta = bw_widtag_delta(tag0);
-        mark = (delta == 255u) || (bw_sub_sat(ts, p.wait_us) >= bw_pane_first_close(bw_widtag_q(tag0) - (i64)delta, p));
+        const u32 delta = bw_widtag_delta(tag0);
+        const i64 qc = q - p.close_back - ((rem < p.wait_rem) ? 1 : 0);
+        mark = (delta == 255u) || (qc >= bw_widtag_q(tag0) - (i64)delta);
       }
       if (mark) bw_mark_dirty(t, sk, s);
     }
@@ -204,31 +230,43 @@ __device__ __forceinline__ void bw_after_fold(const Table& t, const FoldParams& 
 
 // General path: any event (new key, displaced key, second / further pane).
 // `seq` = (batch_no << 32) | arrival index.
+template <class C>
 __device__ __noinline__ void bw_fold_event(const Table& t, const FoldParams& p, BlockSinks* sk, u64 key, i64 ts,
-                                           u64 operand, u64 seq, u32 batch_no) {
-  i64 q = bw_pane_of(ts, p);
+                                           u64 operand, u64 seq, u32 batch_no, u32 known_slot = BW_NO_SLOT) {
+  i64 rem;
+  const i64 q = bw_pane_of_r(ts, p, rem);
   if (q <= -BW_WID_LIMIT || q >= BW_WID_LIMIT) {
     bw_raise(t.ctr, 6u /*BW_ERR_RANGE*/);
     return;
   }
   i64 mts, tag0;
-  u64 s = bw_find_slot(t, sk, key, mts, tag0);
-  if (s == ~0ULL) {
-    bw_raise(t.ctr, 3u);
-    return;
+  u64 s;
+  if (known_slot != BW_NO_SLOT) {
+    u64 kk, aa;
+    s = known_slot;
+    bw_ld_slot(t.hot + s, kk, mts, tag0, aa);
+  } else {
+    s = bw_find_slot(t, sk, key, mts, tag0);
+    if (s == ~0ULL) {
+      bw_raise(t.ctr, 3u);
+      return;
+    }
   }
   HotSlot* hs = t.hot + s;
   ColdSlot* cs = t.cold + s;
   const u32 born = batch_no & 63u;
   if (tag0 == BW_EMPTY_WIDTAG) {
-    i64 mine = bw_pack_widtag(q, 0, born);
+    // delta = q - T, T = a * ceil((q - b + 1) / a): threshold of the first window covering this pane
+    const i64 a = p.panes_per_offset, b = p.panes_per_window;
+    const i64 d0 = (a == 1) ? (b - 1) : (q - a * bw_floordiv(q - b + a, a));
+    i64 mine = bw_pack_widtag(q, d0 > 255 ? 255u : (u32)d0, born);
     i64 old = (i64)atomicCAS((unsigned long long*)&hs->wt0, (unsigned long long)BW_EMPTY_WIDTAG, (unsigned long long)mine);
     tag0 = (old == BW_EMPTY_WIDTAG) ? mine : old;
   }
   bool created = false;
   if (bw_widtag_q(tag0) == q) {
-    bw_apply(p.op, &hs->acc0, operand);
-    if (p.need_count) bw_red_add_u64(&t.aux[s].cnt0, 1ULL);
+    bw_apply(C::op(p), &hs->acc0, operand);
+    if (C::cnt(p)) bw_red_add_u64(&t.aux[s].cnt0, 1ULL);
     if (((u32)tag0 & 0x7Fu) == born) bw_red_min_u64(&cs->seq0, seq);
   } else {
     i64 tag1 = bw_ld_i64_coherent(&cs->wt1);
@@ -243,18 +281,18 @@ __device__ __noinline__ void bw_fold_event(const Table& t, const FoldParams& p, 
       }
     }
     if (bw_widtag_q(tag1) == q) {
-      bw_apply(p.op, &cs->acc1, operand);
-      if (p.need_count) bw_red_add_u64(&t.aux[s].cnt1, 1ULL);
+      bw_apply(C::op(p), &cs->acc1, operand);
+      if (C::cnt(p)) bw_red_add_u64(&t.aux[s].cnt1, 1ULL);
       if (((u32)tag1 & 0x7Fu) == born) bw_red_min_u64(&cs->seq1, seq);
     } else {
       u32 n = bw_spill_node(t, p, s, q, batch_no, created);
       if (!n) return;
-      bw_apply(p.op, &t.nodes[n].acc, operand);
-      if (p.need_count) bw_red_add_u64(&t.node_acc2[n], 1ULL);
+      bw_apply(C::op(p), &t.nodes[n].acc, operand);
+      if (C::cnt(p)) bw_red_add_u64(&t.node_acc2[n], 1ULL);
       if (t.nodes[n].born == batch_no) bw_red_min_u64(&t.nodes[n].open_seq, seq);
     }
   }
-  bw_after_fold(t, p, sk, s, ts, mts, tag0, created);
+  bw_after_fold<C>(t, p, sk, s, ts, mts, tag0, created, q, rem);
 }
 
 // raw value bits -> accumulator operand
@@ -304,7 +342,7 @@ __device__ __forceinline__ void bw_load_event(const BatchView& bv, int seg, u64 
 }
 
 // Map a global arrival index to (segment, offset).
-__device__ __forceinline__ bool bw_locate(const BatchView& bv, const u64* seg_start, u64 g, int& seg, u64& off) {
+__device__ __noinline__ bool bw_locate(const BatchView& bv, const u64* seg_start, u64 g, int& seg, u64& off) {
   seg = 0;
 #pragma unroll
   for (int j = 1; j < BW_MAX_WORLD; ++j)
@@ -313,9 +351,20 @@ __device__ __forceinline__ bool bw_locate(const BatchView& bv, const u64* seg_st
   return true;
 }
 
+// Event time of arrival index g (value-derived, or re-read from the ts column: an L1/L2 hit).
+__device__ __forceinline__ i64 bw_event_ts(const BatchView& bv, const u64* seg_start, const FoldParams& p, u64 g,
+                                           u64 raw) {
+  if (p.ts_from_value) return p.align_us + (i64)raw;
+  int seg = 0;
+  u64 off = g;
+  if (bv.nseg > 1) bw_locate(bv, seg_start, g, seg, off);
+  return (i64)bw_ld_stream_u64((const u64*)bv.ts[seg] + off);
+}
+
 // The fold kernel.  Launched only for batches the prepass proved free of late
 // items (or when the clock never advances on data, wait == forever).
-__global__ void __launch_bounds__(BW_FOLD_THREADS, 4)
+template <class C>
+__global__ void __launch_bounds__(BW_FOLD_THREADS, BW_FOLD_MINB)
 k_fold(BatchView bv, Table t, FoldParams p, u32 batch_no) {
   __shared__ u64 seg_start[BW_MAX_WORLD + 1];
   __shared__ BlockSinks sinks;
@@ -363,34 +412,69 @@ k_fold(BatchView bv, Table t, FoldParams p, u32 batch_no) {
       slot[u] = (u32)bw_home_slot(t, key[u]);
       bw_ld_slot(t.hot + slot[u], k0[u], mts[u], tag0[u], a0[u]);
     }
-    // phase B: steady-state events finish here; everything else goes to the warp's queue
+    // phase B1: events in the key's newest pane finish here; events whose key is
+    // known but whose pane is another one fetch the second pane's tag (all
+    // unrolled events issue that read before any uses it); the rest is queued.
+    i64 tag1[BW_FOLD_UNROLL];
+    u64 seq1[BW_FOLD_UNROLL];
+    u32 state[BW_FOLD_UNROLL];  // 0 done/invalid, 1 wants pane 1, 2 defer (slot known), 3 defer (slot unknown)
 #pragma unroll
     for (int u = 0; u < BW_FOLD_UNROLL; ++u) {
       const u64 g = wbase + (u64)u * 32 + lane;
+      state[u] = 0;
+      tag1[u] = BW_EMPTY_WIDTAG;
+      seq1[u] = 0;
       if (g >= total) continue;
-      i64 ts;
-      if (p.ts_from_value) {
-        ts = p.align_us + (i64)raw[u];
+      i64 rem;
+      const i64 ts = bw_event_ts(bv, seg_start, p, g, raw[u]);
+      const i64 q = bw_pane_of_r(ts, p, rem);
+      const bool in_range = (q > -BW_WID_LIMIT) && (q < BW_WID_LIMIT);
+      if (k0[u] == key[u] && tag0[u] != BW_EMPTY_WIDTAG && in_range) {
+        if (bw_widtag_q(tag0[u]) == q) {
+          u64 operand;
+          bw_operand(p, raw[u], operand);
+          HotSlot* hs = t.hot + slot[u];
+          bw_apply(C::op(p), &hs->acc0, operand);
+          if (C::cnt(p)) bw_red_add_u64(&t.aux[slot[u]].cnt0, 1ULL);
+          if (((u32)tag0[u] & 0x7Fu) == born) bw_red_min_u64(&t.cold[slot[u]].seq0, ((u64)batch_no << 32) | g);
+          bw_after_fold<C>(t, p, &sinks, slot[u], ts, mts[u], tag0[u], false, q, rem);
+        } else {
+          state[u] = 1;
+          u64 acc1_unused;
+          i64 seq0_unused;
+          // {wt1, acc1, seq0, seq1} in one sector read
+          bw_ld_slot(t.cold + slot[u], *(u64*)&tag1[u], *(i64*)&acc1_unused, seq0_unused, seq1[u]);
+        }
       } else {
-        int seg = 0;
-        u64 off = g;
-        if (bv.nseg > 1) bw_locate(bv, seg_start, g, seg, off);
-        ts = (i64)bw_ld_stream_u64((const u64*)bv.ts[seg] + off);
+        state[u] = (k0[u] == key[u]) ? 2 : 3;
       }
-      const i64 q = bw_pane_of(ts, p);
-      const bool fast = (k0[u] == key[u]) && (tag0[u] != BW_EMPTY_WIDTAG) && (bw_widtag_q(tag0[u]) == q) &&
-                        (q > -BW_WID_LIMIT) && (q < BW_WID_LIMIT);
-      if (fast) {
-        u64 operand;
-        bw_operand(p, raw[u], operand);
-        HotSlot* hs = t.hot + slot[u];
-        bw_apply(p.op, &hs->acc0, operand);
-        if (p.need_count) bw_red_add_u64(&t.aux[slot[u]].cnt0, 1ULL);
-        if (((u32)tag0[u] & 0x7Fu) == born) bw_red_min_u64(&t.cold[slot[u]].seq0, ((u64)batch_no << 32) | g);
-        bw_after_fold(t, p, &sinks, slot[u], ts, mts[u], tag0[u], false);
-      } else {
+    }
+    // phase B2: second-pane hits finish here
+#pragma unroll
+    for (int u = 0; u < BW_FOLD_UNROLL; ++u) {
+      if (state[u] == 1) {
+        const u64 g = wbase + (u64)u * 32 + lane;
+        i64 rem;
+        const i64 ts = bw_event_ts(bv, seg_start, p, g, raw[u]);
+        const i64 q = bw_pane_of_r(ts, p, rem);
+        if (tag1[u] != BW_EMPTY_WIDTAG && bw_widtag_q(tag1[u]) == q) {
+          u64 operand;
+          bw_operand(p, raw[u], operand);
+          ColdSlot* cs = t.cold + slot[u];
+          bw_apply(C::op(p), &cs->acc1, operand);
+          if (C::cnt(p)) bw_red_add_u64(&t.aux[slot[u]].cnt1, 1ULL);
+          if (((u32)tag1[u] & 0x7Fu) == born && (((u64)batch_no << 32) | g) < seq1[u])
+            bw_red_min_u64(&cs->seq1, ((u64)batch_no << 32) | g);
+          bw_after_fold<C>(t, p, &sinks, slot[u], ts, mts[u], tag0[u], false, q, rem);
+          state[u] = 0;
+        } else {
+          state[u] = 2;
+        }
+      }
+      if (state[u] >= 2) {
         u32 i = atomicAdd(&sinks.n_defer[warp], 1u);
-        sinks.dq_g[warp][i] = (u32)g;
+        sinks.dq_g[warp][i] = (u32)(wbase + (u64)u * 32 + lane);
+        sinks.dq_slot[warp][i] = (state[u] == 2) ? slot[u] : BW_NO_SLOT;
       }
     }
     __syncwarp();
@@ -404,7 +488,7 @@ k_fold(BatchView bv, Table t, FoldParams p, u32 batch_no) {
       u64 kk, op, rw;
       i64 ts;
       bw_load_event(bv, seg, off, p, kk, ts, op, rw);
-      bw_fold_event(t, p, &sinks, kk, ts, op, ((u64)batch_no << 32) | g, batch_no);
+      bw_fold_event<C>(t, p, &sinks, kk, ts, op, ((u64)batch_no << 32) | g, batch_no, sinks.dq_slot[warp][i]);
     }
     __syncwarp();
     if (lane == 0) sinks.n_defer[warp] = 0;

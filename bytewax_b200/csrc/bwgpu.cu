@@ -129,6 +129,7 @@ struct bw_fold {
   u64 ordinal_base = 0;
   bool eof_done = false;
   int fold_grid = 0, close_grid = 0;
+  void (*fold_kernel)(BatchView, Table, FoldParams, u32) = nullptr;
   // multi-GPU exchange
   void* xchg_base = nullptr;  // one allocation, IPC-shared
   size_t xchg_bytes = 0;
@@ -317,6 +318,26 @@ static cudaError_t dmalloc(T** p, size_t n) {
   return cudaMalloc((void**)p, (n ? n : 1) * sizeof(T));
 }
 
+// k_fold instantiations: accumulator op x watermark tracking (+ MEAN keeps counts)
+typedef void (*fold_kernel_t)(BatchView, Table, FoldParams, u32);
+template <int OP, int CNT>
+static fold_kernel_t pick_wm(bool wm) {
+  return wm ? (fold_kernel_t)k_fold<FoldCfg<OP, 1, CNT>> : (fold_kernel_t)k_fold<FoldCfg<OP, 0, CNT>>;
+}
+static fold_kernel_t pick_fold_kernel(const FoldParams& p) {
+  const bool wm = p.track_wm != 0;
+  if (p.need_count) return pick_wm<BW_OP_ADD_F64, 1>(wm);
+  switch (p.op) {
+    case BW_OP_ADD_ONE: return pick_wm<BW_OP_ADD_ONE, 0>(wm);
+    case BW_OP_ADD_U64: return pick_wm<BW_OP_ADD_U64, 0>(wm);
+    case BW_OP_ADD_F64: return pick_wm<BW_OP_ADD_F64, 0>(wm);
+    case BW_OP_MIN_S64: return pick_wm<BW_OP_MIN_S64, 0>(wm);
+    case BW_OP_MIN_U64: return pick_wm<BW_OP_MIN_U64, 0>(wm);
+    case BW_OP_MAX_S64: return pick_wm<BW_OP_MAX_S64, 0>(wm);
+    default: return pick_wm<BW_OP_MAX_U64, 0>(wm);
+  }
+}
+
 static bw_status fold_alloc(bw_fold* f) {
   bw_ctx* ctx = f->ctx;
   const bw_fold_spec& s = f->spec;
@@ -391,7 +412,8 @@ static bw_status fold_alloc(bw_fold* f) {
     }
   }
   int occ = 0;
-  CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fold, BW_FOLD_THREADS, 0));
+  f->fold_kernel = pick_fold_kernel(f->p);
+  CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, f->fold_kernel, BW_FOLD_THREADS, 0));
   if (occ < 1) occ = 1;
   f->fold_grid = ctx->sm_count * occ;
   f->close_grid = ctx->sm_count * 8;
@@ -497,6 +519,30 @@ bw_status bw_fold_create(bw_ctx* ctx, const bw_fold_spec* spec, bw_fold** out) {
   p.panes_per_offset = spec->offset_us / p.pane_us;
   p.panes_per_window = spec->length_us / p.pane_us;
   p.inv_pane = 1.0 / (double)p.pane_us;
+  {
+    // round-up multiplier for exact u64 division by pane_us (Granlund-Montgomery / libdivide "algorithm 1")
+    const u64 D = (u64)p.pane_us;
+    p.div_is_one = (D == 1);
+    u32 L = 0;
+    while (L < 64 && ((L == 63) ? false : ((1ULL << L) < D))) ++L;
+    if ((1ULL << (L >= 64 ? 63 : L)) < D) L = 64;
+    if (!p.div_is_one) {
+      const unsigned __int128 one = 1;
+      const unsigned __int128 num = (one << 64) * (unsigned __int128)(((L >= 64) ? (unsigned __int128)(one << 64) : (unsigned __int128)(one << L)) - D);
+      p.div_magic = (u64)(num / D) + 1;
+      p.div_shift = L - 1;
+    } else {
+      p.div_magic = 0;
+      p.div_shift = 0;
+    }
+    // bias: multiple of pane, >= 2^59 (covers |ts - align| for every representable datetime pair)
+    const i64 need = (i64)1 << 59;
+    p.div_bias_q = (need + p.pane_us - 1) / p.pane_us;
+    p.div_bias = p.div_bias_q * p.pane_us;
+    const i64 w = p.track_wm ? p.wait_us : 0;
+    p.close_back = p.length_us / p.pane_us + w / p.pane_us;
+    p.wait_rem = w % p.pane_us;
+  }
   p.reduction = spec->reduction;
   p.val_dtype = spec->val_dtype;
   p.ts_from_value = spec->ts_source == BW_TS_FROM_VALUE;
@@ -762,7 +808,7 @@ static bw_status run_batch(bw_fold* f, const u64* d_keys, const void* d_vals, co
       }
       const u64 tile = (u64)BW_FOLD_THREADS * BW_FOLD_UNROLL;
       int grid = (int)std::min<u64>((max_total + tile - 1) / tile, (u64)f->fold_grid);
-      k_fold<<<grid, BW_FOLD_THREADS, 0, f->s_compute>>>(bv, f->t, f->p, batch_no);
+      f->fold_kernel<<<grid, BW_FOLD_THREADS, 0, f->s_compute>>>(bv, f->t, f->p, batch_no);
       CU(ctx, cudaGetLastError());
       if (ep) CU(ctx, cudaEventRecord(ep->b, f->s_compute));
       f->st.kernel_launches++;
