@@ -77,10 +77,12 @@ struct PaneRec {
 };
 
 // Close everything the key's watermark allows, then put the newest pane in
-// the hot slot, the second newest in the cold slot and the rest on the list.
+// the hot slot; pane 1 becomes the pane right before it when that one is still
+// alive (P1_PREV), else it is left empty for the pane right after it; the
+// rest goes on the list.
 __device__ void bw_close_key(const Table& t, const FoldParams& p, const EmitBufs& e, u64 s, bool eof, u64 epoch) {
   HotSlot* hs = t.hot + s;
-  ColdSlot* cs = t.cold + s;
+  P1Slot* ps = t.p1 + s;
   AuxSlot* ax = t.aux + s;
   if (hs->wt0 == BW_EMPTY_WIDTAG) return;
   const u64 key = hs->key;
@@ -97,9 +99,8 @@ __device__ void bw_close_key(const Table& t, const FoldParams& p, const EmitBufs
   PaneRec P[BW_MAX_PANES];
   u32 nodes[BW_MAX_PANES];
   int n = 0, nn = 0;
-  P[n++] = PaneRec{bw_widtag_q(hs->wt0), hs->acc0, ax->cnt0, cs->seq0, (u32)hs->wt0 & 0x7Fu, false};
-  if (cs->wt1 != BW_EMPTY_WIDTAG)
-    P[n++] = PaneRec{bw_widtag_q(cs->wt1), cs->acc1, ax->cnt1, cs->seq1, (u32)cs->wt1 & 0x7Fu, false};
+  P[n++] = PaneRec{bw_widtag_q(hs->wt0), hs->acc0, ax->cnt0, ax->seq0, (u32)hs->wt0 & 0x7Fu, false};
+  if (ps->seq1 != ~0ULL) P[n++] = PaneRec{bw_widtag_q1(hs->wt0), ps->acc1, ax->cnt1, ps->seq1, BW_TAG_STALE, false};
   for (u32 nd = ax->spill_head; nd; nd = t.nodes[nd].next) {
     if (n >= BW_MAX_PANES) {
       bw_raise(t.ctr, 3u);
@@ -125,7 +126,7 @@ __device__ void bw_close_key(const Table& t, const FoldParams& p, const EmitBufs
     if (eof) c_new = INT64_MAX;
     else if (wm == INT64_MIN) c_new = INT64_MIN;
     else c_new = bw_floordiv(wm - p.align_us - p.length_us, p.offset_us);
-    const i64 c_prev = ax->closed_upto;
+    const i64 c_prev = t.closed_upto[s];
     if (c_new > c_prev) {
       for (int i = 0; i < n; ++i) {
         i64 w_lo = bw_floordiv(P[i].q - b + a, a);  // ceil((q - b + 1) / a)
@@ -151,7 +152,7 @@ __device__ void bw_close_key(const Table& t, const FoldParams& p, const EmitBufs
                            epoch);
         }
       }
-      ax->closed_upto = c_new;
+      t.closed_upto[s] = c_new;
     }
     for (int i = 0; i < n; ++i)
       if (wm >= bw_pane_release(P[i].q, p)) P[i].dead = true;
@@ -168,61 +169,57 @@ __device__ void bw_close_key(const Table& t, const FoldParams& p, const EmitBufs
     }
     idx[j] = i;
   }
+  int first_listed = 1;  // survivors idx[first_listed..] go to the list
   if (m == 0) {
     // no panes left: the reference discards the whole logic, watermark included
     // (windowing.py:1110-1113 -> src/operators.rs:796-799)
     hs->max_ts = INT64_MIN;
     hs->wt0 = BW_EMPTY_WIDTAG;
     hs->acc0 = p.acc_identity;
-    ax->closed_upto = INT64_MIN;
+    ax->seq0 = ~0ULL;
+    ax->cnt0 = 0;
+    t.closed_upto[s] = INT64_MIN;
   } else {
     const PaneRec& r0 = P[idx[0]];
+    const bool prev = (m >= 2) && (P[idx[1]].q == r0.q - 1);
     // threshold (pane units) of the earliest window still covering the oldest pane,
     // not yet emitted: T = a * max(ceil((q_old - b + 1) / a), closed_upto + 1)
     i64 w_first = bw_floordiv(P[idx[m - 1]].q - b + a, a);
-    if (!(a == 1 && b == 1) && ax->closed_upto != INT64_MIN && w_first <= ax->closed_upto) w_first = ax->closed_upto + 1;
+    if (!(a == 1 && b == 1) && t.closed_upto[s] != INT64_MIN && w_first <= t.closed_upto[s]) w_first = t.closed_upto[s] + 1;
     const i64 dq = r0.q - w_first * a;
     const u64 delta = dq < 0 ? 0 : (u64)dq;
     // K4 runs after the batch that created a pane, so its open_seq is final: mark stale
-    hs->wt0 = bw_pack_widtag(r0.q, delta > 255 ? 255u : (u32)delta, BW_TAG_STALE);
+    hs->wt0 = bw_pack_widtag(r0.q, delta > BW_TAG_DELTA_MAX ? BW_TAG_DELTA_MAX : (u32)delta, BW_TAG_STALE, prev);
     hs->acc0 = r0.acc;
     ax->cnt0 = r0.cnt;
-    cs->seq0 = r0.seq;
+    ax->seq0 = r0.seq;
+    if (prev) {
+      const PaneRec& r1 = P[idx[1]];
+      ps->acc1 = r1.acc;
+      ps->seq1 = r1.seq;
+      ax->cnt1 = r1.cnt;
+      first_listed = 2;
+    }
   }
-  if (m >= 2) {
-    const PaneRec& r1 = P[idx[1]];
-    cs->wt1 = bw_pack_widtag(r1.q, 0, BW_TAG_STALE);
-    cs->acc1 = r1.acc;
-    ax->cnt1 = r1.cnt;
-    cs->seq1 = r1.seq;
-  } else {
-    cs->wt1 = BW_EMPTY_WIDTAG;
-    cs->acc1 = p.acc_identity;
+  if (first_listed == 1) {  // pane 1 empty: reserved for the pane after pane 0
+    ps->acc1 = p.acc_identity;
+    ps->seq1 = ~0ULL;
     ax->cnt1 = 0;
-    cs->seq1 = ~0ULL;
-  }
-  if (m == 0) {
-    ax->cnt0 = 0;
-    cs->seq0 = ~0ULL;
   }
   // the rest goes back on the list, reusing node storage
   u32 head = 0;
   int used = 0;
-  for (int r = m - 1; r >= 2; --r) {
+  for (int r = m - 1; r >= first_listed; --r) {
     u32 nd;
     if (used < nn) {
       nd = nodes[used++];
     } else {
-      int top = atomicSub(&t.ctr->free_top, 1);
-      if (top > 0) {
-        nd = t.free_stack[top - 1];
-      } else {
-        atomicAdd(&t.ctr->free_top, 1);
-        nd = atomicAdd(&t.ctr->pool_next, 1u);
-        if (nd >= t.pool_cap) {
-          bw_raise(t.ctr, 3u);
-          break;
-        }
+      // bump-allocate only: other K4 threads are pushing onto the free stack right now,
+      // so popping from it here could read a slot that is reserved but not yet written
+      nd = atomicAdd(&t.ctr->pool_next, 1u);
+      if (nd >= t.pool_cap) {
+        bw_raise(t.ctr, 3u);
+        break;
       }
     }
     const PaneRec& rr = P[idx[r]];

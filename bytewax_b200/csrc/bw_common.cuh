@@ -32,29 +32,30 @@ __host__ __device__ __forceinline__ u32 bw_route_hash(u64 h, u32 world) {
 // State layout in HBM (DESIGN.md "Data layout").
 //
 // One 32-byte HOT slot per key == exactly one L2 sector: everything the
-// steady-state fold touches (key, running max ts, newest pane).  One 32-byte
-// COLD slot per key holds the second pane (the one a key is moving out of or
-// into inside an activation) plus both panes' open sequence numbers.  One
-// 32-byte AUX slot per key for counts (MEAN), sliding bookkeeping and the head
-// of a short linked list of 32-byte nodes for any further live panes.
+// steady-state fold touches (key, running max ts, newest pane).  One 16-byte
+// P1 slot per key for the adjacent pane a key is moving into / out of.  One
+// 32-byte AUX slot per key for pane 0's open sequence, counts (MEAN) and the
+// head of a short linked list of 32-byte nodes for any further live panes.
 // ---------------------------------------------------------------------------
 struct __align__(32) HotSlot {
   u64 key;      // BW_EMPTY_KEY when free
   i64 max_ts;   // max event ts seen since the key was (re)created; INT64_MIN when none
-  i64 wt0;      // pane 0 (newest after K4): (pane_id << 16) | older_delta << 8 | dirty << 7 | stale << 6 | born & 63
+  i64 wt0;      // pane 0 (newest after K4): pane_id << 16 | p1_prev << 15 | delta << 8 | dirty << 7 | stale << 6 | born & 63
   u64 acc0;     // pane 0 accumulator (bits)
 };
-struct __align__(32) ColdSlot {
-  i64 wt1;      // pane 1 (second newest after K4), same packing (delta / dirty unused)
+// Pane 1 is implicit: the pane right after pane 0 (the one an in-order key moves
+// into inside an activation), or right before it when wt0 has P1_PREV (the one
+// an out-of-order key is still finishing).  16 bytes per key keeps the working
+// set of a window-boundary activation at hot + 16 B/key.  Present iff seq1 != ~0.
+struct __align__(16) P1Slot {
   u64 acc1;
-  u64 seq0;     // arrival sequence (batch << 32 | index) of the event that opened pane 0
-  u64 seq1;     // ... pane 1
+  u64 seq1;     // arrival sequence of the event that opened pane 1
 };
 struct __align__(32) AuxSlot {
+  u64 seq0;         // arrival sequence (batch << 32 | index) of the event that opened pane 0
   u64 cnt0, cnt1;   // value counts of panes 0 / 1 (MEAN divisor)
   u32 spill_head;   // further panes: linked list of PaneNode, 0 == none
   u32 lock;         // structural lock for the node list
-  i64 closed_upto;  // sliding windows: window ids <= this were already emitted for this key incarnation
 };
 struct __align__(32) PaneNode {
   i64 wid;
@@ -73,13 +74,18 @@ struct __align__(32) PaneNode {
 #define BW_TAG_BORN_MASK 0x7FLL  // bits 5:0 = creating batch & 63, bit 6 = "not fresh" (set by K4)
 #define BW_TAG_STALE 0x40u
 #define BW_TAG_DELTA_SHIFT 8
+#define BW_TAG_DELTA_MAX 127u     // 7 bits; the maximum means "always re-examine"
+#define BW_TAG_P1_PREV 0x8000LL   // pane 1 is pane0 - 1 (else pane0 + 1)
 
-__host__ __device__ __forceinline__ i64 bw_pack_widtag(i64 q, u32 delta, u32 born) {
-  return (i64)((u64)q << BW_WID_SHIFT) | ((i64)(delta > 255u ? 255u : delta) << BW_TAG_DELTA_SHIFT) |
-         (i64)(born & 0x7Fu);
+__host__ __device__ __forceinline__ i64 bw_pack_widtag(i64 q, u32 delta, u32 born, bool p1_prev = false) {
+  return (i64)((u64)q << BW_WID_SHIFT) | (p1_prev ? BW_TAG_P1_PREV : 0LL) |
+         ((i64)(delta > BW_TAG_DELTA_MAX ? BW_TAG_DELTA_MAX : delta) << BW_TAG_DELTA_SHIFT) | (i64)(born & 0x7Fu);
+}
+__host__ __device__ __forceinline__ i64 bw_widtag_q1(i64 tag) {
+  return (tag >> BW_WID_SHIFT) + ((tag & BW_TAG_P1_PREV) ? -1 : 1);
 }
 __host__ __device__ __forceinline__ i64 bw_widtag_q(i64 tag) { return tag >> BW_WID_SHIFT; }
-__host__ __device__ __forceinline__ u32 bw_widtag_delta(i64 tag) { return (u32)((tag >> BW_TAG_DELTA_SHIFT) & 0xFF); }
+__host__ __device__ __forceinline__ u32 bw_widtag_delta(i64 tag) { return (u32)((tag >> BW_TAG_DELTA_SHIFT) & 0x7F); }
 
 // accumulator op codes (uniform per fold)
 enum BwOp : int {
@@ -130,8 +136,9 @@ struct FoldParams {
 
 struct Table {
   HotSlot* hot;
-  ColdSlot* cold;
+  P1Slot* p1;
   AuxSlot* aux;
+  i64* closed_upto;  // sliding windows: window ids <= this were already emitted for this key incarnation
   PaneNode* nodes;
   u64* node_acc2;
   u32* free_stack;

@@ -219,7 +219,7 @@ __device__ __forceinline__ void bw_after_fold(const Table& t, const FoldParams& 
       if (!mark) {
         const u32 delta = bw_widtag_delta(tag0);
         const i64 qc = q - p.close_back - ((rem < p.wait_rem) ? 1 : 0);
-        mark = (delta == 255u) || (qc >= bw_widtag_q(tag0) - (i64)delta);
+        mark = (delta == BW_TAG_DELTA_MAX) || (qc >= bw_widtag_q(tag0) - (i64)delta);
       }
       if (mark) bw_mark_dirty(t, sk, s);
     }
@@ -253,13 +253,12 @@ __device__ __noinline__ void bw_fold_event(const Table& t, const FoldParams& p, 
     }
   }
   HotSlot* hs = t.hot + s;
-  ColdSlot* cs = t.cold + s;
   const u32 born = batch_no & 63u;
   if (tag0 == BW_EMPTY_WIDTAG) {
     // delta = q - T, T = a * ceil((q - b + 1) / a): threshold of the first window covering this pane
     const i64 a = p.panes_per_offset, b = p.panes_per_window;
     const i64 d0 = (a == 1) ? (b - 1) : (q - a * bw_floordiv(q - b + a, a));
-    i64 mine = bw_pack_widtag(q, d0 > 255 ? 255u : (u32)d0, born);
+    i64 mine = bw_pack_widtag(q, d0 > (i64)BW_TAG_DELTA_MAX ? BW_TAG_DELTA_MAX : (u32)d0, born);
     i64 old = (i64)atomicCAS((unsigned long long*)&hs->wt0, (unsigned long long)BW_EMPTY_WIDTAG, (unsigned long long)mine);
     tag0 = (old == BW_EMPTY_WIDTAG) ? mine : old;
   }
@@ -267,30 +266,17 @@ __device__ __noinline__ void bw_fold_event(const Table& t, const FoldParams& p, 
   if (bw_widtag_q(tag0) == q) {
     bw_apply(C::op(p), &hs->acc0, operand);
     if (C::cnt(p)) bw_red_add_u64(&t.aux[s].cnt0, 1ULL);
-    if (((u32)tag0 & 0x7Fu) == born) bw_red_min_u64(&cs->seq0, seq);
+    if (((u32)tag0 & 0x7Fu) == born) bw_red_min_u64(&t.aux[s].seq0, seq);
+  } else if (bw_widtag_q1(tag0) == q) {
+    bw_apply(C::op(p), &t.p1[s].acc1, operand);
+    if (!(tag0 & BW_TAG_P1_PREV)) bw_red_min_u64(&t.p1[s].seq1, seq);  // presence + first-open order
+    if (C::cnt(p)) bw_red_add_u64(&t.aux[s].cnt1, 1ULL);
   } else {
-    i64 tag1 = bw_ld_i64_coherent(&cs->wt1);
-    if (tag1 == BW_EMPTY_WIDTAG) {
-      i64 mine = bw_pack_widtag(q, 0, born);
-      i64 old = (i64)atomicCAS((unsigned long long*)&cs->wt1, (unsigned long long)BW_EMPTY_WIDTAG, (unsigned long long)mine);
-      if (old == BW_EMPTY_WIDTAG) {
-        tag1 = mine;
-        created = true;
-      } else {
-        tag1 = old;
-      }
-    }
-    if (bw_widtag_q(tag1) == q) {
-      bw_apply(C::op(p), &cs->acc1, operand);
-      if (C::cnt(p)) bw_red_add_u64(&t.aux[s].cnt1, 1ULL);
-      if (((u32)tag1 & 0x7Fu) == born) bw_red_min_u64(&cs->seq1, seq);
-    } else {
-      u32 n = bw_spill_node(t, p, s, q, batch_no, created);
-      if (!n) return;
-      bw_apply(C::op(p), &t.nodes[n].acc, operand);
-      if (C::cnt(p)) bw_red_add_u64(&t.node_acc2[n], 1ULL);
-      if (t.nodes[n].born == batch_no) bw_red_min_u64(&t.nodes[n].open_seq, seq);
-    }
+    u32 n = bw_spill_node(t, p, s, q, batch_no, created);
+    if (!n) return;
+    bw_apply(C::op(p), &t.nodes[n].acc, operand);
+    if (C::cnt(p)) bw_red_add_u64(&t.node_acc2[n], 1ULL);
+    if (t.nodes[n].born == batch_no) bw_red_min_u64(&t.nodes[n].open_seq, seq);
   }
   bw_after_fold<C>(t, p, sk, s, ts, mts, tag0, created, q, rem);
 }
@@ -412,69 +398,38 @@ k_fold(BatchView bv, Table t, FoldParams p, u32 batch_no) {
       slot[u] = (u32)bw_home_slot(t, key[u]);
       bw_ld_slot(t.hot + slot[u], k0[u], mts[u], tag0[u], a0[u]);
     }
-    // phase B1: events in the key's newest pane finish here; events whose key is
-    // known but whose pane is another one fetch the second pane's tag (all
-    // unrolled events issue that read before any uses it); the rest is queued.
-    i64 tag1[BW_FOLD_UNROLL];
-    u64 seq1[BW_FOLD_UNROLL];
-    u32 state[BW_FOLD_UNROLL];  // 0 done/invalid, 1 wants pane 1, 2 defer (slot known), 3 defer (slot unknown)
+    // phase B: events in the key's pane 0 or pane 1 finish here from the one
+    // sector already read; everything else goes to the warp's queue.
 #pragma unroll
     for (int u = 0; u < BW_FOLD_UNROLL; ++u) {
       const u64 g = wbase + (u64)u * 32 + lane;
-      state[u] = 0;
-      tag1[u] = BW_EMPTY_WIDTAG;
-      seq1[u] = 0;
       if (g >= total) continue;
       i64 rem;
       const i64 ts = bw_event_ts(bv, seg_start, p, g, raw[u]);
       const i64 q = bw_pane_of_r(ts, p, rem);
-      const bool in_range = (q > -BW_WID_LIMIT) && (q < BW_WID_LIMIT);
-      if (k0[u] == key[u] && tag0[u] != BW_EMPTY_WIDTAG && in_range) {
-        if (bw_widtag_q(tag0[u]) == q) {
-          u64 operand;
-          bw_operand(p, raw[u], operand);
-          HotSlot* hs = t.hot + slot[u];
-          bw_apply(C::op(p), &hs->acc0, operand);
+      const bool known = (k0[u] == key[u]);
+      const bool usable = known && tag0[u] != BW_EMPTY_WIDTAG && (q > -BW_WID_LIMIT) && (q < BW_WID_LIMIT);
+      const bool hit0 = usable && bw_widtag_q(tag0[u]) == q;
+      const bool hit1 = usable && !hit0 && bw_widtag_q1(tag0[u]) == q;
+      if (hit0 || hit1) {
+        u64 operand;
+        bw_operand(p, raw[u], operand);
+        const u64 seq = ((u64)batch_no << 32) | g;
+        if (hit0) {
+          bw_apply(C::op(p), &t.hot[slot[u]].acc0, operand);
           if (C::cnt(p)) bw_red_add_u64(&t.aux[slot[u]].cnt0, 1ULL);
-          if (((u32)tag0[u] & 0x7Fu) == born) bw_red_min_u64(&t.cold[slot[u]].seq0, ((u64)batch_no << 32) | g);
-          bw_after_fold<C>(t, p, &sinks, slot[u], ts, mts[u], tag0[u], false, q, rem);
+          if (((u32)tag0[u] & 0x7Fu) == born) bw_red_min_u64(&t.aux[slot[u]].seq0, seq);
         } else {
-          state[u] = 1;
-          u64 acc1_unused;
-          i64 seq0_unused;
-          // {wt1, acc1, seq0, seq1} in one sector read
-          bw_ld_slot(t.cold + slot[u], *(u64*)&tag1[u], *(i64*)&acc1_unused, seq0_unused, seq1[u]);
-        }
-      } else {
-        state[u] = (k0[u] == key[u]) ? 2 : 3;
-      }
-    }
-    // phase B2: second-pane hits finish here
-#pragma unroll
-    for (int u = 0; u < BW_FOLD_UNROLL; ++u) {
-      if (state[u] == 1) {
-        const u64 g = wbase + (u64)u * 32 + lane;
-        i64 rem;
-        const i64 ts = bw_event_ts(bv, seg_start, p, g, raw[u]);
-        const i64 q = bw_pane_of_r(ts, p, rem);
-        if (tag1[u] != BW_EMPTY_WIDTAG && bw_widtag_q(tag1[u]) == q) {
-          u64 operand;
-          bw_operand(p, raw[u], operand);
-          ColdSlot* cs = t.cold + slot[u];
-          bw_apply(C::op(p), &cs->acc1, operand);
+          P1Slot* ps = t.p1 + slot[u];
+          bw_apply(C::op(p), &ps->acc1, operand);
+          if (!(tag0[u] & BW_TAG_P1_PREV)) bw_red_min_u64(&ps->seq1, seq);
           if (C::cnt(p)) bw_red_add_u64(&t.aux[slot[u]].cnt1, 1ULL);
-          if (((u32)tag1[u] & 0x7Fu) == born && (((u64)batch_no << 32) | g) < seq1[u])
-            bw_red_min_u64(&cs->seq1, ((u64)batch_no << 32) | g);
-          bw_after_fold<C>(t, p, &sinks, slot[u], ts, mts[u], tag0[u], false, q, rem);
-          state[u] = 0;
-        } else {
-          state[u] = 2;
         }
-      }
-      if (state[u] >= 2) {
+        bw_after_fold<C>(t, p, &sinks, slot[u], ts, mts[u], tag0[u], false, q, rem);
+      } else {
         u32 i = atomicAdd(&sinks.n_defer[warp], 1u);
-        sinks.dq_g[warp][i] = (u32)(wbase + (u64)u * 32 + lane);
-        sinks.dq_slot[warp][i] = (state[u] == 2) ? slot[u] : BW_NO_SLOT;
+        sinks.dq_g[warp][i] = (u32)g;
+        sinks.dq_slot[warp][i] = known ? slot[u] : BW_NO_SLOT;
       }
     }
     __syncwarp();

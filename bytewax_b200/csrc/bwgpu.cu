@@ -163,19 +163,18 @@ __global__ void k_init_table(Table t, u64 acc_identity) {
     h.wt0 = BW_EMPTY_WIDTAG;
     h.acc0 = acc_identity;
     t.hot[s] = h;
-    ColdSlot c;
-    c.wt1 = BW_EMPTY_WIDTAG;
+    P1Slot c;
     c.acc1 = acc_identity;
-    c.seq0 = ~0ULL;
     c.seq1 = ~0ULL;
-    t.cold[s] = c;
+    t.p1[s] = c;
     AuxSlot x;
+    x.seq0 = ~0ULL;
     x.cnt0 = 0;
     x.cnt1 = 0;
     x.spill_head = 0;
     x.lock = 0;
-    x.closed_upto = INT64_MIN;
     t.aux[s] = x;
+    t.closed_upto[s] = INT64_MIN;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     Counters z;
@@ -355,7 +354,8 @@ static bw_status fold_alloc(bw_fold* f) {
     f->t.pool_cap = (u32)std::min<u64>(want, 0x7FFFFFF0ULL);
   }
   CU(ctx, dmalloc(&f->t.hot, cap + 1));
-  CU(ctx, dmalloc(&f->t.cold, cap + 1));
+  CU(ctx, dmalloc(&f->t.p1, cap + 1));
+  CU(ctx, dmalloc(&f->t.closed_upto, cap + 1));
   CU(ctx, dmalloc(&f->t.aux, cap + 1));
   CU(ctx, dmalloc(&f->t.nodes, f->t.pool_cap));
   CU(ctx, dmalloc(&f->t.node_acc2, f->t.pool_cap));
@@ -583,7 +583,7 @@ void bw_fold_destroy(bw_fold* f) {
   cudaDeviceSynchronize();
   for (int r = 0; r < f->ctx->world; ++r)
     if (f->peer_base[r] && r != f->ctx->rank && f->spec.exchange == BW_XCHG_P2P) cudaIpcCloseMemHandle(f->peer_base[r]);
-  void* dev[] = {f->t.hot, f->t.cold, f->t.aux, f->t.nodes, f->t.node_acc2, f->t.free_stack, f->t.dirty, f->d_ctr, f->e.c_key,
+  void* dev[] = {f->t.hot, f->t.p1, f->t.closed_upto, f->t.aux, f->t.nodes, f->t.node_acc2, f->t.free_stack, f->t.dirty, f->d_ctr, f->e.c_key,
                  f->e.c_wid, f->e.c_acc, f->e.c_count, f->e.c_seq, f->e.c_epoch, f->e.l_key, f->e.l_wid, f->e.l_val,
                  f->e.l_ts, f->e.l_seq, f->e.l_epoch, f->d_rmin, f->d_rmax, f->d_rbad, f->d_verdict, f->d_kflat,
                  f->d_ksorted, f->d_tsflat, f->d_tssorted, f->d_prefmax, f->d_idx, f->d_idxsorted, f->d_late, f->d_cub,
