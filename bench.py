@@ -190,7 +190,7 @@ def run_gpu(args):
     total_counts = int(em.closed_acc.sum()) + int(em_eof.closed_acc.sum())
     launches = int(st1.kernel_launches - st0.kernel_launches)
     fold_ms_avg = st1.sum_fold_ms / max(1, st1.fold_launches)
-    rows_per_fold = st1.rows_received / max(1, st1.fold_launches) if world == 1 else B  # ~B per rank after the exchange
+    rows_per_fold = st1.fold_rows / max(1, st1.fold_launches) if world == 1 else B  # ~B per rank after the exchange
     fold.close()
     for p in dk + dv:
         ctx.dev_free(p)

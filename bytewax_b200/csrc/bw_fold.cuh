@@ -351,7 +351,7 @@ __device__ __forceinline__ i64 bw_event_ts(const BatchView& bv, const u64* seg_s
 // items (or when the clock never advances on data, wait == forever).
 template <class C>
 __global__ void __launch_bounds__(BW_FOLD_THREADS, BW_FOLD_MINB)
-k_fold(BatchView bv, Table t, FoldParams p, u32 batch_no) {
+k_fold(BatchView bv, Table t, FoldParams p, u32 batch_no, u64 g_base) {
   __shared__ u64 seg_start[BW_MAX_WORLD + 1];
   __shared__ BlockSinks sinks;
   bw_sinks_init(&sinks);
@@ -414,7 +414,7 @@ k_fold(BatchView bv, Table t, FoldParams p, u32 batch_no) {
       if (hit0 || hit1) {
         u64 operand;
         bw_operand(p, raw[u], operand);
-        const u64 seq = ((u64)batch_no << 32) | g;
+        const u64 seq = ((u64)batch_no << 32) | (g_base + g);
         if (hit0) {
           bw_apply(C::op(p), &t.hot[slot[u]].acc0, operand);
           if (C::cnt(p)) bw_red_add_u64(&t.aux[slot[u]].cnt0, 1ULL);
@@ -443,7 +443,7 @@ k_fold(BatchView bv, Table t, FoldParams p, u32 batch_no) {
       u64 kk, op, rw;
       i64 ts;
       bw_load_event(bv, seg, off, p, kk, ts, op, rw);
-      bw_fold_event<C>(t, p, &sinks, kk, ts, op, ((u64)batch_no << 32) | g, batch_no, sinks.dq_slot[warp][i]);
+      bw_fold_event<C>(t, p, &sinks, kk, ts, op, ((u64)batch_no << 32) | (g_base + g), batch_no, sinks.dq_slot[warp][i]);
     }
     __syncwarp();
     if (lane == 0) sinks.n_defer[warp] = 0;

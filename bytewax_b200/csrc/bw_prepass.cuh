@@ -16,6 +16,7 @@
 
 #define BW_RANGE_ROWS 2048  // rows per warp-range
 #define BW_PRE_THREADS 256
+#define BW_PRE_MLP 8        // independent loads in flight per lane
 
 __device__ __forceinline__ i64 bw_load_ts(const BatchView& bv, int seg, u64 off, const FoldParams& p) {
   if (p.ts_from_value) {
@@ -47,35 +48,46 @@ k_prepass_ranges(BatchView bv, FoldParams p, i64* range_min, i64* range_max, u32
   for (u64 r = warp; r < nranges; r += nwarps) {
     i64 run_max = INT64_MIN, rmin = INT64_MAX;
     bool bad = false;
-    for (int c = 0; c < BW_RANGE_ROWS / 32; ++c) {
-      u64 g = r * BW_RANGE_ROWS + (u64)c * 32 + lane;
-      bool valid = g < total;
-      i64 ts = INT64_MIN;
-      if (valid) {
-        int seg = 0;
-        u64 off = g;
-        if (bv.nseg > 1) bw_locate(bv, seg_start, g, seg, off);
-        ts = bw_load_ts(bv, seg, off, p);
-      }
-      i64 incl = ts;
+    for (int c0 = 0; c0 < BW_RANGE_ROWS / 32; c0 += BW_PRE_MLP) {
+      // issue BW_PRE_MLP independent coalesced loads, then consume them in order
+      i64 tsv[BW_PRE_MLP];
+      bool val[BW_PRE_MLP];
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        i64 y = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d && y > incl) incl = y;
+      for (int j = 0; j < BW_PRE_MLP; ++j) {
+        const u64 g = r * BW_RANGE_ROWS + (u64)(c0 + j) * 32 + lane;
+        val[j] = g < total;
+        tsv[j] = INT64_MIN;
+        if (val[j]) {
+          int seg = 0;
+          u64 off = g;
+          if (bv.nseg > 1) bw_locate(bv, seg_start, g, seg, off);
+          tsv[j] = bw_load_ts(bv, seg, off, p);
+        }
       }
-      i64 excl = __shfl_up_sync(0xffffffffu, incl, 1);
-      if (lane == 0) excl = INT64_MIN;
-      i64 before = run_max > excl ? run_max : excl;
-      if (valid && ts < bw_sub_sat(before, p.wait_us)) bad = true;
-      i64 mn = valid ? ts : INT64_MAX;
 #pragma unroll
-      for (int d = 16; d; d >>= 1) {
-        i64 y = __shfl_xor_sync(0xffffffffu, mn, d);
-        if (y < mn) mn = y;
+      for (int j = 0; j < BW_PRE_MLP; ++j) {
+        const bool valid = val[j];
+        const i64 ts = tsv[j];
+        i64 incl = ts;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          i64 y = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d && y > incl) incl = y;
+        }
+        i64 excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = INT64_MIN;
+        i64 before = run_max > excl ? run_max : excl;
+        if (valid && ts < bw_sub_sat(before, p.wait_us)) bad = true;
+        i64 mn = valid ? ts : INT64_MAX;
+#pragma unroll
+        for (int d = 16; d; d >>= 1) {
+          i64 y = __shfl_xor_sync(0xffffffffu, mn, d);
+          if (y < mn) mn = y;
+        }
+        if (mn < rmin) rmin = mn;
+        i64 cm = __shfl_sync(0xffffffffu, incl, 31);
+        if (cm > run_max) run_max = cm;
       }
-      if (mn < rmin) rmin = mn;
-      i64 cm = __shfl_sync(0xffffffffu, incl, 31);
-      if (cm > run_max) run_max = cm;
     }
     bad = __any_sync(0xffffffffu, bad);
     if (lane == 0) {

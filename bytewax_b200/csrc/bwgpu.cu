@@ -129,7 +129,8 @@ struct bw_fold {
   u64 ordinal_base = 0;
   bool eof_done = false;
   int fold_grid = 0, close_grid = 0;
-  void (*fold_kernel)(BatchView, Table, FoldParams, u32) = nullptr;
+  void (*fold_kernel)(BatchView, Table, FoldParams, u32, u64) = nullptr;
+  u64 sub_rows = ~0ULL;  // optional fold + close granularity inside one activation (env BW_SUB_ROWS); measured slower on C1
   // multi-GPU exchange
   void* xchg_base = nullptr;  // one allocation, IPC-shared
   size_t xchg_bytes = 0;
@@ -318,7 +319,7 @@ static cudaError_t dmalloc(T** p, size_t n) {
 }
 
 // k_fold instantiations: accumulator op x watermark tracking (+ MEAN keeps counts)
-typedef void (*fold_kernel_t)(BatchView, Table, FoldParams, u32);
+typedef void (*fold_kernel_t)(BatchView, Table, FoldParams, u32, u64);
 template <int OP, int CNT>
 static fold_kernel_t pick_wm(bool wm) {
   return wm ? (fold_kernel_t)k_fold<FoldCfg<OP, 1, CNT>> : (fold_kernel_t)k_fold<FoldCfg<OP, 0, CNT>>;
@@ -413,6 +414,10 @@ static bw_status fold_alloc(bw_fold* f) {
   }
   int occ = 0;
   f->fold_kernel = pick_fold_kernel(f->p);
+  if (const char* e = getenv("BW_SUB_ROWS")) {
+    long long v = atoll(e);
+    if (v >= 1024) f->sub_rows = (u64)v;
+  }
   CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, f->fold_kernel, BW_FOLD_THREADS, 0));
   if (occ < 1) occ = 1;
   f->fold_grid = ctx->sm_count * occ;
@@ -801,18 +806,40 @@ static bw_status run_batch(bw_fold* f, const u64* d_keys, const void* d_vals, co
   }
   if (max_total > 0) {
     if (clean) {
-      EventPair* ep = next_timer(f);
-      if (ep) {
-        ep->rows = (ctx->world > 1) ? 0 : rows;
-        CU(ctx, cudaEventRecord(ep->a, f->s_compute));
-      }
       const u64 tile = (u64)BW_FOLD_THREADS * BW_FOLD_UNROLL;
-      int grid = (int)std::min<u64>((max_total + tile - 1) / tile, (u64)f->fold_grid);
-      f->fold_kernel<<<grid, BW_FOLD_THREADS, 0, f->s_compute>>>(bv, f->t, f->p, batch_no);
-      CU(ctx, cudaGetLastError());
-      if (ep) CU(ctx, cudaEventRecord(ep->b, f->s_compute));
-      f->st.kernel_launches++;
-      f->st.fold_launches++;
+      // Fold + close in sub-ranges of the activation (single GPU, host-known counts).
+      // Windows a key has left are closed -- and its new pane promoted into the hot slot --
+      // between sub-ranges, so events after a window boundary mostly take the one-sector
+      // path.  Rows are identical: a pane closed early would also close at the end (the
+      // watermark only grows, and the pane holding max_ts never closes).
+      const u64 step = (ctx->world == 1 && max_total > f->sub_rows) ? f->sub_rows : max_total;
+      for (u64 lo = 0; lo < max_total; lo += step) {
+        const u64 n = std::min<u64>(step, max_total - lo);
+        BatchView sub = bv;
+        if (step != max_total) {
+          sub.keys[0] = bv.keys[0] + lo;
+          if (bv.vals[0]) sub.vals[0] = (const char*)bv.vals[0] + lo * (u64)f->val_bytes;
+          if (bv.ts[0]) sub.ts[0] = bv.ts[0] + lo;
+          sub.h_counts[0] = n;
+          sub.max_rows = n;
+        }
+        EventPair* ep = next_timer(f);
+        if (ep) {
+          ep->rows = (ctx->world > 1) ? 0 : n;
+          CU(ctx, cudaEventRecord(ep->a, f->s_compute));
+        }
+        int grid = (int)std::min<u64>((n + tile - 1) / tile, (u64)f->fold_grid);
+        f->fold_kernel<<<grid, BW_FOLD_THREADS, 0, f->s_compute>>>(sub, f->t, f->p, batch_no, lo);
+        CU(ctx, cudaGetLastError());
+        if (ep) CU(ctx, cudaEventRecord(ep->b, f->s_compute));
+        f->st.kernel_launches++;
+        f->st.fold_launches++;
+        if (lo + n < max_total) {
+          k_close_dirty<<<f->close_grid, 256, 0, f->s_compute>>>(f->t, f->p, f->e, ord);
+          k_reset_dirty<<<1, 1, 0, f->s_compute>>>(f->t);
+          f->st.kernel_launches += 2;
+        }
+      }
     } else {
       u64 total = rows;
       if (ctx->world > 1) {

@@ -16,6 +16,8 @@ for s in range(steps):
     fold.ingest_device(dk, dv, None, B)
     ms = fold.time_end()
     st = fold.stats()
-    print(f"step {s:2d}: step {ms:.3f} ms  fold {st.last_fold_ms:.3f} ms  -> {B/st.last_fold_ms/1e6:.1f} G ev/s   nodes {st.pane_nodes_used} live {st.live_keys}")
+    fold_ms = st.sum_fold_ms
+    fold.reset_timers()
+    print(f"step {s:2d}: step {ms:.3f} ms  fold {fold_ms:.3f} ms  -> {B/fold_ms/1e6:.1f} G ev/s")
 em = fold.advance()
 print("closed rows", len(em.closed_key))
