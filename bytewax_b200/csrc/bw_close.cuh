@@ -247,9 +247,9 @@ __global__ void k_close_dirty(Table t, FoldParams p, EmitBufs e, u64 epoch) {
 }
 // EOF: every slot (including the BW_EMPTY_KEY alias slot at index capacity)
 __global__ void k_close_all(Table t, FoldParams p, EmitBufs e, u64 epoch) {
-  const u64 n = t.mask + 2;
+  const u64 n = t.cap + 1;
   for (u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += (u64)gridDim.x * blockDim.x) {
-    if (s <= t.mask && t.hot[s].key == BW_EMPTY_KEY) continue;
+    if (s < t.cap && t.hot[s].key == BW_EMPTY_KEY) continue;
     bw_close_key(t, p, e, s, true, epoch);
   }
 }

@@ -143,7 +143,7 @@ struct Table {
   u64* node_acc2;
   u32* free_stack;
   u32* dirty;      // list of slot indices with possibly closable panes
-  u64 mask;        // capacity - 1 (capacity is a power of two); slot `capacity` is the BW_EMPTY_KEY alias slot
+  u64 cap;         // number of slots (any size); slot `cap` is the BW_EMPTY_KEY alias slot
   u32 pool_cap;
   // device counters
   struct Counters* ctr;
@@ -162,6 +162,14 @@ struct Counters {
   u32 pad;
 };
 
+// home slot = high part of hash * capacity (no power-of-two constraint on the table)
+__host__ __device__ __forceinline__ u64 bw_slot_of_hash(u64 h, u64 cap) {
+#ifdef __CUDA_ARCH__
+  return __umul64hi(h, cap);
+#else
+  return (u64)(((unsigned __int128)h * cap) >> 64);
+#endif
+}
 __device__ __forceinline__ void bw_raise(Counters* c, u32 status) { atomicCAS(&c->err, 0u, status); }
 
 // up to BW_MAX_WORLD column segments forming one activation in arrival order

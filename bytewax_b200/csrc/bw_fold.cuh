@@ -84,7 +84,7 @@ __device__ __forceinline__ i64 bw_ld_i64_coherent(const i64* p) {
 }
 
 __device__ __forceinline__ u64 bw_home_slot(const Table& t, u64 key) {
-  return (key == BW_EMPTY_KEY) ? (t.mask + 1) : (bw_mix64(key) & t.mask);
+  return (key == BW_EMPTY_KEY) ? t.cap : bw_slot_of_hash(bw_mix64(key), t.cap);
 }
 
 // Find (or create) the slot of `key`, starting at its home slot.  Four
@@ -98,14 +98,19 @@ __device__ __forceinline__ u64 bw_find_slot(const Table& t, BlockSinks* sk, u64 
     bw_ld_slot(t.hot + s, k, max_ts, wt0, a);
     return s;
   }
-  for (u64 probe = 0; probe <= t.mask; probe += BW_PROBE_WIDTH) {
+  for (u64 probe = 0; probe < t.cap; probe += BW_PROBE_WIDTH) {
     u64 k[BW_PROBE_WIDTH], a[BW_PROBE_WIDTH];
     i64 m[BW_PROBE_WIDTH], w[BW_PROBE_WIDTH];
 #pragma unroll
-    for (int j = 0; j < BW_PROBE_WIDTH; ++j) bw_ld_slot(t.hot + ((s + j) & t.mask), k[j], m[j], w[j], a[j]);
+    for (int j = 0; j < BW_PROBE_WIDTH; ++j) {
+      u64 sj = s + j;
+      if (sj >= t.cap) sj -= t.cap;
+      bw_ld_slot(t.hot + sj, k[j], m[j], w[j], a[j]);
+    }
 #pragma unroll
     for (int j = 0; j < BW_PROBE_WIDTH; ++j) {
-      const u64 sj = (s + j) & t.mask;
+      u64 sj = s + j;
+      if (sj >= t.cap) sj -= t.cap;
       if (k[j] == key) {
         max_ts = m[j];
         wt0 = w[j];
@@ -129,7 +134,8 @@ __device__ __forceinline__ u64 bw_find_slot(const Table& t, BlockSinks* sk, u64 
         // another key took it: keep probing past it
       }
     }
-    s = (s + BW_PROBE_WIDTH) & t.mask;
+    s += BW_PROBE_WIDTH;
+    if (s >= t.cap) s -= t.cap;
   }
   return ~0ULL;
 }

@@ -45,12 +45,12 @@ __global__ void k_gather_i64(const i64* src, const u32* idx, i64* dst, u64 n) {
 
 // read-only lookup of a key's running max ts (INT64_MIN when the key has no state)
 __device__ __forceinline__ i64 bw_lookup_max_ts(const Table& t, u64 key) {
-  u64 s = (key == BW_EMPTY_KEY) ? (t.mask + 1) : (bw_mix64(key) & t.mask);
-  for (u64 probe = 0; probe <= t.mask; ++probe) {
+  u64 s = (key == BW_EMPTY_KEY) ? t.cap : bw_slot_of_hash(bw_mix64(key), t.cap);
+  for (u64 probe = 0; probe < t.cap; ++probe) {
     u64 k = t.hot[s].key;
     if (k == key) return t.hot[s].max_ts;
     if (k == BW_EMPTY_KEY) return INT64_MIN;
-    s = (s + 1) & t.mask;
+    if (++s >= t.cap) s = 0;
   }
   return INT64_MIN;
 }

@@ -156,7 +156,7 @@ struct bw_fold {
 // small kernels
 // ---------------------------------------------------------------------------
 __global__ void k_init_table(Table t, u64 acc_identity) {
-  const u64 n = t.mask + 2;
+  const u64 n = t.cap + 1;
   for (u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += (u64)gridDim.x * blockDim.x) {
     HotSlot h;
     h.key = BW_EMPTY_KEY;
@@ -341,11 +341,17 @@ static fold_kernel_t pick_fold_kernel(const FoldParams& p) {
 static bw_status fold_alloc(bw_fold* f) {
   bw_ctx* ctx = f->ctx;
   const bw_fold_spec& s = f->spec;
-  // table: power of two >= 2 * hint, at least 1024
-  u64 cap = 1024;
-  while (cap < 2 * std::max<u64>(s.capacity_hint, 1)) cap <<= 1;
+  // table: capacity_hint / load factor slots (any size; load 0.5 by default, env BW_LOAD_PCT),
+  // rounded up to a multiple of 4 slots (one 128-byte line of hot slots)
+  int load_pct = 50;
+  if (const char* e = getenv("BW_LOAD_PCT")) {
+    int v = atoi(e);
+    if (v >= 10 && v <= 90) load_pct = v;
+  }
+  u64 cap = std::max<u64>(1024, (std::max<u64>(s.capacity_hint, 1) * 100 + load_pct - 1) / load_pct);
+  cap = (cap + 3) & ~3ULL;
   if (cap > (1ULL << 31)) FAIL(f, BW_ERR_SPEC, "capacity_hint too large");
-  f->t.mask = cap - 1;
+  f->t.cap = cap;
   {
     // overflow pane nodes: panes a key can hold beyond its two direct slots
     const i64 per_window = f->p.panes_per_window;
@@ -394,24 +400,9 @@ static bw_status fold_alloc(bw_fold* f) {
   CU(ctx, cudaEventCreateWithFlags(&f->ev_in, cudaEventDisableTiming));
   CU(ctx, cudaEventCreateWithFlags(&f->ev_pre, cudaEventDisableTiming));
   CU(ctx, cudaEventCreateWithFlags(&f->ev_h2d, cudaEventDisableTiming));
-  // Pin the hot slots (one sector per key) in L2: persisting access window on the compute stream.
-  {
-    cudaDeviceProp prop;
-    CU(ctx, cudaGetDeviceProperties(&prop, ctx->device));
-    const size_t hot_bytes = (cap + 1) * sizeof(HotSlot);
-    if (prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
-      const size_t persist = std::min<size_t>(hot_bytes, (size_t)prop.persistingL2CacheMaxSize);
-      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist);
-      cudaStreamAttrValue av;
-      memset(&av, 0, sizeof av);
-      av.accessPolicyWindow.base_ptr = f->t.hot;
-      av.accessPolicyWindow.num_bytes = std::min<size_t>(hot_bytes, (size_t)prop.accessPolicyMaxWindowSize);
-      av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)persist / (double)av.accessPolicyWindow.num_bytes);
-      av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-      av.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
-      if (cudaStreamSetAttribute(f->s_compute, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) cudaGetLastError();
-    }
-  }
+  // No persisting-L2 carve-out: measured on this part (profiles/r01_notes.md) a 64 MiB persisting
+  // window on the hot slots leaves too little normal L2 for the second-pane array and slows
+  // window-boundary activations by 15-30 %; plain LRU + evict_first input loads is faster.
   int occ = 0;
   f->fold_kernel = pick_fold_kernel(f->p);
   if (const char* e = getenv("BW_SUB_ROWS")) {

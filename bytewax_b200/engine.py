@@ -1,0 +1,600 @@
+"""Host engine: executes a ``Dataflow`` step tree (the role of ``bytewax._bytewax``).
+
+A small single-process restatement of what the reference's Rust engine does
+with the eight core operators (src/worker.rs:255-497, src/operators.rs,
+src/inputs.rs, src/outputs.rs; rules collected in SURVEY.md Appendix A):
+first data epoch is 1, one ``next_batch`` per partition per activation, one
+``mapper(list)`` call per batch, ``stateful_batch`` groups an epoch's items by
+key and walks keys in ascending string order, ``on_eof`` once every input is
+exhausted, engine errors surface as ``BytewaxRuntimeError`` chained to the
+user's exception.  Workers are logical (``worker_count_per_proc`` shards state
+by key inside one thread); TCP clusters are out of scope.
+
+Arbitrary Python logic always runs here, on the host.  The one exception is a
+``stateful_batch`` whose builder carries a ``GpuFoldPlan`` (numeric windowed
+folds made by ``bytewax_b200.operators.windowing``): with the GPU path enabled
+(``BYTEWAX_B200_GPU=1`` or ``run_main(..., gpu=True)``) whole epochs are
+handed to ``libbwgpu`` instead of calling Python per key.
+"""
+
+from __future__ import annotations
+
+import os
+import time
+from collections import defaultdict
+from datetime import datetime, timedelta, timezone
+from typing import Any, Dict, List, Optional, Tuple
+
+from bytewax_b200.dataflow import Dataflow, _CoreOperator
+from bytewax_b200.errors import BytewaxRuntimeError
+from bytewax_b200.inputs import AbortExecution, DynamicSource, FixedPartitionedSource, KeyedColumns
+from bytewax_b200.outputs import DynamicSink, FixedPartitionedSink
+
+EPOCH = datetime(1970, 1, 1, tzinfo=timezone.utc)
+_CORE = {"branch", "flat_map_batch", "input", "inspect_debug", "merge", "output", "redistribute", "stateful_batch", "_noop"}
+
+
+def _us(dt: datetime) -> int:
+    d = dt - EPOCH
+    return (d.days * 86400 + d.seconds) * 1_000_000 + d.microseconds
+
+
+def _dt(us: int) -> datetime:
+    return EPOCH + timedelta(microseconds=int(us))
+
+
+def _route(key: str, workers: int) -> int:
+    if workers == 1:
+        return 0
+    from zlib import crc32
+
+    return crc32(key.encode()) % workers
+
+
+def _core_steps(flow: Dataflow) -> list:
+    out = []
+
+    def walk(steps):
+        for st in steps:
+            if isinstance(st, _CoreOperator):
+                name = type(st).__name__
+                if name not in _CORE:
+                    raise TypeError(f"Unknown core operator {name!r}")  # src/worker.rs:462-465
+                out.append(st)
+            else:
+                walk(st.substeps)
+
+    walk(flow.substeps)
+    return out
+
+
+def _reraise(msg: str, ex: BaseException):
+    if isinstance(ex, KeyboardInterrupt):
+        raise ex
+    raise BytewaxRuntimeError(msg) from ex
+
+
+# ---------------------------------------------------------------------------
+# GPU-planned windowing step
+# ---------------------------------------------------------------------------
+
+_gpu_ctx = None
+
+
+def _get_gpu_ctx():
+    global _gpu_ctx
+    if _gpu_ctx is None:
+        from bytewax_b200 import gpu
+
+        _gpu_ctx = gpu.Context(int(os.environ.get("BYTEWAX_B200_DEVICE", "0")))
+    return _gpu_ctx
+
+
+class _GpuWindowStep:
+    """One worker's ``stateful_batch`` of a numeric windowed fold, on ``libbwgpu``."""
+
+    def __init__(self, step_id: str, plan):
+        import numpy as np
+
+        from bytewax_b200 import gpu
+        from bytewax_b200.operators.windowing import SlidingWindower
+
+        self.np, self.plan, self.step_id = np, plan, step_id
+        w = plan.windower
+        length = w.length
+        offset = w.offset if isinstance(w, SlidingWindower) else w.length
+        td_us = lambda td: (td.days * 86400 + td.seconds) * 1_000_000 + td.microseconds  # noqa: E731
+        wait = plan.clock.wait_for_system_duration
+        wait_us = None if wait >= timedelta(days=365 * 200) else td_us(wait)
+        self.float_vals = False
+        self.fold = None
+        self._mk = lambda dtype: gpu.WindowFold(
+            _get_gpu_ctx(), plan.reduction, td_us(length), td_us(offset), _us(w.align_to), wait_us, val_dtype=dtype,
+            ordered=plan.ordered, capacity_hint=int(os.environ.get("BYTEWAX_B200_KEYS", 1 << 20)),
+            max_batch_rows=int(os.environ.get("BYTEWAX_B200_BATCH", 1 << 22)), max_emit_rows=1 << 22, max_late_rows=1 << 20)
+        self.key_ids: Dict[str, int] = {}
+        self.id_keys: Dict[int, str] = {}
+        self.resort = False
+        self.originals: Dict[int, Any] = {}
+
+    def _key_id(self, k: str) -> int:
+        if k.isdigit() and (k == "0" or k[0] != "0") and len(k) < 20:
+            return int(k)  # canonical decimal text: the id is the number itself
+        i = self.key_ids.get(k)
+        if i is None:
+            i = self.key_ids[k] = (1 << 63) + len(self.key_ids)
+            self.id_keys[i] = k
+            self.resort = True
+        return i
+
+    def _key_str(self, i: int) -> str:
+        return self.id_keys.get(i) or str(i)
+
+    def on_epoch(self, epoch: int, items: list) -> list:
+        np, plan = self.np, self.plan
+        keys, ts, vals, orig = [], [], [], []
+        cols = [it for it in items if isinstance(it, tuple) and len(it) == 2 and isinstance(it[1], KeyedColumns)]
+        if cols and len(cols) != len(items):
+            raise TypeError(f"step {self.step_id!r}: mixing KeyedColumns and per-item values in one batch")
+        if cols:
+            k = np.concatenate([c[1].keys for c in cols]).astype(np.uint64)
+            t = np.concatenate([c[1].ts_us for c in cols]).astype(np.int64)
+            v = None if cols[0][1].vals is None else np.concatenate([c[1].vals for c in cols])
+        else:
+            getter = plan.clock.ts_getter
+            for item in items:
+                try:
+                    key, value = item
+                except (TypeError, ValueError) as ex:
+                    raise TypeError(f"step {self.step_id!r} requires `(key, value)` 2-tuple as upstream for routing; got a {type(item)!r} instead") from ex
+                if not isinstance(key, str):
+                    raise TypeError(f"step {self.step_id!r} requires `str` keys in `(key, value)` from upstream; got a {type(key)!r} instead")
+                keys.append(self._key_id(key))
+                ts.append(_us(getter(value)))
+                if plan.reduction == "count":
+                    vals.append(len(orig))  # the value column carries the arrival index (late rows map back)
+                    orig.append(value)
+                else:
+                    num = plan.value_of(value)
+                    if isinstance(num, bool) or not isinstance(num, (int, float)):
+                        raise TypeError(f"step {self.step_id!r}: the CUDA fold needs numeric values; got a {type(num)!r}")
+                    vals.append(num)
+            k, t = np.array(keys, dtype=np.uint64), np.array(ts, dtype=np.int64)
+            v = np.array(vals) if vals else np.zeros(0, dtype=np.int64)
+        if self.fold is None:
+            self.float_vals = v is not None and v.dtype.kind == "f"
+            self.fold = self._mk("f64" if self.float_vals else "i64")
+        if v is not None and v.dtype.kind == "f" and not self.float_vals:
+            raise TypeError(f"step {self.step_id!r}: value type changed from integer to float mid-stream")
+        self.fold.ingest(k, v, t, epoch)
+        return self._rows(self.fold.advance(), orig)
+
+    def on_eof(self) -> list:
+        if self.fold is None:
+            return []
+        out = self._rows(self.fold.eof(), [])
+        self.fold.close()
+        self.fold = None
+        return out
+
+    def _rows(self, em, orig) -> list:
+        from bytewax_b200.operators.windowing import WindowMetadata
+
+        rows = []
+        for k, w, val in zip(em.late_key.tolist(), em.late_window_id.tolist(), em.late_val.tolist()):
+            if self.plan.reduction == "count" and orig:
+                val = orig[int(val)]
+            rows.append((self._key_str(k), (w, "L", val)))
+        closed = []
+        for k, w, acc, ep in zip(em.closed_key.tolist(), em.closed_window_id.tolist(), em.closed_acc.tolist(), em.closed_epoch.tolist()):
+            closed.append((ep, self._key_str(k), w, acc))
+        if self.resort:
+            # interned (non-numeric) keys: restore ascending key-string order per activation; stable
+            closed.sort(key=lambda r: (r[0], r[1]))
+        for _ep, ks, w, acc in closed:
+            o, c = self.fold.window_bounds(w)
+            rows.append((ks, (w, "E", acc)))
+            rows.append((ks, (w, "M", WindowMetadata(_dt(o), _dt(c)))))
+        return rows
+
+
+# ---------------------------------------------------------------------------
+# the engine proper
+# ---------------------------------------------------------------------------
+
+
+class _InputPart:
+    __slots__ = ("part", "worker", "epoch", "started", "eof", "awake_at")
+
+    def __init__(self, part, worker):
+        self.part, self.worker, self.epoch, self.started, self.eof, self.awake_at = part, worker, 1, time.monotonic(), False, None
+
+
+class _Run:
+    def __init__(self, flow: Dataflow, workers: int, epoch_interval: Optional[timedelta], gpu: Optional[bool]):
+        self.flow, self.W = flow, workers
+        self.interval = (epoch_interval if epoch_interval is not None else timedelta(seconds=10)).total_seconds()
+        self.gpu = gpu if gpu is not None else os.environ.get("BYTEWAX_B200_GPU", "0") == "1"
+        self.steps = _core_steps(flow)
+        names = [type(s).__name__ for s in self.steps]
+        if "input" not in names:
+            raise ValueError("Dataflow needs to contain at least one input step; add with `bytewax.operators.input`")
+        if "output" not in names and "inspect_debug" not in names:
+            raise ValueError("Dataflow needs to contain at least one output or inspect step; add with `bytewax.operators.output` or `bytewax.operators.inspect`")
+        seen = set()
+        for st in self.steps:
+            for name in st.dwn_names:
+                port = getattr(st, name)
+                for sid in ([port.stream_id] if hasattr(port, "stream_id") else list(port.stream_ids.values())):
+                    if sid in seen:
+                        raise ValueError(f"duplicate stream ID {sid!r}")
+                    seen.add(sid)
+        # buffers[stream_id][worker] -> list of (epoch, [items])
+        self.buf: Dict[str, List[list]] = defaultdict(lambda: [[] for _ in range(self.W)])
+        self.inputs: Dict[str, List[_InputPart]] = {}
+        self.sinks: Dict[str, Any] = {}
+        self.state: Dict[str, Any] = {}
+        self.rr = 0
+        self.abort = False
+
+    # -- helpers -------------------------------------------------------------
+    def _emit(self, port, worker: int, epoch: int, items: list):
+        if items:
+            self.buf[port.stream_id][worker].append((epoch, items))
+
+    def _take(self, port) -> List[list]:
+        sid = port.stream_id
+        if sid not in self.buf:
+            return [[] for _ in range(self.W)]
+        got = self.buf[sid]
+        return got
+
+    # -- per-step execution ----------------------------------------------------
+    def _run_input(self, st, now_mono):
+        parts = self.inputs.get(st.step_id)
+        if parts is None:
+            src, parts = st.source, []
+            try:
+                if isinstance(src, FixedPartitionedSource):
+                    for i, name in enumerate(src.list_parts()):
+                        parts.append(_InputPart(src.build_part(st.step_id, name, None), i % self.W))
+                elif isinstance(src, DynamicSource):
+                    for w in range(self.W):
+                        parts.append(_InputPart(src.build(st.step_id, w, self.W), w))
+                else:
+                    raise TypeError("unknown source type; must subclass `FixedPartitionedSource` or `DynamicSource`")
+            except Exception as ex:
+                _reraise(f"error building input in step {st.step_id}", ex)
+            self.inputs[st.step_id] = parts
+        for ip in parts:
+            if ip.eof:
+                continue
+            if ip.awake_at is not None and datetime.now(timezone.utc) < ip.awake_at:
+                continue
+            try:
+                batch = list(ip.part.next_batch())
+            except StopIteration:
+                ip.eof = True
+                batch = None
+            except AbortExecution:
+                self.abort = True
+                return
+            except Exception as ex:
+                _reraise(f"error calling `next_batch` in step {st.step_id}", ex)
+            if batch is not None:
+                self._emit(st.down, ip.worker, ip.epoch, batch)
+                try:
+                    ip.awake_at = ip.part.next_awake()
+                except Exception as ex:
+                    _reraise(f"error calling `next_awake` in step {st.step_id}", ex)
+                if ip.awake_at is None and not batch:
+                    ip.awake_at = datetime.now(timezone.utc) + timedelta(milliseconds=1)
+            if ip.eof or now_mono - ip.started >= self.interval:
+                ip.epoch += 1
+                ip.started = now_mono
+
+    def _all_eof(self) -> bool:
+        return all(ip.eof for parts in self.inputs.values() for ip in parts) and len(self.inputs) == sum(
+            1 for s in self.steps if type(s).__name__ == "input")
+
+    def _run_step(self, st, eof: bool):
+        name = type(st).__name__
+        if name == "input":
+            return
+        if name == "flat_map_batch":
+            for w, chunks in enumerate(self._take(st.up)):
+                for epoch, items in chunks:
+                    try:
+                        out = st.mapper(items)
+                        out = list(out)
+                    except Exception as ex:
+                        _reraise(f"error calling `mapper` in step {st.step_id}", ex)
+                    self._emit(st.down, w, epoch, out)
+        elif name == "branch":
+            for w, chunks in enumerate(self._take(st.up)):
+                for epoch, items in chunks:
+                    trues, falses = [], []
+                    for item in items:
+                        try:
+                            keep = st.predicate(item)
+                        except Exception as ex:
+                            _reraise(f"error calling `predicate` in step {st.step_id}", ex)
+                        if not isinstance(keep, bool):
+                            _reraise(f"error in step {st.step_id}", TypeError(
+                                f"return value of `predicate` in step {st.step_id} must be a `bool`; got a {type(keep)!r} instead"))
+                        (trues if keep else falses).append(item)
+                    self._emit(st.trues, w, epoch, trues)
+                    self._emit(st.falses, w, epoch, falses)
+        elif name == "inspect_debug":
+            for w, chunks in enumerate(self._take(st.up)):
+                for epoch, items in chunks:
+                    for item in items:
+                        try:
+                            st.inspector(st.step_id, item, epoch, w)
+                        except Exception as ex:
+                            _reraise(f"error calling `inspector` in step {st.step_id}", ex)
+                    self._emit(st.down, w, epoch, items)
+        elif name == "merge":
+            for sid in st.ups.stream_ids.values():
+                if sid in self.buf:
+                    for w, chunks in enumerate(self.buf[sid]):
+                        for epoch, items in chunks:
+                            self._emit(st.down, w, epoch, items)
+        elif name == "redistribute":
+            for w, chunks in enumerate(self._take(st.up)):
+                for epoch, items in chunks:
+                    per = [[] for _ in range(self.W)]
+                    for item in items:
+                        per[self.rr % self.W].append(item)
+                        self.rr += 1
+                    for dw, its in enumerate(per):
+                        self._emit(st.down, dw, epoch, its)
+        elif name == "output":
+            self._run_output(st)
+        elif name == "stateful_batch":
+            self._run_stateful(st, eof)
+        elif name == "_noop":
+            for w, chunks in enumerate(self._take(st.up)):
+                for epoch, items in chunks:
+                    self._emit(st.down, w, epoch, items)
+
+    def _run_output(self, st):
+        sink = st.sink
+        parts = self.sinks.get(st.step_id)
+        if parts is None:
+            parts = self.sinks[st.step_id] = {}
+        for w, chunks in enumerate(self._take(st.up)):
+            for _epoch, items in chunks:
+                try:
+                    if isinstance(sink, DynamicSink):
+                        part = parts.get(w)
+                        if part is None:
+                            part = parts[w] = sink.build(st.step_id, w, self.W)
+                        part.write_batch(items)
+                    elif isinstance(sink, FixedPartitionedSink):
+                        names = parts.get("__names__")
+                        if names is None:
+                            names = parts["__names__"] = sink.list_parts()
+                        per: Dict[str, list] = defaultdict(list)
+                        for item in items:
+                            try:
+                                key, value = item
+                            except (TypeError, ValueError) as ex:
+                                raise TypeError(f"step {st.step_id!r} requires `(key, value)` 2-tuple as upstream for routing; got a {type(item)!r} instead") from ex
+                            if not isinstance(key, str):
+                                raise TypeError(f"step {st.step_id!r} requires `str` keys in `(key, value)` from upstream; got a {type(key)!r} instead")
+                            per[names[sink.part_fn(key) % len(names)]].append(value)
+                        for pname, values in per.items():
+                            part = parts.get(pname)
+                            if part is None:
+                                part = parts[pname] = sink.build_part(st.step_id, pname, None)
+                            part.write_batch(values)
+                    else:
+                        raise TypeError("unknown sink type; must subclass `FixedPartitionedSink` or `DynamicSink`")
+                except Exception as ex:
+                    _reraise(f"error writing output in step {st.step_id}", ex)
+
+    def _run_stateful(self, st, eof: bool):
+        S = self.state.get(st.step_id)
+        plan = getattr(st.builder, "_gpu_plan", None) if self.gpu else None
+        if S is None:
+            S = self.state[st.step_id] = {
+                "logics": [dict() for _ in range(self.W)], "sched": [dict() for _ in range(self.W)],
+                "gpu": [(_GpuWindowStep(st.step_id, plan) if plan is not None else None) for _ in range(self.W)], "eof_done": False,
+            }
+        # exchange: route every item to the worker owning its key (src/operators.rs:582-591)
+        routed: List[Dict[int, list]] = [defaultdict(list) for _ in range(self.W)]
+        for _w, chunks in enumerate(self._take(st.up)):
+            for epoch, items in chunks:
+                for item in items:
+                    if plan is not None and isinstance(item, tuple) and len(item) == 2 and isinstance(item[1], KeyedColumns):
+                        routed[0][epoch].append(item)
+                        continue
+                    try:
+                        key, _value = item
+                    except (TypeError, ValueError):
+                        _reraise(f"error in step {st.step_id}", TypeError(
+                            f"step {st.step_id!r} requires `(key, value)` 2-tuple as upstream for routing; got a {type(item)!r} instead"))
+                    if not isinstance(key, str):
+                        _reraise(f"error in step {st.step_id}", TypeError(
+                            f"step {st.step_id!r} requires `str` keys in `(key, value)` from upstream; got a {type(key)!r} instead"))
+                    routed[_route(key, self.W)][epoch].append(item)
+        now = datetime.now(timezone.utc)
+        for w in range(self.W):
+            g = S["gpu"][w]
+            last_epoch = 0
+            for epoch in sorted(routed[w]):
+                last_epoch = epoch
+                items = routed[w][epoch]
+                if g is not None:
+                    try:
+                        self._emit(st.down, w, epoch, g.on_epoch(epoch, items))
+                    except Exception as ex:
+                        _reraise(f"error in the CUDA fold of step {st.step_id}", ex)
+                    continue
+                self._host_on_batch(st, S, w, epoch, items)
+            if g is None:
+                self._host_notify(st, S, w, last_epoch, now)
+            if eof and not S["eof_done"]:
+                ep = last_epoch or max((ip.epoch for parts in self.inputs.values() for ip in parts), default=1)
+                if g is not None:
+                    try:
+                        self._emit(st.down, w, ep, g.on_eof())
+                    except Exception as ex:
+                        _reraise(f"error in the CUDA fold of step {st.step_id}", ex)
+                else:
+                    self._host_on_eof(st, S, w, ep)
+        if eof:
+            S["eof_done"] = True
+
+    def _logic_call(self, st, what, key, fn, *a):
+        try:
+            res = fn(*a)
+        except Exception as ex:
+            _reraise(f"error calling `StatefulBatchLogic.{what}` in step {st.step_id} for key {key}", ex)
+        if what in ("on_batch", "on_notify", "on_eof"):
+            try:
+                emit, done = res
+                emit = list(emit)
+            except (TypeError, ValueError) as ex:
+                _reraise(f"error in step {st.step_id}", TypeError(
+                    f"return value of `{what}` in step {st.step_id} must be a 2-tuple of `(emit, is_complete)`; got a {type(res)!r} instead"))
+            if not isinstance(done, bool):
+                _reraise(f"error in step {st.step_id}", TypeError(f"`is_complete` in step {st.step_id} must be a `bool`"))
+            return emit, done
+        return res
+
+    def _host_on_batch(self, st, S, w, epoch, items):
+        logics, sched = S["logics"][w], S["sched"][w]
+        grouped: Dict[str, list] = {}
+        for key, value in items:
+            grouped.setdefault(key, []).append(value)
+        out, awoken = [], []
+        for key in sorted(grouped):  # BTreeMap order, src/operators.rs:758-767
+            logic = logics.get(key)
+            if logic is None:
+                try:
+                    logic = logics[key] = st.builder(None)
+                except Exception as ex:
+                    _reraise(f"error calling `builder` in step {st.step_id} for key {key}", ex)
+            emit, done = self._logic_call(st, "on_batch", key, logic.on_batch, grouped[key])
+            out.extend((key, v) for v in emit)
+            if done:
+                del logics[key]
+                sched.pop(key, None)
+            awoken.append(key)
+        self._emit(st.down, w, epoch, out)
+        for key in awoken:
+            logic = logics.get(key)
+            if logic is not None:
+                at = self._logic_call(st, "notify_at", key, logic.notify_at)
+                if at is not None:
+                    sched[key] = at
+
+    def _host_notify(self, st, S, w, epoch, now):
+        logics, sched = S["logics"][w], S["sched"][w]
+        due = sorted(k for k, at in sched.items() if at <= now)
+        if not due:
+            return
+        out = []
+        for key in due:
+            logic = logics[key]
+            emit, done = self._logic_call(st, "on_notify", key, logic.on_notify)
+            out.extend((key, v) for v in emit)
+            sched.pop(key, None)
+            if done:
+                del logics[key]
+            else:
+                at = self._logic_call(st, "notify_at", key, logic.notify_at)
+                if at is not None:
+                    sched[key] = at
+        ep = epoch or max((ip.epoch for parts in self.inputs.values() for ip in parts), default=1)
+        self._emit(st.down, w, ep, out)
+
+    def _host_on_eof(self, st, S, w, epoch):
+        logics = S["logics"][w]
+        out = []
+        for key in sorted(logics):  # src/operators.rs:862-894
+            emit, done = self._logic_call(st, "on_eof", key, logics[key].on_eof)
+            out.extend((key, v) for v in emit)
+            if done:
+                logics[key] = None
+        for key in [k for k, v in logics.items() if v is None]:
+            del logics[key]
+        self._emit(st.down, w, epoch, out)
+
+    def _next_wakeup(self) -> Optional[datetime]:
+        times = [ip.awake_at for parts in self.inputs.values() for ip in parts if not ip.eof and ip.awake_at is not None]
+        for S in self.state.values():
+            for sched in S["sched"]:
+                times.extend(sched.values())
+        return min(times) if times else None
+
+    # -- main loop ---------------------------------------------------------------
+    def run(self):
+        try:
+            while True:
+                now_mono = time.monotonic()
+                for st in self.steps:
+                    if type(st).__name__ == "input":
+                        self._run_input(st, now_mono)
+                        if self.abort:
+                            return
+                eof = self._all_eof()
+                for st in self.steps:
+                    self._run_step(st, eof)
+                moved = any(chunks for per in self.buf.values() for chunks in per)
+                self.buf.clear()
+                if eof:
+                    return
+                if not moved:
+                    wake = self._next_wakeup()
+                    if wake is not None:
+                        delay = (wake - datetime.now(timezone.utc)).total_seconds()
+                        if delay > 0:
+                            time.sleep(min(delay, 0.05))
+        finally:
+            for parts in self.inputs.values():
+                for ip in parts:
+                    try:
+                        ip.part.close()
+                    except Exception:
+                        pass
+            for parts in self.sinks.values():
+                for name, part in parts.items():
+                    if name != "__names__":
+                        try:
+                            part.close()
+                        except Exception:
+                            pass
+            for S in self.state.values():
+                for g in S["gpu"]:
+                    if g is not None and g.fold is not None:
+                        g.fold.close()
+
+
+def run_main(flow: Dataflow, *, epoch_interval: Optional[timedelta] = None, recovery_config=None, gpu: Optional[bool] = None) -> None:
+    """Run a dataflow in the calling thread on one worker (src/run.rs:110-119)."""
+    if recovery_config is not None:
+        raise NotImplementedError("recovery is out of scope of this engine (SURVEY.md section 2 row 12)")
+    _Run(flow, 1, epoch_interval, gpu).run()
+
+
+def cluster_main(flow: Dataflow, addresses: Optional[List[str]], proc_id: int, *, epoch_interval: Optional[timedelta] = None,
+                 recovery_config=None, worker_count_per_proc: int = 1, gpu: Optional[bool] = None) -> None:
+    """Run with ``worker_count_per_proc`` logical workers in this process (src/run.rs:238-250)."""
+    if addresses:
+        raise NotImplementedError("multi-process TCP clusters are out of scope; GPUs scale through libbwgpu's exchange")
+    if recovery_config is not None:
+        raise NotImplementedError("recovery is out of scope of this engine (SURVEY.md section 2 row 12)")
+    _Run(flow, max(1, worker_count_per_proc), epoch_interval, gpu).run()
+
+
+def cli_main(flow: Dataflow, *, workers_per_process: int = 1, process_id: Optional[int] = None, addresses: Optional[List[str]] = None,
+             epoch_interval: Optional[timedelta] = None, recovery_config=None) -> None:
+    """Entry point of ``python -m bytewax_b200.run`` (src/run.rs:357-394)."""
+    if workers_per_process == 1 and not addresses:
+        run_main(flow, epoch_interval=epoch_interval, recovery_config=recovery_config)
+    else:
+        cluster_main(flow, addresses or [], process_id or 0, epoch_interval=epoch_interval, recovery_config=recovery_config,
+                     worker_count_per_proc=workers_per_process)

@@ -1,0 +1,198 @@
+"""Input sources: host-side mirror of ``bytewax.inputs`` (pysrc/bytewax/inputs.py).
+
+Abstract base classes only -- the I/O itself is out of the GPU path's scope
+(SURVEY.md section 2 row 10); they exist so flows written against the reference load
+unchanged.  ``KeyedColumns`` is this repository's addition: a columnar batch a
+source may yield so a whole epoch reaches the CUDA fold without per-item
+Python objects.
+"""
+
+from __future__ import annotations
+
+import asyncio
+from abc import ABC, abstractmethod
+from dataclasses import dataclass
+from datetime import datetime, timedelta, timezone
+from itertools import islice
+from typing import Any, Callable, Generic, Iterable, Iterator, List, Optional, TypeVar
+
+X = TypeVar("X")
+S = TypeVar("S")
+
+
+class AbortExecution(RuntimeError):
+    """Raise from ``next_batch`` to stop the run without EOF processing (src/inputs.rs:478-481)."""
+
+
+class Source(ABC, Generic[X]):  # noqa: B024
+    """A location to read items from."""
+
+
+class StatefulSourcePartition(ABC, Generic[X, S]):
+    @abstractmethod
+    def next_batch(self) -> Iterable[X]: ...
+
+    def next_awake(self) -> Optional[datetime]:
+        return None
+
+    @abstractmethod
+    def snapshot(self) -> S: ...
+
+    def close(self) -> None:
+        return
+
+
+class FixedPartitionedSource(Source[X], Generic[X, S]):
+    @abstractmethod
+    def list_parts(self) -> List[str]: ...
+
+    @abstractmethod
+    def build_part(self, step_id: str, for_part: str, resume_state: Optional[S]) -> StatefulSourcePartition[X, S]: ...
+
+
+class StatelessSourcePartition(ABC, Generic[X]):
+    @abstractmethod
+    def next_batch(self) -> Iterable[X]: ...
+
+    def next_awake(self) -> Optional[datetime]:
+        return None
+
+    def close(self) -> None:
+        return
+
+
+class DynamicSource(Source[X]):
+    @abstractmethod
+    def build(self, step_id: str, worker_index: int, worker_count: int) -> StatelessSourcePartition[X]: ...
+
+
+class _SimplePollingPartition(StatefulSourcePartition):
+    def __init__(self, now: datetime, interval: timedelta, align_to: Optional[datetime], getter: Callable[[], Any]):
+        self._interval, self._getter = interval, getter
+        if align_to is not None:
+            if align_to > now:
+                raise ValueError("`align_to` must be in the past")
+            # next tick on the align_to grid
+            self._next_awake = align_to + ((now - align_to) // interval + 1) * interval
+        else:
+            self._next_awake = now
+
+    def next_batch(self):
+        try:
+            item = self._getter()
+            self._next_awake += self._interval
+            return [] if item is None else [item]
+        except SimplePollingSource.Retry as ex:
+            self._next_awake += ex.timeout
+            return []
+
+    def next_awake(self):
+        return self._next_awake
+
+    def snapshot(self):
+        return None
+
+
+class SimplePollingSource(FixedPartitionedSource):
+    """Call ``next_item`` every ``interval`` on one worker (inputs.py:333-452)."""
+
+    @dataclass
+    class Retry(Exception):
+        timeout: timedelta
+
+    def __init__(self, interval: timedelta, align_to: Optional[datetime] = None):
+        self._interval, self._align_to = interval, align_to
+
+    def list_parts(self):
+        return ["singleton"]
+
+    def build_part(self, step_id, for_part, resume_state):
+        now = datetime.now(timezone.utc)
+        return _SimplePollingPartition(now, self._interval, self._align_to, self.next_item)
+
+    @abstractmethod
+    def next_item(self): ...
+
+
+def batch(ib: Iterable[X], batch_size: int) -> Iterator[List[X]]:
+    """Chunk an iterable (inputs.py:455)."""
+    it = iter(ib)
+    while True:
+        chunk = list(islice(it, batch_size))
+        if not chunk:
+            return
+        yield chunk
+
+
+def batch_getter(getter: Callable[[], X], batch_size: int, yield_on: Optional[X] = None) -> Iterator[List[X]]:
+    """inputs.py:477."""
+    while True:
+        chunk = []
+        while len(chunk) < batch_size:
+            item = getter()
+            if item == yield_on:
+                break
+            chunk.append(item)
+        yield chunk
+
+
+def batch_getter_ex(getter: Callable[[], X], batch_size: int, yield_ex=Exception) -> Iterator[List[X]]:
+    """inputs.py:512."""
+    while True:
+        chunk = []
+        while len(chunk) < batch_size:
+            try:
+                chunk.append(getter())
+            except yield_ex:
+                break
+        yield chunk
+
+
+def batch_async(aib, timeout: timedelta, batch_size: int, loop=None) -> Iterator[List[X]]:
+    """Batch an async iterator with a time limit per batch (inputs.py:546)."""
+    loop = loop if loop is not None else asyncio.new_event_loop()
+    task = None
+
+    async def anext_batch():
+        nonlocal task
+        chunk = []
+        deadline = loop.time() + timeout.total_seconds()
+        try:
+            while len(chunk) < batch_size:
+                if task is None:
+                    task = loop.create_task(aib.__anext__())
+                remain = deadline - loop.time()
+                done, _ = await asyncio.wait({task}, timeout=max(remain, 0))
+                if not done:
+                    break
+                item = task.result()
+                task = None
+                chunk.append(item)
+        except StopAsyncIteration:
+            if not chunk:
+                raise
+        return chunk
+
+    while True:
+        try:
+            yield loop.run_until_complete(anext_batch())
+        except StopAsyncIteration:
+            return
+
+
+@dataclass
+class KeyedColumns:
+    """A whole batch of ``(key, value)`` items as columns.
+
+    ``keys``: uint64 array (the item key is ``str(key)``), ``ts_us``: int64
+    microseconds since the Unix epoch, ``vals``: numeric array or ``None``.
+    Stateless operators forward it untouched; a GPU-planned windowing step
+    ingests it as one activation.
+    """
+
+    keys: Any
+    ts_us: Any
+    vals: Any = None
+
+    def __len__(self):
+        return len(self.keys)
