@@ -175,7 +175,7 @@ def _step_class(builder: Callable, core: bool, field_names: tuple) -> type:
     if cls is None:
         base = _CoreOperator if core else Operator
         cls = dataclasses.make_dataclass(
-            builder.__name__, [(n, Any) for n in field_names], bases=(base,), frozen=True, eq=False
+            builder.__name__, [(n, Any, field(default=None)) for n in field_names], bases=(base,), frozen=True, eq=False
         )
         cls.__module__ = builder.__module__
         cls.__doc__ = f"`{builder.__name__}` operator data model."
