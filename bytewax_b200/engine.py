@@ -180,11 +180,14 @@ class _GpuWindowStep:
     def _rows(self, em, orig) -> list:
         from bytewax_b200.operators.windowing import WindowMetadata
 
-        rows = []
-        for k, w, val in zip(em.late_key.tolist(), em.late_window_id.tolist(), em.late_val.tolist()):
+        lates = []
+        for k, w, val, ep in zip(em.late_key.tolist(), em.late_window_id.tolist(), em.late_val.tolist(), em.late_epoch.tolist()):
             if self.plan.reduction == "count" and orig:
                 val = orig[int(val)]
-            rows.append((self._key_str(k), (w, "L", val)))
+            lates.append((ep, self._key_str(k), w, val))
+        if self.resort:
+            lates.sort(key=lambda r: (r[0], r[1]))  # stable: arrival order within a key is kept
+        rows = [(ks, (w, "L", val)) for _ep, ks, w, val in lates]
         closed = []
         for k, w, acc, ep in zip(em.closed_key.tolist(), em.closed_window_id.tolist(), em.closed_acc.tolist(), em.closed_epoch.tolist()):
             closed.append((ep, self._key_str(k), w, acc))
