@@ -125,8 +125,8 @@ struct bw_fold {
   i64 *ho_lwid = nullptr, *ho_lts = nullptr;
   // bookkeeping
   u32 batch_no = 0;
-  std::vector<u64> ordinal_epoch;  // batch ordinal -> user epoch (since last advance)
-  u64 ordinal_base = 0;
+  u64 last_epoch = 0, min_epoch = 0;  // epochs are non-decreasing; rows carry the user epoch
+  bool have_epoch = false, have_pending = false;
   bool eof_done = false;
   int fold_grid = 0, close_grid = 0;
   void (*fold_kernel)(BatchView, Table, FoldParams, u32, u64) = nullptr;
@@ -151,6 +151,8 @@ struct bw_fold {
 };
 
 #define FAIL(f, code, ...) CTX_FAIL((f)->ctx, code, __VA_ARGS__)
+static bw_status ensure_sort_cap(bw_fold* f, u64 n);
+static bw_status grow_host(bw_fold* f, u64 nc, u64 nl);
 
 // ---------------------------------------------------------------------------
 // small kernels
@@ -568,6 +570,11 @@ bw_status bw_fold_create(bw_ctx* ctx, const bw_fold_spec* spec, bw_fold** out) {
     st = xchg_setup(f);
     if (st != BW_OK) return st;
   }
+  // emission staging is sized once: no allocation on the advance path
+  st = ensure_sort_cap(f, std::max<u64>(spec->max_emit_rows, spec->max_late_rows));
+  if (st != BW_OK) return st;
+  st = grow_host(f, spec->max_emit_rows, spec->max_late_rows);
+  if (st != BW_OK) return st;
   CU(ctx, cudaStreamSynchronize(f->s_compute));
   *out = f;
   return BW_OK;
@@ -758,8 +765,11 @@ static bw_status exchange(bw_fold* f, const u64* d_keys, const void* d_vals, con
 static bw_status run_batch(bw_fold* f, const u64* d_keys, const void* d_vals, const i64* d_ts, u64 rows, u64 epoch) {
   bw_ctx* ctx = f->ctx;
   const u32 batch_no = f->batch_no++;
-  const u64 ord = f->ordinal_base + f->ordinal_epoch.size();
-  f->ordinal_epoch.push_back(epoch);
+  if (f->have_epoch && epoch < f->last_epoch) FAIL(f, BW_ERR_STATE, "epochs must not decrease (got %llu after %llu)", (unsigned long long)epoch, (unsigned long long)f->last_epoch);
+  if (!f->have_pending) { f->min_epoch = epoch; f->have_pending = true; }
+  f->last_epoch = epoch;
+  f->have_epoch = true;
+  const u64 ord = epoch;
   f->st.rows_ingested += rows;
   BatchView bv;
   memset(&bv, 0, sizeof bv);
@@ -916,7 +926,7 @@ static bw_status slow_path(bw_fold* f, const BatchView& bv, u64 total, u64 epoch
   const u32 batch_no = f->batch_no - 1;
   if (total == 0) return BW_OK;
   if (total > f->slow_cap) {
-    void* old[] = {f->d_kflat, f->d_ksorted, f->d_tsflat, f->d_tssorted, f->d_prefmax, f->d_idx, f->d_idxsorted, f->d_late, f->d_cub};
+    void* old[] = {f->d_kflat, f->d_ksorted, f->d_tsflat, f->d_tssorted, f->d_prefmax, f->d_idx, f->d_idxsorted, f->d_late};
     CU(ctx, cudaStreamSynchronize(s));
     for (void* p : old)
       if (p) cudaFree(p);
@@ -933,8 +943,11 @@ static bw_status slow_path(bw_fold* f, const BatchView& bv, u64 total, u64 epoch
     cub::DeviceRadixSort::SortPairs(nullptr, b1, f->d_kflat, f->d_ksorted, f->d_idx, f->d_idxsorted, (int)cap, 0, 64, s);
     cub::DeviceScan::ExclusiveScanByKey(nullptr, b2, f->d_ksorted, f->d_tssorted, f->d_prefmax, MaxI64(), (i64)INT64_MIN,
                                         (int)cap, ::cuda::std::equal_to<>(), s);
-    f->cub_bytes = std::max(b1, b2) + 256;
-    CU(ctx, cudaMalloc(&f->d_cub, f->cub_bytes));
+    if (std::max(b1, b2) + 256 > f->cub_bytes) {  // the scratch is shared with the emission sort: only ever grow it
+      if (f->d_cub) cudaFree(f->d_cub);
+      f->cub_bytes = std::max(b1, b2) + 256;
+      CU(ctx, cudaMalloc(&f->d_cub, f->cub_bytes));
+    }
     f->slow_cap = cap;
   }
   const int grid = ctx->sm_count * 8;
@@ -998,7 +1011,7 @@ static bw_status order_rows(bw_fold* f, u64 n, const u64* key, const u64* seq, c
   passes.push_back({BW_SK_ALIGNED, 64});
   if (n_ordinals > 1) passes.push_back({BW_SK_EPOCH, ebits});
   for (const Pass& ps : passes) {
-    k_sortkey<<<grid, 256, 0, s>>>(ps.kind, key, seq, epoch, wid, f->d_perm, f->d_sk, n, f->ordinal_base);
+    k_sortkey<<<grid, 256, 0, s>>>(ps.kind, key, seq, epoch, wid, f->d_perm, f->d_sk, n, f->min_epoch);
     size_t tb = f->cub_bytes;
     CU(ctx, cub::DeviceRadixSort::SortPairs(f->d_cub, tb, f->d_sk, f->d_sk2, f->d_perm, f->d_perm2, (int)n, 0, ps.bits, s));
     std::swap(f->d_perm, f->d_perm2);
@@ -1059,7 +1072,7 @@ static bw_status collect(bw_fold* f, bw_emit* out) {
   if (st != BW_OK) return st;
   const bool ordered = f->spec.emit_order == BW_ORDER_REFERENCE;
   const int grid = ctx->sm_count * 4;
-  const u64 n_ord = f->ordinal_epoch.size() + 1;  // +1: the eof activation
+  const u64 n_ord = f->have_pending ? (f->last_epoch - f->min_epoch + 1) : 1;
   const bool sliding = f->p.panes_per_window > 1 || f->p.panes_per_offset > 1;
   auto ship = [&](u64 n, const u64* src, u64* dst, bool use_perm) -> bw_status {
     if (use_perm) {
@@ -1101,21 +1114,7 @@ static bw_status collect(bw_fold* f, bw_emit* out) {
   // reset the row counters for the next round
   CU(ctx, cudaMemsetAsync(&f->d_ctr->n_closed, 0, sizeof(unsigned long long) * 2, s));
   CU(ctx, cudaStreamSynchronize(s));
-  // ordinal -> user epoch
-  const u64 base = f->ordinal_base;
-  const u64 last_epoch = f->ordinal_epoch.empty() ? 0 : f->ordinal_epoch.back();
-  auto to_epoch = [&](u64 o) -> u64 {
-    u64 i = o - base;
-    return i < f->ordinal_epoch.size() ? f->ordinal_epoch[i] : last_epoch;
-  };
-  for (u64 i = 0; i < nc; ++i) f->ho_cepoch[i] = to_epoch(f->ho_cepoch[i]);
-  for (u64 i = 0; i < nl; ++i) f->ho_lepoch[i] = to_epoch(f->ho_lepoch[i]);
-  f->ordinal_base += f->ordinal_epoch.size();
-  if (!f->ordinal_epoch.empty()) {
-    u64 keep = f->ordinal_epoch.back();
-    f->ordinal_epoch.clear();
-    (void)keep;
-  }
+  f->have_pending = false;
   out->n_closed = nc;
   out->closed_key = f->ho_ckey;
   out->closed_window_id = f->ho_cwid;
@@ -1144,7 +1143,8 @@ bw_status bw_eof(bw_fold* f, bw_emit* out) {
   bw_ctx* ctx = f->ctx;
   CU(ctx, cudaSetDevice(ctx->device));
   if (f->eof_done) FAIL(f, BW_ERR_STATE, "eof called twice");
-  const u64 ord = f->ordinal_base + f->ordinal_epoch.size();
+  const u64 ord = f->last_epoch;
+  if (!f->have_pending) { f->min_epoch = f->last_epoch; f->have_pending = true; }
   k_close_all<<<f->close_grid, 256, 0, f->s_compute>>>(f->t, f->p, f->e, ord);
   CU(ctx, cudaGetLastError());
   f->st.kernel_launches++;
