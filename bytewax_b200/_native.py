@@ -67,6 +67,21 @@ class BwStats(C.Structure):
     ]
 
 
+class BwSmapSpec(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("window", C.c_int32), ("val_dtype", C.c_int32), ("reserved", C.c_int32),
+                ("threshold", C.c_double), ("capacity_hint", C.c_uint64), ("max_batch_rows", C.c_uint64)]
+
+
+class BwJoinSpec(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("insert_mode", C.c_int32), ("emit_mode", C.c_int32), ("reserved", C.c_int32),
+                ("capacity_hint", C.c_uint64), ("max_batch_rows", C.c_uint64), ("max_emit_rows", C.c_uint64)]
+
+
+class BwJoinRows(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("key", C.POINTER(C.c_uint64)), ("left", C.POINTER(C.c_uint64)), ("right", C.POINTER(C.c_uint64)),
+                ("mask", C.POINTER(C.c_uint64)), ("epoch", C.POINTER(C.c_uint64))]
+
+
 # every symbol include/bwgpu.h declares: (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -92,6 +107,16 @@ SYMBOLS = {
     "bw_fold_time_begin": (C.c_int32, [_P]),
     "bw_fold_time_end": (C.c_int32, [_P, C.POINTER(C.c_float)]),
     "bw_gen_c1": (C.c_int32, [_P, _P, _P, C.c_uint64, C.c_uint64, C.c_uint64]),
+    "bw_smap_create": (C.c_int32, [_P, C.POINTER(BwSmapSpec), C.POINTER(_P)]),
+    "bw_smap_destroy": (None, [_P]),
+    "bw_smap_apply": (C.c_int32, [_P, _P, _P, C.c_uint64, _P, _P, _P]),
+    "bw_smap_apply_device": (C.c_int32, [_P, _P, _P, C.c_uint64, _P, _P, _P]),
+    "bw_smap_sync": (C.c_int32, [_P]),
+    "bw_join_create": (C.c_int32, [_P, C.POINTER(BwJoinSpec), C.POINTER(_P)]),
+    "bw_join_destroy": (None, [_P]),
+    "bw_join_apply": (C.c_int32, [_P, _P, _P, _P, C.c_uint64, C.c_uint64]),
+    "bw_join_advance": (C.c_int32, [_P, C.POINTER(BwJoinRows)]),
+    "bw_join_eof": (C.c_int32, [_P, C.POINTER(BwJoinRows)]),
     "bw_dev_alloc": (C.c_int32, [_P, C.c_uint64, C.POINTER(_P)]),
     "bw_dev_free": (C.c_int32, [_P, _P]),
     "bw_host_alloc": (C.c_int32, [_P, C.c_uint64, C.POINTER(_P)]),

@@ -27,6 +27,7 @@
 #include "bw_common.cuh"
 #include "bw_exchange.cuh"
 #include "bw_fold.cuh"
+#include "bw_keyed.cuh"
 #include "bw_prepass.cuh"
 #include "bw_slow.cuh"
 
@@ -1232,3 +1233,326 @@ bw_status bw_gen_c1(bw_fold* f, uint64_t* d_keys, uint64_t* d_vals, uint64_t sta
   return BW_OK;
 }
 
+
+// ===========================================================================
+// K5 / K6 host side
+// ===========================================================================
+struct MaxU32 {
+  __host__ __device__ __forceinline__ u32 operator()(const u32& a, const u32& b) const { return a > b ? a : b; }
+};
+
+struct KeyedScratch {  // grouping of one activation by key (stable)
+  u64 cap = 0;
+  u64 *d_keys = nullptr, *d_ksorted = nullptr, *d_slot = nullptr;
+  u32 *d_idx = nullptr, *d_isorted = nullptr, *d_head = nullptr;
+  void* d_cub = nullptr;
+  size_t cub_bytes = 0;
+};
+
+static bw_status keyed_alloc(bw_ctx* ctx, KeyedScratch& k, u64 cap, cudaStream_t s) {
+  k.cap = cap;
+  CU(ctx, dmalloc(&k.d_keys, cap));
+  CU(ctx, dmalloc(&k.d_ksorted, cap));
+  CU(ctx, dmalloc(&k.d_slot, cap));
+  CU(ctx, dmalloc(&k.d_idx, cap));
+  CU(ctx, dmalloc(&k.d_isorted, cap));
+  CU(ctx, dmalloc(&k.d_head, cap));
+  size_t b1 = 0, b2 = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, b1, k.d_keys, k.d_ksorted, k.d_idx, k.d_isorted, (int)cap, 0, 64, s);
+  cub::DeviceScan::InclusiveScan(nullptr, b2, k.d_head, k.d_head, MaxU32(), (int)cap, s);
+  k.cub_bytes = std::max(b1, b2) + 256;
+  CU(ctx, cudaMalloc(&k.d_cub, k.cub_bytes));
+  return BW_OK;
+}
+static void keyed_free(KeyedScratch& k) {
+  void* p[] = {k.d_keys, k.d_ksorted, k.d_slot, k.d_idx, k.d_isorted, k.d_head, k.d_cub};
+  for (void* q : p)
+    if (q) cudaFree(q);
+}
+// stable group-by-key of n device keys: ksorted / isorted / head positions
+static bw_status keyed_group(bw_ctx* ctx, KeyedScratch& k, const u64* d_keys, u64 n, cudaStream_t s) {
+  const int grid = ctx->sm_count * 4;
+  k_iota<<<grid, 256, 0, s>>>(k.d_idx, n);
+  size_t tb = k.cub_bytes;
+  CU(ctx, cub::DeviceRadixSort::SortPairs(k.d_cub, tb, d_keys, k.d_ksorted, k.d_idx, k.d_isorted, (int)n, 0, 64, s));
+  k_keyed_heads<<<grid, 256, 0, s>>>(k.d_ksorted, k.d_head, n);
+  tb = k.cub_bytes;
+  CU(ctx, cub::DeviceScan::InclusiveScan(k.d_cub, tb, k.d_head, k.d_head, MaxU32(), (int)n, s));
+  CU(ctx, cudaGetLastError());
+  return BW_OK;
+}
+
+struct bw_smap {
+  bw_ctx* ctx = nullptr;
+  bw_smap_spec spec{};
+  SmapTable t{};
+  KeyedScratch k;
+  cudaStream_t s = nullptr;
+  u32* h_err = nullptr;
+  void* d_vals = nullptr;
+  double *d_mu = nullptr, *d_sigma = nullptr;
+  unsigned char* d_flag = nullptr;
+};
+
+bw_status bw_smap_create(bw_ctx* ctx, const bw_smap_spec* spec, bw_smap** out) {
+  if (!ctx || !spec || !out) CTX_FAIL(ctx, BW_ERR_SPEC, "bw_smap_create: NULL argument");
+  if (spec->struct_size != sizeof(bw_smap_spec)) CTX_FAIL(ctx, BW_ERR_SPEC, "bw_smap_spec.struct_size mismatch");
+  if (spec->window < 1 || spec->window > BW_SMAP_MAXW) CTX_FAIL(ctx, BW_ERR_SPEC, "window must be in 1..%d", BW_SMAP_MAXW);
+  if (spec->val_dtype != BW_VAL_F32 && spec->val_dtype != BW_VAL_F64) CTX_FAIL(ctx, BW_ERR_SPEC, "val_dtype must be F32 or F64");
+  if (spec->max_batch_rows == 0 || spec->max_batch_rows >= (1ULL << 31)) CTX_FAIL(ctx, BW_ERR_SPEC, "bad max_batch_rows");
+  CU(ctx, cudaSetDevice(ctx->device));
+  bw_smap* m = new bw_smap();
+  m->ctx = ctx;
+  m->spec = *spec;
+  u64 cap = std::max<u64>(1024, 2 * std::max<u64>(spec->capacity_hint, 1));
+  m->t.cap = cap;
+  m->t.window = spec->window;
+  CU(ctx, cudaStreamCreateWithFlags(&m->s, cudaStreamNonBlocking));
+  CU(ctx, dmalloc(&m->t.keys, cap + 1));
+  CU(ctx, dmalloc(&m->t.cnt, cap + 1));
+  CU(ctx, dmalloc(&m->t.ring, (cap + 1) * (u64)spec->window));
+  CU(ctx, dmalloc(&m->t.err, 1));
+  CU(ctx, cudaMemsetAsync(m->t.err, 0, 4, m->s));
+  CU(ctx, cudaHostAlloc((void**)&m->h_err, 64, cudaHostAllocDefault));
+  const u64 n = spec->max_batch_rows;
+  bw_status st = keyed_alloc(ctx, m->k, n, m->s);
+  if (st != BW_OK) return st;
+  CU(ctx, cudaMalloc(&m->d_vals, n * 8));
+  CU(ctx, dmalloc(&m->d_mu, n));
+  CU(ctx, dmalloc(&m->d_sigma, n));
+  CU(ctx, dmalloc(&m->d_flag, n));
+  k_smap_init<<<ctx->sm_count * 4, 256, 0, m->s>>>(m->t);
+  CU(ctx, cudaGetLastError());
+  CU(ctx, cudaStreamSynchronize(m->s));
+  *out = m;
+  return BW_OK;
+}
+
+void bw_smap_destroy(bw_smap* m) {
+  if (!m) return;
+  cudaSetDevice(m->ctx->device);
+  cudaStreamSynchronize(m->s);
+  void* p[] = {m->t.keys, m->t.cnt, m->t.ring, m->t.err, m->d_vals, m->d_mu, m->d_sigma, m->d_flag};
+  for (void* q : p)
+    if (q) cudaFree(q);
+  keyed_free(m->k);
+  if (m->h_err) cudaFreeHost(m->h_err);
+  cudaStreamDestroy(m->s);
+  delete m;
+}
+
+bw_status bw_smap_apply_device(bw_smap* m, const uint64_t* d_keys, const void* d_vals, uint64_t rows, double* d_mu,
+                               double* d_sigma, uint8_t* d_flag) {
+  if (!m) return BW_ERR_SPEC;
+  bw_ctx* ctx = m->ctx;
+  if (rows > m->spec.max_batch_rows) CTX_FAIL(ctx, BW_ERR_SPEC, "smap: rows > max_batch_rows");
+  if (rows == 0) return BW_OK;
+  CU(ctx, cudaSetDevice(ctx->device));
+  bw_status st = keyed_group(ctx, m->k, d_keys, rows, m->s);
+  if (st != BW_OK) return st;
+  const int grid = ctx->sm_count * 8;
+  const int is_f32 = m->spec.val_dtype == BW_VAL_F32;
+  k_smap_slots<<<grid, 256, 0, m->s>>>(m->t, m->k.d_ksorted, m->k.d_head, m->k.d_slot, rows);
+  k_smap_eval<<<grid, 256, 0, m->s>>>(m->t, m->k.d_isorted, m->k.d_head, m->k.d_slot, d_vals, is_f32, m->spec.threshold, d_mu, d_sigma,
+                                       d_flag, rows);
+  k_smap_update<<<grid, 256, 0, m->s>>>(m->t, m->k.d_ksorted, m->k.d_isorted, m->k.d_head, m->k.d_slot, d_vals, is_f32, rows);
+  CU(ctx, cudaGetLastError());
+  return BW_OK;
+}
+
+bw_status bw_smap_sync(bw_smap* m) {
+  if (!m) return BW_ERR_SPEC;
+  bw_ctx* ctx = m->ctx;
+  CU(ctx, cudaMemcpyAsync(m->h_err, m->t.err, 4, cudaMemcpyDeviceToHost, m->s));
+  CU(ctx, cudaStreamSynchronize(m->s));
+  if (*m->h_err) CTX_FAIL(ctx, (bw_status)*m->h_err, "smap kernel raised status %u: key table full (raise capacity_hint)", *m->h_err);
+  return BW_OK;
+}
+
+bw_status bw_smap_apply(bw_smap* m, const uint64_t* keys, const void* vals, uint64_t rows, double* out_mu, double* out_sigma,
+                        uint8_t* out_flag) {
+  if (!m) return BW_ERR_SPEC;
+  bw_ctx* ctx = m->ctx;
+  if (rows > m->spec.max_batch_rows) CTX_FAIL(ctx, BW_ERR_SPEC, "smap: rows > max_batch_rows");
+  if (rows == 0) return BW_OK;
+  CU(ctx, cudaSetDevice(ctx->device));
+  const size_t vb = m->spec.val_dtype == BW_VAL_F32 ? 4 : 8;
+  CU(ctx, cudaMemcpyAsync(m->k.d_keys, keys, rows * 8, cudaMemcpyHostToDevice, m->s));
+  CU(ctx, cudaMemcpyAsync(m->d_vals, vals, rows * vb, cudaMemcpyHostToDevice, m->s));
+  bw_status st = bw_smap_apply_device(m, m->k.d_keys, m->d_vals, rows, m->d_mu, m->d_sigma, m->d_flag);
+  if (st != BW_OK) return st;
+  CU(ctx, cudaMemcpyAsync(out_mu, m->d_mu, rows * 8, cudaMemcpyDeviceToHost, m->s));
+  CU(ctx, cudaMemcpyAsync(out_sigma, m->d_sigma, rows * 8, cudaMemcpyDeviceToHost, m->s));
+  CU(ctx, cudaMemcpyAsync(out_flag, m->d_flag, rows, cudaMemcpyDeviceToHost, m->s));
+  return bw_smap_sync(m);
+}
+
+struct bw_join {
+  bw_ctx* ctx = nullptr;
+  bw_join_spec spec{};
+  JoinSlot* slots = nullptr;
+  u64 cap = 0;
+  KeyedScratch k;
+  cudaStream_t s = nullptr;
+  u32 *d_err = nullptr, *h_err = nullptr;
+  unsigned long long *d_nrows = nullptr, *h_nrows = nullptr;
+  unsigned char* d_side = nullptr;
+  u64* d_vals = nullptr;
+  JoinEmit e{};
+  // ordering scratch + host output
+  u64 *d_sk = nullptr, *d_sk2 = nullptr, *d_gather = nullptr;
+  u32 *d_perm = nullptr, *d_perm2 = nullptr;
+  void* d_cub = nullptr;
+  size_t cub_bytes = 0;
+  u64 *h_key = nullptr, *h_l = nullptr, *h_r = nullptr, *h_mask = nullptr, *h_epoch = nullptr;
+  u32 batch_no = 0;
+  u64 min_epoch = 0, last_epoch = 0;
+  bool pending = false;
+};
+
+bw_status bw_join_create(bw_ctx* ctx, const bw_join_spec* spec, bw_join** out) {
+  if (!ctx || !spec || !out) CTX_FAIL(ctx, BW_ERR_SPEC, "bw_join_create: NULL argument");
+  if (spec->struct_size != sizeof(bw_join_spec)) CTX_FAIL(ctx, BW_ERR_SPEC, "bw_join_spec.struct_size mismatch");
+  if (spec->insert_mode < 0 || spec->insert_mode > 1) CTX_FAIL(ctx, BW_ERR_SPEC, "insert_mode must be first or last (product: host path)");
+  if (spec->emit_mode < 0 || spec->emit_mode > 2) CTX_FAIL(ctx, BW_ERR_SPEC, "bad emit_mode");
+  if (spec->max_batch_rows == 0 || spec->max_batch_rows >= (1ULL << 31)) CTX_FAIL(ctx, BW_ERR_SPEC, "bad max_batch_rows");
+  CU(ctx, cudaSetDevice(ctx->device));
+  bw_join* j = new bw_join();
+  j->ctx = ctx;
+  j->spec = *spec;
+  j->cap = std::max<u64>(1024, 2 * std::max<u64>(spec->capacity_hint, 1));
+  CU(ctx, cudaStreamCreateWithFlags(&j->s, cudaStreamNonBlocking));
+  CU(ctx, dmalloc(&j->slots, j->cap + 1));
+  CU(ctx, dmalloc(&j->d_err, 1));
+  CU(ctx, dmalloc(&j->d_nrows, 1));
+  CU(ctx, cudaMemsetAsync(j->d_err, 0, 4, j->s));
+  CU(ctx, cudaMemsetAsync(j->d_nrows, 0, 8, j->s));
+  CU(ctx, cudaHostAlloc((void**)&j->h_err, 64, cudaHostAllocDefault));
+  CU(ctx, cudaHostAlloc((void**)&j->h_nrows, 64, cudaHostAllocDefault));
+  const u64 n = spec->max_batch_rows, m = std::max<u64>(spec->max_emit_rows, 1024);
+  bw_status st = keyed_alloc(ctx, j->k, n, j->s);
+  if (st != BW_OK) return st;
+  CU(ctx, dmalloc(&j->d_side, n));
+  CU(ctx, dmalloc(&j->d_vals, n));
+  u64** cols[] = {&j->e.key, &j->e.l, &j->e.r, &j->e.mask, &j->e.seq, &j->e.epoch, &j->d_sk, &j->d_sk2, &j->d_gather};
+  for (u64** c : cols) CU(ctx, dmalloc(c, m));
+  CU(ctx, dmalloc(&j->d_perm, m));
+  CU(ctx, dmalloc(&j->d_perm2, m));
+  j->e.max_rows = spec->max_emit_rows;
+  j->e.n_rows = j->d_nrows;
+  size_t b = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, b, j->d_sk, j->d_sk2, j->d_perm, j->d_perm2, (int)m, 0, 64, j->s);
+  j->cub_bytes = b + 256;
+  CU(ctx, cudaMalloc(&j->d_cub, j->cub_bytes));
+  u64** hcols[] = {&j->h_key, &j->h_l, &j->h_r, &j->h_mask, &j->h_epoch};
+  for (u64** c : hcols) CU(ctx, cudaHostAlloc((void**)c, m * 8, cudaHostAllocDefault));
+  k_join_init<<<ctx->sm_count * 4, 256, 0, j->s>>>(j->slots, j->cap);
+  CU(ctx, cudaGetLastError());
+  CU(ctx, cudaStreamSynchronize(j->s));
+  *out = j;
+  return BW_OK;
+}
+
+void bw_join_destroy(bw_join* j) {
+  if (!j) return;
+  cudaSetDevice(j->ctx->device);
+  cudaStreamSynchronize(j->s);
+  void* p[] = {j->slots, j->d_err, j->d_nrows, j->d_side, j->d_vals, j->e.key, j->e.l, j->e.r, j->e.mask, j->e.seq, j->e.epoch,
+               j->d_sk, j->d_sk2, j->d_gather, j->d_perm, j->d_perm2, j->d_cub};
+  for (void* q : p)
+    if (q) cudaFree(q);
+  keyed_free(j->k);
+  void* h[] = {j->h_err, j->h_nrows, j->h_key, j->h_l, j->h_r, j->h_mask, j->h_epoch};
+  for (void* q : h)
+    if (q) cudaFreeHost(q);
+  cudaStreamDestroy(j->s);
+  delete j;
+}
+
+bw_status bw_join_apply(bw_join* j, const uint64_t* keys, const uint8_t* side, const uint64_t* vals, uint64_t rows, uint64_t epoch) {
+  if (!j) return BW_ERR_SPEC;
+  bw_ctx* ctx = j->ctx;
+  if (rows > j->spec.max_batch_rows) CTX_FAIL(ctx, BW_ERR_SPEC, "join: rows > max_batch_rows");
+  if (j->pending && epoch < j->last_epoch) CTX_FAIL(ctx, BW_ERR_STATE, "join: epochs must not decrease");
+  if (!j->pending) {
+    j->min_epoch = epoch;
+    j->pending = true;
+  }
+  j->last_epoch = epoch;
+  const u32 batch_no = j->batch_no++;
+  if (rows == 0) return BW_OK;
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaMemcpyAsync(j->k.d_keys, keys, rows * 8, cudaMemcpyHostToDevice, j->s));
+  CU(ctx, cudaMemcpyAsync(j->d_side, side, rows, cudaMemcpyHostToDevice, j->s));
+  CU(ctx, cudaMemcpyAsync(j->d_vals, vals, rows * 8, cudaMemcpyHostToDevice, j->s));
+  bw_status st = keyed_group(ctx, j->k, j->k.d_keys, rows, j->s);
+  if (st != BW_OK) return st;
+  k_join_apply<<<ctx->sm_count * 8, 256, 0, j->s>>>(j->slots, j->cap, j->d_err, j->k.d_ksorted, j->k.d_isorted, j->k.d_head, j->d_side,
+                                                      j->d_vals, rows, j->spec.insert_mode, j->spec.emit_mode, j->e, batch_no, epoch);
+  CU(ctx, cudaGetLastError());
+  // the host columns may be reused by the caller once this returns
+  CU(ctx, cudaStreamSynchronize(j->s));
+  return BW_OK;
+}
+
+static bw_status join_collect(bw_join* j, bw_join_rows* out) {
+  bw_ctx* ctx = j->ctx;
+  cudaStream_t s = j->s;
+  CU(ctx, cudaMemcpyAsync(j->h_err, j->d_err, 4, cudaMemcpyDeviceToHost, s));
+  CU(ctx, cudaMemcpyAsync(j->h_nrows, j->d_nrows, 8, cudaMemcpyDeviceToHost, s));
+  CU(ctx, cudaStreamSynchronize(s));
+  if (*j->h_err) CTX_FAIL(ctx, (bw_status)*j->h_err, "join kernel raised status %u: key table or emit buffer full", *j->h_err);
+  const u64 n = std::min<u64>(*j->h_nrows, j->e.max_rows);
+  if (n) {
+    const int grid = ctx->sm_count * 4;
+    k_iota<<<grid, 256, 0, s>>>(j->d_perm, n);
+    const u64 n_ord = j->last_epoch - j->min_epoch + 1;
+    int ebits = 1;
+    while ((1ULL << ebits) < n_ord + 1) ++ebits;
+    struct Pass { int kind, bits; };
+    std::vector<Pass> passes = {{BW_SK_SEQ, 64}, {BW_SK_DIGITS, 16}, {BW_SK_ALIGNED, 64}};
+    if (n_ord > 1) passes.push_back({BW_SK_EPOCH, ebits});
+    for (const Pass& ps : passes) {
+      k_sortkey<<<grid, 256, 0, s>>>(ps.kind, j->e.key, j->e.seq, j->e.epoch, nullptr, j->d_perm, j->d_sk, n, j->min_epoch);
+      size_t tb = j->cub_bytes;
+      CU(ctx, cub::DeviceRadixSort::SortPairs(j->d_cub, tb, j->d_sk, j->d_sk2, j->d_perm, j->d_perm2, (int)n, 0, ps.bits, s));
+      std::swap(j->d_perm, j->d_perm2);
+    }
+    const u64* src[] = {j->e.key, j->e.l, j->e.r, j->e.mask, j->e.epoch};
+    u64* dst[] = {j->h_key, j->h_l, j->h_r, j->h_mask, j->h_epoch};
+    for (int c = 0; c < 5; ++c) {
+      k_gather_u64<<<grid, 256, 0, s>>>(src[c], j->d_perm, j->d_gather, n);
+      CU(ctx, cudaMemcpyAsync(dst[c], j->d_gather, n * 8, cudaMemcpyDeviceToHost, s));
+    }
+    CU(ctx, cudaGetLastError());
+  }
+  CU(ctx, cudaMemsetAsync(j->d_nrows, 0, 8, s));
+  CU(ctx, cudaStreamSynchronize(s));
+  j->pending = false;
+  out->n = n;
+  out->key = j->h_key;
+  out->left = j->h_l;
+  out->right = j->h_r;
+  out->mask = j->h_mask;
+  out->epoch = j->h_epoch;
+  return BW_OK;
+}
+
+bw_status bw_join_advance(bw_join* j, bw_join_rows* out) {
+  if (!j || !out) return BW_ERR_SPEC;
+  CU(j->ctx, cudaSetDevice(j->ctx->device));
+  return join_collect(j, out);
+}
+
+bw_status bw_join_eof(bw_join* j, bw_join_rows* out) {
+  if (!j || !out) return BW_ERR_SPEC;
+  bw_ctx* ctx = j->ctx;
+  CU(ctx, cudaSetDevice(ctx->device));
+  if (!j->pending) {
+    j->min_epoch = j->last_epoch;
+    j->pending = true;
+  }
+  k_join_eof<<<ctx->sm_count * 8, 256, 0, j->s>>>(j->slots, j->cap, j->d_err, j->spec.emit_mode, j->e, j->last_epoch);
+  CU(ctx, cudaGetLastError());
+  return join_collect(j, out);
+}

@@ -259,3 +259,88 @@ class WindowFold:
         if self.h:
             self.lib.bw_fold_destroy(self.h)
             self.h = None
+
+
+class ZScoreMap:
+    """``stateful_map`` with the rolling z-score detector (``bw_smap``; examples/anomaly_detector.py:16-48)."""
+
+    def __init__(self, ctx: Context, window: int = 10, threshold: float = 2.0, val_dtype: str = "f32", capacity_hint: int = 1 << 16,
+                 max_batch_rows: int = 1 << 20):
+        self.ctx, self.lib, self.val_dtype = ctx, ctx.lib, val_dtype
+        s = N.BwSmapSpec()
+        s.struct_size = C.sizeof(N.BwSmapSpec)
+        s.window, s.val_dtype, s.threshold = window, N.VAL[val_dtype], threshold
+        s.capacity_hint, s.max_batch_rows = capacity_hint, max_batch_rows
+        h = C.c_void_p()
+        N.check(self.lib.bw_smap_create(ctx.h, C.byref(s), C.byref(h)), ctx.h)
+        self.h = h
+
+    def apply(self, keys, vals):
+        """One activation -> (mu f64[n], sigma f64[n], anomalous bool[n]) aligned with the input rows."""
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        vals = np.ascontiguousarray(vals, dtype=_NP_VAL[self.val_dtype])
+        n = keys.shape[0]
+        mu, sigma, flag = np.empty(n, np.float64), np.empty(n, np.float64), np.empty(n, np.uint8)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        N.check(self.lib.bw_smap_apply(self.h, vp(keys), vp(vals), n, vp(mu), vp(sigma), vp(flag)), self.ctx.h)
+        return mu, sigma, flag.astype(bool)
+
+    def close(self):
+        if self.h:
+            self.lib.bw_smap_destroy(self.h)
+            self.h = None
+
+
+class KeyedJoin:
+    """Two-sided keyed join (``bw_join``; operators/__init__.py:2157-2190)."""
+
+    INSERT = {"first": 0, "last": 1}
+    EMIT = {"complete": 0, "final": 1, "running": 2}
+
+    def __init__(self, ctx: Context, insert_mode: str = "last", emit_mode: str = "complete", capacity_hint: int = 1 << 16,
+                 max_batch_rows: int = 1 << 20, max_emit_rows: int = 1 << 20):
+        self.ctx, self.lib = ctx, ctx.lib
+        s = N.BwJoinSpec()
+        s.struct_size = C.sizeof(N.BwJoinSpec)
+        s.insert_mode, s.emit_mode = self.INSERT[insert_mode], self.EMIT[emit_mode]
+        s.capacity_hint, s.max_batch_rows, s.max_emit_rows = capacity_hint, max_batch_rows, max_emit_rows
+        h = C.c_void_p()
+        N.check(self.lib.bw_join_create(ctx.h, C.byref(s), C.byref(h)), ctx.h)
+        self.h = h
+        self._epoch = 0
+
+    def apply(self, keys, sides, vals, epoch: Optional[int] = None):
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        sides = np.ascontiguousarray(sides, dtype=np.uint8)
+        vals = np.ascontiguousarray(vals, dtype=np.uint64)
+        if epoch is None:
+            self._epoch += 1
+            epoch = self._epoch
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        N.check(self.lib.bw_join_apply(self.h, vp(keys), vp(sides), vp(vals), keys.shape[0], epoch), self.ctx.h)
+
+    def _rows(self, r: N.BwJoinRows):
+        n = int(r.n)
+
+        def arr(ptr):
+            return np.ctypeslib.as_array(ptr, shape=(n,)).copy() if n else np.zeros(0, np.uint64)
+
+        key, l, rr, mask, epoch = arr(r.key), arr(r.left), arr(r.right), arr(r.mask), arr(r.epoch)
+        rows = [(int(k), int(a) if m & 1 else None, int(b) if m & 2 else None) for k, a, b, m in zip(key, l, rr, mask)]
+        return rows, epoch
+
+    def advance(self):
+        """Rows ``(key, left_or_None, right_or_None)`` emitted since the last call, in the reference's order."""
+        r = N.BwJoinRows()
+        N.check(self.lib.bw_join_advance(self.h, C.byref(r)), self.ctx.h)
+        return self._rows(r)
+
+    def eof(self):
+        r = N.BwJoinRows()
+        N.check(self.lib.bw_join_eof(self.h, C.byref(r)), self.ctx.h)
+        return self._rows(r)
+
+    def close(self):
+        if self.h:
+            self.lib.bw_join_destroy(self.h)
+            self.h = None

@@ -244,6 +244,66 @@ void* bw_fold_stream(bw_fold* fold);
 bw_status bw_gen_c1(bw_fold* fold, uint64_t* d_keys, uint64_t* d_vals, uint64_t start, uint64_t rows,
                     uint64_t n_keys);
 
+/* ---- keyed steps that are not window folds (BASELINE configs C2 and C4) ---------------- */
+
+/* `stateful_map` with the rolling z-score mapper of examples/anomaly_detector.py:16-48, run by
+ * `_StatefulLogic.on_batch` / `_StatefulFlatMapLogic.on_item`
+ * (pysrc/bytewax/operators/__init__.py:1024-1042, 2860-2890) behind src/operators.rs:755-806:
+ * per key, in arrival order: flag = |v - mu| / sigma > threshold on the statistics BEFORE the
+ * push (false while mu or sigma is None or 0.0), then push v into the last-`window` ring and
+ * recompute mu = sum/len, sigma = sqrt(sum((x - mu)^2)/len), both newest -> oldest. */
+typedef struct bw_smap bw_smap;
+typedef struct bw_smap_spec {
+  uint32_t struct_size;
+  int32_t window;      /* ring length, 1..32 (the example uses 10) */
+  int32_t val_dtype;   /* BW_VAL_F32 or BW_VAL_F64 */
+  int32_t reserved;
+  double threshold;    /* the example uses 2.0 */
+  uint64_t capacity_hint;
+  uint64_t max_batch_rows;
+} bw_smap_spec;
+bw_status bw_smap_create(bw_ctx* ctx, const bw_smap_spec* spec, bw_smap** out);
+void bw_smap_destroy(bw_smap* m);
+/* One activation from HOST columns; outputs are aligned with the input rows. Blocking. */
+bw_status bw_smap_apply(bw_smap* m, const uint64_t* keys, const void* vals, uint64_t rows, double* out_mu,
+                        double* out_sigma, uint8_t* out_flag);
+/* Same with DEVICE columns in and out (returns after enqueueing; bw_smap_sync to wait). */
+bw_status bw_smap_apply_device(bw_smap* m, const uint64_t* d_keys, const void* d_vals, uint64_t rows, double* d_mu,
+                               double* d_sigma, uint8_t* d_flag);
+bw_status bw_smap_sync(bw_smap* m);
+
+/* Two-sided keyed join: `_JoinLogic.on_item` / `on_eof` (operators/__init__.py:2157-2190) over the
+ * side-labelled merged stream of `_join_label_merge` (:2193-2204); insert modes first / last,
+ * emit modes complete / final / running (`product` keeps lists per side: host path only). */
+typedef enum { BW_JOIN_INSERT_FIRST = 0, BW_JOIN_INSERT_LAST = 1 } bw_join_insert;
+typedef enum { BW_JOIN_EMIT_COMPLETE = 0, BW_JOIN_EMIT_FINAL = 1, BW_JOIN_EMIT_RUNNING = 2 } bw_join_emit_mode;
+typedef struct bw_join bw_join;
+typedef struct bw_join_spec {
+  uint32_t struct_size;
+  int32_t insert_mode;
+  int32_t emit_mode;
+  int32_t reserved;
+  uint64_t capacity_hint;
+  uint64_t max_batch_rows;
+  uint64_t max_emit_rows;
+} bw_join_spec;
+typedef struct bw_join_rows {
+  uint64_t n;
+  const uint64_t* key;
+  const uint64_t* left;   /* valid where mask bit 0 is set (else the reference emits None) */
+  const uint64_t* right;  /* valid where mask bit 1 is set */
+  const uint64_t* mask;
+  const uint64_t* epoch;
+} bw_join_rows;
+bw_status bw_join_create(bw_ctx* ctx, const bw_join_spec* spec, bw_join** out);
+void bw_join_destroy(bw_join* j);
+/* One activation: items of both sides in arrival order, side[i] in {0 = left, 1 = right}; host columns. */
+bw_status bw_join_apply(bw_join* j, const uint64_t* keys, const uint8_t* side, const uint64_t* vals, uint64_t rows,
+                        uint64_t epoch);
+/* Rows emitted since the last call, reference order: per activation ascending key string, then item order. */
+bw_status bw_join_advance(bw_join* j, bw_join_rows* out);
+bw_status bw_join_eof(bw_join* j, bw_join_rows* out);
+
 /* ---- plain device-memory helpers (tests / bench / host bindings without torch) ---- */
 bw_status bw_dev_alloc(bw_ctx* ctx, uint64_t bytes, void** out);
 bw_status bw_dev_free(bw_ctx* ctx, void* ptr);

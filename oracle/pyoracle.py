@@ -384,3 +384,96 @@ def c1_rows(start: int, n: int, n_keys: int = 1_000_000, align_us: int = 1_640_9
     vals = list(range(start, start + n))
     ts = [align_us + i for i in range(start, start + n)]
     return keys, ts, vals
+
+
+# ---------------------------------------------------------------------------
+# Config C2: stateful_map with the anomaly detector of examples/anomaly_detector.py:16-48
+# (engine half: operators/__init__.py:1024-1042 `_StatefulLogic.on_batch`, :2860-2890)
+# ---------------------------------------------------------------------------
+
+
+class ZScoreDetector:
+    """Per-key state of the reference's example mapper, restated verbatim in behaviour:
+    last-N values newest first, ``mu = sum/len``, ``sigma = (sum((v-mu)**2)/len) ** 0.5`` (both
+    summed newest -> oldest like Python's ``sum``), anomalous iff ``mu and sigma`` are truthy and
+    ``abs(v - mu) / sigma > threshold`` evaluated BEFORE the push (anomaly_detector.py:33-46)."""
+
+    def __init__(self, window: int = 10, threshold: float = 2.0):
+        self.window, self.threshold = window, threshold
+        self.last: List[float] = []
+        self.mu: Optional[float] = None
+        self.sigma: Optional[float] = None
+
+    def on_value(self, value: float):
+        anomalous = False
+        if self.mu and self.sigma:
+            anomalous = abs(value - self.mu) / self.sigma > self.threshold
+        self.last.insert(0, value)
+        del self.last[self.window:]
+        n = len(self.last)
+        self.mu = sum(self.last) / n
+        self.sigma = (sum((v - self.mu) ** 2 for v in self.last) / n) ** 0.5
+        return (value, self.mu, self.sigma, anomalous)
+
+
+def run_zscore(batches, window: int = 10, threshold: float = 2.0):
+    """``batches`` = [(keys, vals), ...] -> per batch a list of (mu, sigma, anomalous) aligned with the input rows."""
+    states: Dict[int, ZScoreDetector] = {}
+    out = []
+    for keys, vals in batches:
+        rows = []
+        for k, v in zip(keys, vals):
+            st = states.get(int(k))
+            if st is None:
+                st = states[int(k)] = ZScoreDetector(window, threshold)
+            _, mu, sigma, flag = st.on_value(float(v))
+            rows.append((mu, sigma, flag))
+        out.append(rows)
+    return out
+
+
+# ---------------------------------------------------------------------------
+# Config C4: keyed join (operators/__init__.py:2075-2190 `_JoinState`, `_JoinLogic`)
+# ---------------------------------------------------------------------------
+
+
+def run_join(batches, insert_mode: str = "last", emit_mode: str = "complete", eof: bool = True):
+    """Two-sided join.  ``batches`` = [(keys, sides, vals), ...] in arrival order (the merged, side-labelled
+    stream of `_join_label_merge`, operators/__init__.py:2193-2204).  Returns per activation a list of
+    ``(key, left_or_None, right_or_None)`` in the engine's order: ascending key string, then item order."""
+    assert insert_mode in ("first", "last")
+    states: Dict[str, list] = {}
+    ids: Dict[str, int] = {}
+    acts = []
+    for keys, sides, vals in batches:
+        grouped: Dict[str, list] = {}
+        for k, s, v in zip(keys, sides, vals):
+            ks = key_str(k)
+            ids[ks] = int(k)
+            grouped.setdefault(ks, []).append((int(s), int(v)))
+        rows = []
+        for ks in sorted(grouped):
+            for side, v in grouped[ks]:
+                st = states.get(ks)
+                if st is None:  # builder(None): fresh _JoinState (also after a DISCARD mid-batch, :1029-1042)
+                    st = states[ks] = [None, None]
+                if insert_mode == "first":
+                    if st[side] is None:
+                        st[side] = v
+                else:
+                    st[side] = v
+                if emit_mode == "complete" and st[0] is not None and st[1] is not None:
+                    rows.append((ids[ks], st[0], st[1]))
+                    del states[ks]
+                elif emit_mode == "running":
+                    rows.append((ids[ks], st[0], st[1]))
+        acts.append(rows)
+    if eof:
+        rows = []
+        if emit_mode == "final":
+            for ks in sorted(states):
+                st = states[ks]
+                rows.append((ids[ks], st[0], st[1]))
+            states.clear()
+        acts.append(rows)
+    return acts
