@@ -342,5 +342,49 @@ def main():
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
+def main_keyed():
+    """Goldens for config C2 (the reference example's own mapper) and C4 (the reference's `_JoinLogic`)."""
+    src = open("/root/reference/examples/anomaly_detector.py").read()
+    ns = {}
+    start, end = src.index("@dataclass\nclass DetectorState"), src.index("labeled_metrics =")
+    exec("from dataclasses import dataclass, field\nfrom typing import List, Optional\n" + src[start:end], ns)  # examples/anomaly_detector.py:16-48
+    rnd = random.Random(77)
+    out = {"zscore": [], "join": []}
+    for case in range(3):
+        n, nkeys = 600, [1, 7, 40][case]
+        keys = [rnd.randrange(nkeys) for _ in range(n)]
+        vals = [float(rnd.randrange(0, 10)) if case < 2 else round(rnd.uniform(0, 10), 3) for _ in range(n)]
+        states, rows = {}, []
+        for k, v in zip(keys, vals):
+            st, emit = ns["mapper"](states.get(k), v)
+            states[k] = st
+            rows.append([emit[1], emit[2], emit[3]])
+        out["zscore"].append(dict(keys=keys, vals=vals, rows=rows))
+    import bytewax.operators as rop
+
+    for im in ("first", "last"):
+        for em in ("complete", "running", "final"):
+            items = [(rnd.randrange(9), rnd.randrange(2), rnd.randrange(1000)) for _ in range(400)]
+            logics, rows = {}, []
+            for k, sd, v in items:  # one item per activation (TestingSource batch_size=1)
+                lg = logics.get(k)
+                if lg is None:
+                    lg = logics[k] = rop._JoinLogic(im, em, rop._JoinState.for_side_count(2))
+                emitted, discard = lg.on_item((sd, v))
+                rows.extend([k, t[0], t[1]] for t in emitted)
+                if discard:
+                    del logics[k]
+            if em == "final":
+                for k in sorted(logics, key=str):
+                    emitted, _ = logics[k].on_eof()
+                    rows.extend([k, t[0], t[1]] for t in emitted)
+            out["join"].append(dict(insert_mode=im, emit_mode=em, items=[list(i) for i in items], rows=rows))
+    path = os.path.join(os.path.dirname(HERE), "tests", "golden", "keyed_cases.json")
+    with open(path, "w") as f:
+        json.dump(out, f, separators=(",", ":"))
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 if __name__ == "__main__":
     main()
+    main_keyed()

@@ -134,3 +134,15 @@ def test_oracle_vs_live_reference_random():
     ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+def test_keyed_oracles_match_reference_goldens(golden_dir):
+    """C2 / C4 restatements against rows produced by the reference's example mapper and `_JoinLogic`."""
+    g = _load(golden_dir, "keyed_cases.json")
+    for case in g["zscore"]:
+        got = po.run_zscore([(case["keys"], case["vals"])])[0]
+        assert [[m, s, f] for m, s, f in got] == case["rows"]
+    for case in g["join"]:
+        items = case["items"]
+        acts = po.run_join([([k], [s], [v]) for k, s, v in items], case["insert_mode"], case["emit_mode"])
+        assert [list(r) for a in acts for r in a] == case["rows"], (case["insert_mode"], case["emit_mode"])
