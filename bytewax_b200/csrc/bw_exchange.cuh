@@ -108,10 +108,20 @@ __global__ void __launch_bounds__(1024) k_part_scan(u64 n, int world, u32* tile_
   if (threadIdx.x == 0) __threadfence_system();
 }
 
+// Stable scatter, staged through shared memory: rows of a tile are first laid out
+// destination-major in shared memory, then every destination's run is copied out by the
+// whole block with consecutive lanes on consecutive addresses.  Peer (NVLink) stores
+// therefore arrive as long contiguous runs (2-8 KB per destination per tile) instead of
+// warp-sized fragments -- the fragmented version reached ~200 GB/s over NVLink.
 __global__ void __launch_bounds__(BW_PART_THREADS)
 k_part_scatter(PartIn in, const u32* tile_off, PartOut out) {
   // [iteration][warp][dest] counts, scanned in (iteration, warp) order per dest
   __shared__ u32 cnt[BW_PART_PER_THREAD][BW_PART_THREADS / 32][BW_MAX_WORLD];
+  __shared__ u32 tot[BW_MAX_WORLD], dstart[BW_MAX_WORLD + 1];
+  extern __shared__ __align__(16) unsigned char stage_raw[];
+  u64* s_keys = (u64*)stage_raw;
+  unsigned char* s_vals = stage_raw + (size_t)BW_PART_TILE * 8;
+  i64* s_ts = (i64*)(s_vals + (size_t)BW_PART_TILE * (in.val_bytes ? in.val_bytes : 0));
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const u32 lt = (1u << lane) - 1u;
   const u64 ntiles = (in.n + BW_PART_TILE - 1) / BW_PART_TILE;
@@ -149,21 +159,51 @@ k_part_scatter(PartIn in, const u32* tile_off, PartOut out) {
         *p = run + inc - v;
         run += __shfl_sync(0xffffffffu, inc, 31);
       }
+      if (lane == 0) tot[d] = run;
     }
     __syncthreads();
+    if (threadIdx.x == 0) {
+      u32 acc = 0;
+      for (int d = 0; d < BW_MAX_WORLD; ++d) {
+        dstart[d] = acc;
+        acc += tot[d];
+      }
+      dstart[BW_MAX_WORLD] = acc;
+    }
+    __syncthreads();
+    // stage destination-major
 #pragma unroll
     for (int j = 0; j < BW_PART_PER_THREAD; ++j) {
       u64 i = tile * BW_PART_TILE + (u64)j * BW_PART_THREADS + threadIdx.x;
       if (i < in.n) {
         const u32 d = dst[j];
-        const u64 pos = (u64)tile_off[tile * BW_MAX_WORLD + d] + cnt[j][warp][d] + rk[j];
-        out.keys[d][pos] = key[j];
+        const u32 lp = dstart[d] + cnt[j][warp][d] + rk[j];
+        s_keys[lp] = key[j];
         if (in.val_bytes == 8) {
-          ((u64*)out.vals[d])[pos] = bw_ld_stream_u64((const u64*)in.vals + i);
+          ((u64*)s_vals)[lp] = bw_ld_stream_u64((const u64*)in.vals + i);
         } else if (in.val_bytes == 4) {
-          ((u32*)out.vals[d])[pos] = bw_ld_stream_u32((const u32*)in.vals + i);
+          ((u32*)s_vals)[lp] = bw_ld_stream_u32((const u32*)in.vals + i);
         }
-        if (in.ts) out.ts[d][pos] = (i64)bw_ld_stream_u64((const u64*)in.ts + i);
+        if (in.ts) s_ts[lp] = (i64)bw_ld_stream_u64((const u64*)in.ts + i);
+      }
+    }
+    __syncthreads();
+    // copy every destination's run out, block-wide, lane-consecutive
+    for (int d = 0; d < in.world; ++d) {
+      const u32 n_d = tot[d], s0 = dstart[d];
+      const u64 g0 = tile_off[tile * BW_MAX_WORLD + d];
+      u64* gk = out.keys[d] + g0;
+      for (u32 e = threadIdx.x; e < n_d; e += BW_PART_THREADS) gk[e] = s_keys[s0 + e];
+      if (in.val_bytes == 8) {
+        u64* gv = (u64*)out.vals[d] + g0;
+        for (u32 e = threadIdx.x; e < n_d; e += BW_PART_THREADS) gv[e] = ((const u64*)s_vals)[s0 + e];
+      } else if (in.val_bytes == 4) {
+        u32* gv = (u32*)out.vals[d] + g0;
+        for (u32 e = threadIdx.x; e < n_d; e += BW_PART_THREADS) gv[e] = ((const u32*)s_vals)[s0 + e];
+      }
+      if (in.ts) {
+        i64* gt = out.ts[d] + g0;
+        for (u32 e = threadIdx.x; e < n_d; e += BW_PART_THREADS) gt[e] = s_ts[s0 + e];
       }
     }
     __syncthreads();

@@ -378,6 +378,17 @@ k_fold(BatchView bv, Table t, FoldParams p, u32 batch_no, u64 g_base) {
   for (u64 base = (u64)blockIdx.x * tile; base < total; base += (u64)gridDim.x * tile) {
     // a warp owns BW_FOLD_UNROLL runs of 32 consecutive events
     const u64 wbase = base + (u64)warp * (32 * BW_FOLD_UNROLL);
+    // after an exchange the activation is up to 8 segments: resolve the segment once per warp-run
+    // when the whole run lies inside one (all but <= 7 runs of a launch do)
+    int wseg = 0;
+    bool wuni = true;
+    if (bv.nseg > 1) {
+      const u64 wlast = (wbase + 32 * BW_FOLD_UNROLL - 1 < total) ? wbase + 32 * BW_FOLD_UNROLL - 1 : total - 1;
+#pragma unroll
+      for (int j = 1; j < BW_MAX_WORLD; ++j)
+        if (j < bv.nseg && wbase >= seg_start[j]) wseg = j;
+      wuni = (wseg + 1 >= bv.nseg) || (wlast < seg_start[wseg + 1]);
+    }
     u64 key[BW_FOLD_UNROLL], raw[BW_FOLD_UNROLL];
     // phase A: stream the events in, then issue every home-slot read before using any
 #pragma unroll
@@ -386,9 +397,9 @@ k_fold(BatchView bv, Table t, FoldParams p, u32 batch_no, u64 g_base) {
       key[u] = 0;
       raw[u] = 0;
       if (g < total) {
-        int seg = 0;
-        u64 off = g;
-        if (bv.nseg > 1) bw_locate(bv, seg_start, g, seg, off);
+        int seg = wseg;
+        u64 off = g - seg_start[wseg];
+        if (!wuni) bw_locate(bv, seg_start, g, seg, off);
         key[u] = bw_ld_stream_u64(bv.keys[seg] + off);
         if (p.ts_from_value || bv.vals[seg]) {
           raw[u] = (p.val_dtype == 2) ? (u64)bw_ld_stream_u32((const u32*)bv.vals[seg] + off)

@@ -60,7 +60,20 @@ k_prepass_ranges(BatchView bv, FoldParams p, i64* range_min, i64* range_max, u32
         if (val[j]) {
           int seg = 0;
           u64 off = g;
-          if (bv.nseg > 1) bw_locate(bv, seg_start, g, seg, off);
+          if (bv.nseg > 1) {
+            // resolve the segment once per 32-row chunk when the chunk lies inside one segment
+            const u64 g0 = g - lane;
+            int cs = 0;
+#pragma unroll
+            for (int q = 1; q < BW_MAX_WORLD; ++q)
+              if (q < bv.nseg && g0 >= seg_start[q]) cs = q;
+            if (cs + 1 >= bv.nseg || g0 + 31 < seg_start[cs + 1]) {
+              seg = cs;
+              off = g - seg_start[cs];
+            } else {
+              bw_locate(bv, seg_start, g, seg, off);
+            }
+          }
           tsv[j] = bw_load_ts(bv, seg, off, p);
         }
       }

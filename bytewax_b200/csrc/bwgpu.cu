@@ -79,6 +79,34 @@ struct Stage {  // device staging for host-ingested batches
   bool used = false;
 };
 
+// optional per-phase timing (env BW_TIMING=1): events on the streams, summed at destroy
+struct PhaseTimer {
+  static const int NPH = 8;
+  const char* names[NPH] = {"part_hist+scan+scatter", "barrier", "prepass", "fold", "close", "", "", ""};
+  std::vector<cudaEvent_t> ev[NPH][2];
+  bool on = false;
+  void mark(int ph, int which, cudaStream_t s) {
+    if (!on) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, s);
+    ev[ph][which].push_back(e);
+  }
+  void report(int rank) {
+    if (!on) return;
+    for (int p = 0; p < NPH; ++p) {
+      size_t n = std::min(ev[p][0].size(), ev[p][1].size());
+      if (!n) continue;
+      double tot = 0;
+      for (size_t i = 0; i < n; ++i) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ev[p][0][i], ev[p][1][i]) == cudaSuccess) tot += ms;
+      }
+      fprintf(stderr, "[bwgpu rank %d] %-24s n=%zu avg %.3f ms\n", rank, names[p], n, tot / n);
+    }
+  }
+};
+
 struct EventPair {
   cudaEvent_t a, b;
   u64 rows;
@@ -92,7 +120,9 @@ struct bw_fold {
   EmitBufs e{};
   Counters* d_ctr = nullptr;
   Counters* h_ctr = nullptr;  // pinned mirror
-  cudaStream_t s_compute = nullptr, s_copy = nullptr, s_pre = nullptr;
+  cudaStream_t s_compute = nullptr, s_copy = nullptr, s_pre = nullptr, s_x = nullptr;  // s_x: partition + exchange
+  cudaEvent_t ev_fold_done = nullptr, ev_xchg_done = nullptr, ev_src_ready = nullptr;
+  bool fold_recorded = false;
   cudaEvent_t ev_in = nullptr, ev_pre = nullptr, ev_h2d = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
   int val_bytes = 8;
   bool has_vals = true, has_ts = false;
@@ -149,6 +179,7 @@ struct bw_fold {
   bw_stats st{};
   std::vector<EventPair> timers;
   size_t timers_used = 0;
+  PhaseTimer pt;
 };
 
 #define FAIL(f, code, ...) CTX_FAIL((f)->ctx, code, __VA_ARGS__)
@@ -400,6 +431,10 @@ static bw_status fold_alloc(bw_fold* f) {
   CU(ctx, cudaStreamCreateWithFlags(&f->s_compute, cudaStreamNonBlocking));
   CU(ctx, cudaStreamCreateWithFlags(&f->s_copy, cudaStreamNonBlocking));
   CU(ctx, cudaStreamCreateWithFlags(&f->s_pre, cudaStreamNonBlocking));
+  CU(ctx, cudaStreamCreateWithFlags(&f->s_x, cudaStreamNonBlocking));
+  CU(ctx, cudaEventCreateWithFlags(&f->ev_fold_done, cudaEventDisableTiming));
+  CU(ctx, cudaEventCreateWithFlags(&f->ev_xchg_done, cudaEventDisableTiming));
+  CU(ctx, cudaEventCreateWithFlags(&f->ev_src_ready, cudaEventDisableTiming));
   CU(ctx, cudaEventCreateWithFlags(&f->ev_in, cudaEventDisableTiming));
   CU(ctx, cudaEventCreateWithFlags(&f->ev_pre, cudaEventDisableTiming));
   CU(ctx, cudaEventCreateWithFlags(&f->ev_h2d, cudaEventDisableTiming));
@@ -408,6 +443,7 @@ static bw_status fold_alloc(bw_fold* f) {
   // window-boundary activations by 15-30 %; plain LRU + evict_first input loads is faster.
   int occ = 0;
   f->fold_kernel = pick_fold_kernel(f->p);
+  f->pt.on = getenv("BW_TIMING") != nullptr;
   if (const char* e = getenv("BW_SUB_ROWS")) {
     long long v = atoll(e);
     if (v >= 1024) f->sub_rows = (u64)v;
@@ -454,6 +490,7 @@ static bw_status xchg_setup(bw_fold* f) {
   f->xchg_bytes = L.total;
   CU(ctx, cudaMalloc(&f->xchg_base, L.total));
   CU(ctx, cudaMemset(f->xchg_base, 0, L.total));
+  CU(ctx, cudaFuncSetAttribute(k_part_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_PART_TILE * 24));
   u64 ntiles = (f->spec.max_batch_rows + BW_PART_TILE - 1) / BW_PART_TILE + 1;
   CU(ctx, dmalloc(&f->d_tile_counts, ntiles * BW_MAX_WORLD));
   if (f->spec.exchange == BW_XCHG_P2P) {
@@ -585,6 +622,7 @@ void bw_fold_destroy(bw_fold* f) {
   if (!f) return;
   cudaSetDevice(f->ctx->device);
   cudaDeviceSynchronize();
+  f->pt.report(f->ctx->rank);
   for (int r = 0; r < f->ctx->world; ++r)
     if (f->peer_base[r] && r != f->ctx->rank && f->spec.exchange == BW_XCHG_P2P) cudaIpcCloseMemHandle(f->peer_base[r]);
   void* dev[] = {f->t.hot, f->t.p1, f->t.closed_upto, f->t.aux, f->t.nodes, f->t.node_acc2, f->t.free_stack, f->t.dirty, f->d_ctr, f->e.c_key,
@@ -617,6 +655,7 @@ void bw_fold_destroy(bw_fold* f) {
   if (f->s_compute) cudaStreamDestroy(f->s_compute);
   if (f->s_copy) cudaStreamDestroy(f->s_copy);
   if (f->s_pre) cudaStreamDestroy(f->s_pre);
+  if (f->s_x) cudaStreamDestroy(f->s_x);
   if (f->ev_in) cudaEventDestroy(f->ev_in);
   if (f->ev_pre) cudaEventDestroy(f->ev_pre);
   if (f->ev_h2d) cudaEventDestroy(f->ev_h2d);
@@ -676,7 +715,12 @@ static bw_status slow_path(bw_fold* f, const BatchView& bv, u64 total, u64 epoch
 static bw_status exchange(bw_fold* f, const u64* d_keys, const void* d_vals, const i64* d_ts, u64 rows, BatchView* bv) {
   bw_ctx* ctx = f->ctx;
   const int W = ctx->world, R = ctx->rank;
-  cudaStream_t s = f->s_compute;
+  // Partition + exchange run on their own stream so that the scatter of activation b+1 (NVLink-bound)
+  // overlaps the fold of activation b.  The producer of the input columns is ordered before it through
+  // ev_src_ready; the barrier waits for this rank's fold of the previous activation, which is what makes
+  // the double-buffered receive regions safe to overwrite two activations later.
+  cudaStream_t s = f->s_x;
+  CU(ctx, cudaStreamWaitEvent(s, f->ev_src_ready, 0));
   const int buf = f->xbuf;
   f->xbuf ^= 1;
   XLayout L = xlayout(f);
@@ -708,13 +752,18 @@ static bw_status exchange(bw_fold* f, const u64* d_keys, const void* d_vals, con
   }
   const u64 ntiles = (rows + BW_PART_TILE - 1) / BW_PART_TILE;
   int grid = (int)std::min<u64>(std::max<u64>(ntiles, 1), (u64)ctx->sm_count * 8);
+  f->pt.mark(0, 0, s);
   k_part_hist<<<grid, BW_PART_THREADS, 0, s>>>(in, f->d_tile_counts);
   k_part_scan<<<1, 1024, 0, s>>>(rows, W, f->d_tile_counts, po, f->d_ctr);
-  k_part_scatter<<<grid, BW_PART_THREADS, 0, s>>>(in, f->d_tile_counts, po);
+  const size_t stage_bytes = (size_t)BW_PART_TILE * (8 + (size_t)in.val_bytes + (in.ts ? 8 : 0));
+  k_part_scatter<<<grid, BW_PART_THREADS, stage_bytes, s>>>(in, f->d_tile_counts, po);
   CU(ctx, cudaGetLastError());
   f->st.kernel_launches += 3;
+  f->pt.mark(0, 1, s);
   char* mine = (char*)f->xchg_base;
   u64* my_counts = (u64*)(mine + L.counts_off[buf]);
+  if (f->fold_recorded) CU(ctx, cudaStreamWaitEvent(s, f->ev_fold_done, 0));
+  f->pt.mark(1, 0, s);
   if (p2p) {
     // every rank's stores are complete once it enters this collective (stream
     // order); its completion here means all peers have entered it.
@@ -749,6 +798,9 @@ static bw_status exchange(bw_fold* f, const u64* d_keys, const void* d_vals, con
     // recv_counts is a stack array: make the copy complete before returning
     CU(ctx, cudaStreamSynchronize(s));
   }
+  f->pt.mark(1, 1, s);
+  CU(ctx, cudaEventRecord(f->ev_xchg_done, s));
+  CU(ctx, cudaStreamWaitEvent(f->s_compute, f->ev_xchg_done, 0));
   memset(bv, 0, sizeof *bv);
   bv->nseg = W;
   bv->counts_on_device = 1;
@@ -796,10 +848,12 @@ static bw_status run_batch(bw_fold* f, const u64* d_keys, const void* d_vals, co
     const u64 nranges = (max_total + BW_RANGE_ROWS - 1) / BW_RANGE_ROWS;
     int grid = (int)std::min<u64>((nranges * 32 + BW_PRE_THREADS - 1) / BW_PRE_THREADS, (u64)ctx->sm_count * 8);
     if (grid < 1) grid = 1;
+    f->pt.mark(2, 0, pre_stream);
     k_prepass_ranges<<<grid, BW_PRE_THREADS, 0, pre_stream>>>(bv, f->p, f->d_rmin, f->d_rmax, f->d_rbad);
     k_prepass_scan<<<1, 1024, 0, pre_stream>>>(bv, f->p, f->d_rmin, f->d_rmax, f->d_rbad, f->d_ctr, f->d_verdict);
     CU(ctx, cudaGetLastError());
     f->st.kernel_launches += 2;
+    f->pt.mark(2, 1, pre_stream);
     CU(ctx, cudaMemcpyAsync(f->h_verdict, f->d_verdict, sizeof(u32), cudaMemcpyDeviceToHost, pre_stream));
     CU(ctx, cudaEventRecord(f->ev_pre, pre_stream));
     CU(ctx, cudaEventSynchronize(f->ev_pre));
@@ -836,6 +890,10 @@ static bw_status run_batch(bw_fold* f, const u64* d_keys, const void* d_vals, co
         if (ep) CU(ctx, cudaEventRecord(ep->b, f->s_compute));
         f->st.kernel_launches++;
         f->st.fold_launches++;
+        if (f->pt.on && ep) {
+          f->pt.ev[3][0].push_back(ep->a);
+          f->pt.ev[3][1].push_back(ep->b);
+        }
         if (lo + n < max_total) {
           k_close_dirty<<<f->close_grid, 256, 0, f->s_compute>>>(f->t, f->p, f->e, ord);
           k_reset_dirty<<<1, 1, 0, f->s_compute>>>(f->t);
@@ -855,10 +913,16 @@ static bw_status run_batch(bw_fold* f, const u64* d_keys, const void* d_vals, co
       if (st != BW_OK) return st;
       f->st.slow_batches++;
     }
+    f->pt.mark(4, 0, f->s_compute);
     k_close_dirty<<<f->close_grid, 256, 0, f->s_compute>>>(f->t, f->p, f->e, ord);
     k_reset_dirty<<<1, 1, 0, f->s_compute>>>(f->t);
     CU(ctx, cudaGetLastError());
     f->st.kernel_launches += 2;
+    f->pt.mark(4, 1, f->s_compute);
+  }
+  if (ctx->world > 1) {
+    CU(ctx, cudaEventRecord(f->ev_fold_done, f->s_compute));
+    f->fold_recorded = true;
   }
   return BW_OK;
 }
@@ -891,6 +955,7 @@ bw_status bw_ingest_commit(bw_fold* f, const bw_batch* batch, uint64_t rows, uin
   CU(ctx, cudaEventRecord(f->ev_h2d, f->s_copy));
   CU(ctx, cudaStreamWaitEvent(f->s_compute, f->ev_h2d, 0));
   CU(ctx, cudaEventRecord(f->ev_in, f->s_copy));
+  CU(ctx, cudaEventRecord(f->ev_src_ready, f->s_copy));
   bw_status st = run_batch(f, sg.d_keys, sg.d_vals, sg.d_ts, rows, epoch);
   if (st != BW_OK) return st;
   CU(ctx, cudaEventRecord(sg.consumed, f->s_compute));
@@ -911,6 +976,9 @@ bw_status bw_ingest_device(bw_fold* f, const uint64_t* d_keys, const void* d_val
     FAIL(f, BW_ERR_SPEC, "ingest: missing column");
   CU(ctx, cudaSetDevice(ctx->device));
   CU(ctx, cudaEventRecord(f->ev_in, f->s_compute));
+  // multi-GPU: the caller's columns must already be complete (see bwgpu.h); no ordering with the fold's
+  // stream is taken, so that this activation's exchange can overlap the previous activation's fold
+  CU(ctx, cudaEventRecord(f->ev_src_ready, f->s_x));
   return run_batch(f, d_keys, d_vals, d_ts_us, rows, epoch);
 }
 
@@ -1194,6 +1262,7 @@ bw_status bw_fold_sync(bw_fold* f) {
   CU(f->ctx, cudaSetDevice(f->ctx->device));
   CU(f->ctx, cudaStreamSynchronize(f->s_copy));
   CU(f->ctx, cudaStreamSynchronize(f->s_pre));
+  CU(f->ctx, cudaStreamSynchronize(f->s_x));
   CU(f->ctx, cudaStreamSynchronize(f->s_compute));
   return BW_OK;
 }
@@ -1208,6 +1277,7 @@ bw_status bw_fold_time_begin(bw_fold* f) {
   // everything submitted so far (copies, prepass) must be done before the clock starts
   CU(ctx, cudaStreamSynchronize(f->s_copy));
   CU(ctx, cudaStreamSynchronize(f->s_pre));
+  CU(ctx, cudaStreamSynchronize(f->s_x));
   CU(ctx, cudaStreamSynchronize(f->s_compute));
   CU(ctx, cudaEventRecord(f->ev_t0, f->s_compute));
   return BW_OK;
@@ -1217,6 +1287,7 @@ bw_status bw_fold_time_end(bw_fold* f, float* ms) {
   bw_ctx* ctx = f->ctx;
   CU(ctx, cudaStreamSynchronize(f->s_copy));
   CU(ctx, cudaStreamSynchronize(f->s_pre));
+  CU(ctx, cudaStreamSynchronize(f->s_x));
   CU(ctx, cudaEventRecord(f->ev_t1, f->s_compute));
   CU(ctx, cudaEventSynchronize(f->ev_t1));
   CU(ctx, cudaEventElapsedTime(ms, f->ev_t0, f->ev_t1));

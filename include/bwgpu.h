@@ -207,7 +207,10 @@ bw_status bw_ingest_commit(bw_fold* fold, const bw_batch* batch, uint64_t rows, 
 
 /* Same as acquire+commit for columns already resident in device memory
  * (they must stay valid until the next bw_ingest_* / bw_advance / bw_eof
- * call on this fold returns). */
+ * call on this fold returns).  When world > 1 the columns must be completely
+ * written before the call: the exchange runs on its own stream so that it can
+ * overlap the previous activation's fold, and takes no ordering from the
+ * fold's stream. */
 bw_status bw_ingest_device(bw_fold* fold, const uint64_t* d_keys, const void* d_vals,
                            const int64_t* d_ts_us, uint64_t rows, uint64_t epoch);
 
