@@ -81,6 +81,20 @@ k_prepass_ranges(BatchView bv, FoldParams p, i64* range_min, i64* range_max, u32
       for (int j = 0; j < BW_PRE_MLP; ++j) {
         const bool valid = val[j];
         const i64 ts = tsv[j];
+        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+        if (vmask == 0u) continue;  // uniform
+        // cheap case first: the 32 timestamps are already non-decreasing (in-order streams)
+        const i64 prev = __shfl_up_sync(0xffffffffu, ts, 1);
+        const bool in_order = !valid || lane == 0 || ts >= prev;
+        if (__all_sync(0xffffffffu, in_order)) {
+          const int last_lane = 31 - __clz(vmask);
+          const i64 first = __shfl_sync(0xffffffffu, ts, 0);
+          const i64 last = __shfl_sync(0xffffffffu, ts, last_lane);
+          if (first < bw_sub_sat(run_max, p.wait_us)) bad = true;
+          if (first < rmin) rmin = first;
+          if (last > run_max) run_max = last;
+          continue;
+        }
         i64 incl = ts;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
