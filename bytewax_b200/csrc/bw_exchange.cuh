@@ -75,13 +75,13 @@ __global__ void __launch_bounds__(BW_PART_THREADS) k_part_hist(PartIn in, u32* t
   }
 }
 
-// one block of 1024 threads; tile_counts -> exclusive offsets in place, totals published
+// one block of 1024 threads per destination (grid = world); tile_counts -> exclusive offsets in place, totals published
 __global__ void __launch_bounds__(1024) k_part_scan(u64 n, int world, u32* tile_counts, PartOut out, Counters* ctr) {
   __shared__ u32 strip[1024];
   const u64 ntiles = (n + BW_PART_TILE - 1) / BW_PART_TILE;
   const u64 per = (ntiles + blockDim.x - 1) / blockDim.x;
   const u64 lo = (u64)threadIdx.x * per, hi = (lo + per < ntiles) ? lo + per : ntiles;
-  for (int d = 0; d < world; ++d) {
+  for (int d = blockIdx.x; d < world; d += gridDim.x) {
     u32 s = 0;
     for (u64 t = lo; t < hi; ++t) s += tile_counts[t * BW_MAX_WORLD + d];
     strip[threadIdx.x] = s;

@@ -431,7 +431,8 @@ static bw_status fold_alloc(bw_fold* f) {
   CU(ctx, cudaStreamCreateWithFlags(&f->s_compute, cudaStreamNonBlocking));
   CU(ctx, cudaStreamCreateWithFlags(&f->s_copy, cudaStreamNonBlocking));
   CU(ctx, cudaStreamCreateWithFlags(&f->s_pre, cudaStreamNonBlocking));
-  CU(ctx, cudaStreamCreateWithFlags(&f->s_x, cudaStreamNonBlocking));
+  if (getenv("BW_NO_OVERLAP")) f->s_x = f->s_compute;  // diagnostic: serialise exchange and fold
+  else CU(ctx, cudaStreamCreateWithFlags(&f->s_x, cudaStreamNonBlocking));
   CU(ctx, cudaEventCreateWithFlags(&f->ev_fold_done, cudaEventDisableTiming));
   CU(ctx, cudaEventCreateWithFlags(&f->ev_xchg_done, cudaEventDisableTiming));
   CU(ctx, cudaEventCreateWithFlags(&f->ev_src_ready, cudaEventDisableTiming));
@@ -451,6 +452,9 @@ static bw_status fold_alloc(bw_fold* f) {
   CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, f->fold_kernel, BW_FOLD_THREADS, 0));
   if (occ < 1) occ = 1;
   f->fold_grid = ctx->sm_count * occ;
+  // multi-GPU: leave register-file room on every SM so the next activation's partition/scatter
+  // (NVLink-bound, on its own stream) can really run beside the fold instead of queueing behind it
+  if (ctx->world > 1 && occ > 2 && !getenv("BW_FOLD_FULL")) f->fold_grid = ctx->sm_count * 2;
   f->close_grid = ctx->sm_count * 8;
   k_init_table<<<ctx->sm_count * 8, 256, 0, f->s_compute>>>(f->t, f->p.acc_identity);
   CU(ctx, cudaGetLastError());
@@ -655,7 +659,7 @@ void bw_fold_destroy(bw_fold* f) {
   if (f->s_compute) cudaStreamDestroy(f->s_compute);
   if (f->s_copy) cudaStreamDestroy(f->s_copy);
   if (f->s_pre) cudaStreamDestroy(f->s_pre);
-  if (f->s_x) cudaStreamDestroy(f->s_x);
+  if (f->s_x && f->s_x != f->s_compute) cudaStreamDestroy(f->s_x);
   if (f->ev_in) cudaEventDestroy(f->ev_in);
   if (f->ev_pre) cudaEventDestroy(f->ev_pre);
   if (f->ev_h2d) cudaEventDestroy(f->ev_h2d);
@@ -754,7 +758,7 @@ static bw_status exchange(bw_fold* f, const u64* d_keys, const void* d_vals, con
   int grid = (int)std::min<u64>(std::max<u64>(ntiles, 1), (u64)ctx->sm_count * 8);
   f->pt.mark(0, 0, s);
   k_part_hist<<<grid, BW_PART_THREADS, 0, s>>>(in, f->d_tile_counts);
-  k_part_scan<<<1, 1024, 0, s>>>(rows, W, f->d_tile_counts, po, f->d_ctr);
+  k_part_scan<<<W, 1024, 0, s>>>(rows, W, f->d_tile_counts, po, f->d_ctr);
   const size_t stage_bytes = (size_t)BW_PART_TILE * (8 + (size_t)in.val_bytes + (in.ts ? 8 : 0));
   k_part_scatter<<<grid, BW_PART_THREADS, stage_bytes, s>>>(in, f->d_tile_counts, po);
   CU(ctx, cudaGetLastError());
@@ -799,8 +803,6 @@ static bw_status exchange(bw_fold* f, const u64* d_keys, const void* d_vals, con
     CU(ctx, cudaStreamSynchronize(s));
   }
   f->pt.mark(1, 1, s);
-  CU(ctx, cudaEventRecord(f->ev_xchg_done, s));
-  CU(ctx, cudaStreamWaitEvent(f->s_compute, f->ev_xchg_done, 0));
   memset(bv, 0, sizeof *bv);
   bv->nseg = W;
   bv->counts_on_device = 1;
@@ -832,7 +834,7 @@ static bw_status run_batch(bw_fold* f, const u64* d_keys, const void* d_vals, co
     bw_status st = exchange(f, d_keys, d_vals, d_ts, rows, &bv);
     if (st != BW_OK) return st;
     max_total = f->max_recv_rows;
-    pre_stream = f->s_compute;  // received counts live on the device: keep one stream
+    pre_stream = f->s_x;  // the verdict is computed right behind the exchange, beside the previous fold
   } else {
     bv.nseg = 1;
     bv.keys[0] = d_keys;
@@ -844,7 +846,7 @@ static bw_status run_batch(bw_fold* f, const u64* d_keys, const void* d_vals, co
   }
   bool clean = true;
   if (f->p.track_wm && max_total > 0) {
-    if (pre_stream != f->s_compute) CU(ctx, cudaStreamWaitEvent(pre_stream, f->ev_in, 0));
+    if (pre_stream != f->s_compute && ctx->world == 1) CU(ctx, cudaStreamWaitEvent(pre_stream, f->ev_in, 0));
     const u64 nranges = (max_total + BW_RANGE_ROWS - 1) / BW_RANGE_ROWS;
     int grid = (int)std::min<u64>((nranges * 32 + BW_PRE_THREADS - 1) / BW_PRE_THREADS, (u64)ctx->sm_count * 8);
     if (grid < 1) grid = 1;
@@ -859,6 +861,10 @@ static bw_status run_batch(bw_fold* f, const u64* d_keys, const void* d_vals, co
     CU(ctx, cudaEventSynchronize(f->ev_pre));
     clean = (*f->h_verdict != 0);
     if (pre_stream != f->s_compute) CU(ctx, cudaStreamWaitEvent(f->s_compute, f->ev_pre, 0));
+  }
+  if (ctx->world > 1) {  // the fold may start once the exchange (and the verdict pass behind it) is done
+    CU(ctx, cudaEventRecord(f->ev_xchg_done, f->s_x));
+    CU(ctx, cudaStreamWaitEvent(f->s_compute, f->ev_xchg_done, 0));
   }
   if (max_total > 0) {
     if (clean) {

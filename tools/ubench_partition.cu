@@ -16,7 +16,7 @@ int main(){
     float t[3]={0,0,0};
     for(int rep=0;rep<4;++rep){
       cudaEventRecord(e[0]); k_part_hist<<<grid,BW_PART_THREADS>>>(in,tc);
-      cudaEventRecord(e[1]); k_part_scan<<<1,1024>>>(n,world,tc,po,ctr);
+      cudaEventRecord(e[1]); k_part_scan<<<world,1024>>>(n,world,tc,po,ctr);
       cudaEventRecord(e[2]); k_part_scatter<<<grid,BW_PART_THREADS,(size_t)BW_PART_TILE*16>>>(in,tc,po);
       cudaEventRecord(e[3]); cudaEventSynchronize(e[3]);
       if(rep){ for(int i=0;i<3;++i){ float ms; cudaEventElapsedTime(&ms,e[i],e[i+1]); t[i]+=ms/3; } }
