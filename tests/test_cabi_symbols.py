@@ -73,17 +73,21 @@ def test_no_gpu_fails_loudly(lib):
     """Without a device the product path must error, not fall back."""
     import ctypes
 
-    h = ctypes.c_void_p()
-    st = lib.bw_ctx_create(0, 0, 1, None, ctypes.byref(h))
     try:
         import torch
 
         has_gpu = torch.cuda.is_available()
     except Exception:
         has_gpu = False
+    h = ctypes.c_void_p()
+    st = lib.bw_ctx_create(0, 0, 1, None, ctypes.byref(h))
     if has_gpu:
         assert st == 0
         lib.bw_ctx_destroy(h)
     else:
-        assert st == N.STATUS_NAMES.keys().__iter__().__next__() + 1 or st != 0
-        assert b"CUDA" in lib.bw_last_global_error() or b"device" in lib.bw_last_global_error()
+        assert st == 1  # BW_ERR_CUDA
+        assert b"CUDA device" in lib.bw_last_global_error()
+        from bytewax_b200 import gpu
+
+        with pytest.raises(N.BwError):
+            gpu.Context(0)
