@@ -144,12 +144,15 @@ def share_nccl_id(dist, rank, local):
 
 
 def run_gpu(args):
+    if args.ts_stride != 1:
+        import torch  # noqa: F401  (diagnostic mode only; torch must load its own NCCL before libbwgpu loads the system one)
     from bytewax_b200 import _native as N, gpu
 
     rank, world, local, dist = dist_setup(args.gpus)
     nccl_id = share_nccl_id(dist, rank, local) if world > 1 else None
     ctx = gpu.Context(local, rank, world, nccl_id)
     K, W, B = args.steps, args.warmup, args.batch_rows
+    N_KEYS = args.n_keys
 
     def make_fold(ring_slots=3, emit_order=N.ORDER_REFERENCE):
         return gpu.WindowFold(
@@ -166,6 +169,18 @@ def run_gpu(args):
     for s in range(nbuf):
         fold.gen_c1(dk[s], dv[s], (s * world + rank) * B, B, N_KEYS)
     fold.sync()
+    if args.ts_stride != 1:
+        # diagnostic: stretch event time (ts = stride * row index) to reproduce on one GPU the
+        # activations of an N-rank job, which span N x 2^24 us each
+        import torch
+
+        scratch = torch.empty(B, dtype=torch.int64, device=f"cuda:{local}")
+        for s in range(nbuf):
+            ctx.lib.bw_memcpy(ctx.h, C.c_void_p(scratch.data_ptr()), C.c_void_p(dv[s]), B * 8, 2)
+            scratch.mul_(args.ts_stride)
+            torch.cuda.synchronize(local)
+            ctx.lib.bw_memcpy(ctx.h, C.c_void_p(dv[s]), C.c_void_p(scratch.data_ptr()), B * 8, 2)
+        del scratch
     # warm-up: W untimed steps on a scratch fold (same shapes), then a fresh fold for the job
     for s in range(W):
         fold.ingest_device(dk[K + s], dv[K + s], None, B)
@@ -190,7 +205,10 @@ def run_gpu(args):
     total_counts = int(em.closed_acc.sum()) + int(em_eof.closed_acc.sum())
     launches = int(st1.kernel_launches - st0.kernel_launches)
     fold_ms_avg = st1.sum_fold_ms / max(1, st1.fold_launches)
-    rows_per_fold = st1.fold_rows / max(1, st1.fold_launches) if world == 1 else B  # ~B per rank after the exchange
+    # rows per fold launch (an activation may be folded in several sub-range launches); ~B per rank per step after an exchange
+    rows_per_fold = st1.fold_rows / max(1, st1.fold_launches) if world == 1 else K * B / max(1, st1.fold_launches)
+    combined = int(st1.combined_folds)
+    fold_path = "direct" if combined == 0 else ("combine" if combined == st1.fold_launches else "mixed")
     fold.close()
     for p in dk + dv:
         ctx.dev_free(p)
@@ -225,12 +243,15 @@ def run_gpu(args):
                 "l2": "inputs larger than L2 (each step reads a distinct 256 MiB batch; 16 GiB resident)",
                 "exchange": ("none" if world == 1 else args.exchange), "emit_order": "reference",
                 "sum_of_counts_check": total_counts,
+                "fold_path": fold_path,
             },
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": launches,
             "roofline": {
-                "bound": "hbm", "kernel": "k_fold", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "bound": "hbm",
+                "kernel": "k_fold" if fold_path == "direct" else "fold stage: k_bkt_hist + k_bkt_scan + k_bkt_base + k_bkt_scatter + k_fold_seg",
+                "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_event": BYTES_PER_EVENT,
                 "avg_launch_ms": fold_ms_avg, "rows_per_launch": rows_per_fold,
@@ -354,6 +375,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--batch-rows", type=int, default=BATCH_ROWS)
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"])
+    ap.add_argument("--n-keys", type=int, default=N_KEYS, help="diagnostic: key cardinality (the metric is quoted at the default)")
+    ap.add_argument("--ts-stride", type=int, default=1, help="diagnostic: event time advances this many us per row")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

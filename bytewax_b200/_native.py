@@ -63,7 +63,7 @@ class BwStats(C.Structure):
         ("kernel_launches", C.c_uint64), ("rows_ingested", C.c_uint64), ("rows_received", C.c_uint64),
         ("slow_batches", C.c_uint64), ("live_keys", C.c_uint64), ("table_capacity", C.c_uint64),
         ("pane_nodes_used", C.c_uint64), ("last_fold_ms", C.c_float), ("sum_fold_ms", C.c_float),
-        ("fold_launches", C.c_uint64), ("fold_rows", C.c_uint64),
+        ("fold_launches", C.c_uint64), ("fold_rows", C.c_uint64), ("combined_folds", C.c_uint64),
     ]
 
 

@@ -38,9 +38,14 @@ typedef FoldCfg<-1, -1, -1> FoldCfgRuntime;
 #define BW_FOLD_WARPS (BW_FOLD_THREADS / 32)
 #define BW_WARP_DEFER_CAP (32 * BW_FOLD_UNROLL)
 #define BW_NO_SLOT 0xFFFFFFFFu
-struct BlockSinks {
+// Staging of the rare global appends: common to every fold kernel.
+struct DirtySink {
   u32 n_dirty;
   u32 n_new_keys;
+  u32 cap;    // entries in buf
+  u32* buf;   // shared-memory staging of dirty slot indices
+};
+struct BlockSinks : DirtySink {
   u32 dirty[BW_SINK_CAP];
   // per-warp queues of deferred events (arrival index within the batch)
   u32 n_defer[BW_FOLD_WARPS];
@@ -51,19 +56,21 @@ __device__ __forceinline__ void bw_sinks_init(BlockSinks* sk) {
   if (threadIdx.x == 0) {
     sk->n_dirty = 0;
     sk->n_new_keys = 0;
+    sk->cap = BW_SINK_CAP;
+    sk->buf = sk->dirty;
   }
   if (threadIdx.x < BW_FOLD_WARPS) sk->n_defer[threadIdx.x] = 0;
 }
 // call by all threads of the block, after a __syncthreads()
-__device__ __forceinline__ void bw_sinks_flush(BlockSinks* sk, const Table& t) {
+__device__ __forceinline__ void bw_sinks_flush(DirtySink* sk, const Table& t) {
   __shared__ u32 base;
-  u32 n = sk->n_dirty < BW_SINK_CAP ? sk->n_dirty : BW_SINK_CAP;
+  u32 n = sk->n_dirty < sk->cap ? sk->n_dirty : sk->cap;
   if (threadIdx.x == 0) {
     base = n ? atomicAdd(&t.ctr->dirty_count, n) : 0u;
     if (sk->n_new_keys) atomicAdd(&t.ctr->live_keys, (unsigned long long)sk->n_new_keys);
   }
   __syncthreads();
-  for (u32 i = threadIdx.x; i < n; i += blockDim.x) t.dirty[base + i] = sk->dirty[i];
+  for (u32 i = threadIdx.x; i < n; i += blockDim.x) t.dirty[base + i] = sk->buf[i];
   __syncthreads();
   if (threadIdx.x == 0) {
     sk->n_dirty = 0;
@@ -91,14 +98,16 @@ __device__ __forceinline__ u64 bw_home_slot(const Table& t, u64 key) {
 // consecutive slots are fetched per round trip (independent LDG.256s), so a
 // linear-probe chain costs ceil(len / 4) L2 latencies.  Returns ~0 on a full table.
 #define BW_PROBE_WIDTH 4
-__device__ __forceinline__ u64 bw_find_slot(const Table& t, BlockSinks* sk, u64 key, i64& max_ts, i64& wt0) {
+__device__ __forceinline__ u64 bw_find_slot(const Table& t, DirtySink* sk, u64 key, i64& max_ts, i64& wt0) {
   u64 s = bw_home_slot(t, key);
   if (key == BW_EMPTY_KEY) {  // alias slot: always "found"
     u64 k, a;
     bw_ld_slot(t.hot + s, k, max_ts, wt0, a);
     return s;
   }
-  for (u64 probe = 0; probe < t.cap; probe += BW_PROBE_WIDTH) {
+  for (u64 probe = 0; probe < t.cap;) {
+    // four independent sector loads, then pick the first slot that holds the key or is free
+    // (constant indices only: the probe state stays in registers)
     u64 k[BW_PROBE_WIDTH], a[BW_PROBE_WIDTH];
     i64 m[BW_PROBE_WIDTH], w[BW_PROBE_WIDTH];
 #pragma unroll
@@ -107,45 +116,59 @@ __device__ __forceinline__ u64 bw_find_slot(const Table& t, BlockSinks* sk, u64 
       if (sj >= t.cap) sj -= t.cap;
       bw_ld_slot(t.hot + sj, k[j], m[j], w[j], a[j]);
     }
+    int jm = BW_PROBE_WIDTH;
+    u64 kk = 0;
+    i64 mm = 0, ww = 0;
 #pragma unroll
-    for (int j = 0; j < BW_PROBE_WIDTH; ++j) {
-      u64 sj = s + j;
-      if (sj >= t.cap) sj -= t.cap;
-      if (k[j] == key) {
-        max_ts = m[j];
-        wt0 = w[j];
-        return sj;
-      }
-      if (k[j] == BW_EMPTY_KEY) {
-        HotSlot* hs = t.hot + sj;
-        u64 old = atomicCAS((unsigned long long*)&hs->key, (unsigned long long)BW_EMPTY_KEY, (unsigned long long)key);
-        if (old == BW_EMPTY_KEY) {
-          // a free slot is always in the reset state; nobody else touches it before the key is set
-          atomicAdd(&sk->n_new_keys, 1u);
-          max_ts = m[j];
-          wt0 = w[j];
-          return sj;
-        }
-        if (old == key) {
-          u64 kk, aa;
-          bw_ld_slot(hs, kk, max_ts, wt0, aa);
-          return sj;
-        }
-        // another key took it: keep probing past it
+    for (int j = BW_PROBE_WIDTH - 1; j >= 0; --j) {
+      if (k[j] == key || k[j] == BW_EMPTY_KEY) {
+        jm = j;
+        kk = k[j];
+        mm = m[j];
+        ww = w[j];
       }
     }
-    s += BW_PROBE_WIDTH;
+    if (jm == BW_PROBE_WIDTH) {
+      s += BW_PROBE_WIDTH;
+      if (s >= t.cap) s -= t.cap;
+      probe += BW_PROBE_WIDTH;
+      continue;
+    }
+    u64 sj = s + (u64)jm;
+    if (sj >= t.cap) sj -= t.cap;
+    if (kk == key) {
+      max_ts = mm;
+      wt0 = ww;
+      return sj;
+    }
+    HotSlot* hs = t.hot + sj;
+    u64 old = atomicCAS((unsigned long long*)&hs->key, (unsigned long long)BW_EMPTY_KEY, (unsigned long long)key);
+    if (old == BW_EMPTY_KEY) {
+      // a free slot is always in the reset state; nobody else touches it before the key is set
+      atomicAdd(&sk->n_new_keys, 1u);
+      max_ts = mm;
+      wt0 = ww;
+      return sj;
+    }
+    if (old == key) {
+      u64 k2, a2;
+      bw_ld_slot(hs, k2, max_ts, wt0, a2);
+      return sj;
+    }
+    // another key took it: resume right after it
+    s = sj + 1;
     if (s >= t.cap) s -= t.cap;
+    probe += (u64)jm + 1;
   }
   return ~0ULL;
 }
 
-__device__ __noinline__ void bw_mark_dirty(const Table& t, BlockSinks* sk, u64 s) {
+__device__ __noinline__ void bw_mark_dirty(const Table& t, DirtySink* sk, u64 s) {
   unsigned long long old = atomicOr((unsigned long long*)&t.hot[s].wt0, (unsigned long long)BW_TAG_DIRTY);
   if (!(old & (unsigned long long)BW_TAG_DIRTY)) {
     u32 i = atomicAdd(&sk->n_dirty, 1u);
-    if (i < BW_SINK_CAP) {
-      sk->dirty[i] = (u32)s;
+    if (i < sk->cap) {
+      sk->buf[i] = (u32)s;
     } else {  // staging full: append directly
       u32 g = atomicAdd(&t.ctr->dirty_count, 1u);
       t.dirty[g] = (u32)s;
@@ -215,7 +238,7 @@ __device__ __noinline__ u32 bw_spill_node(const Table& t, const FoldParams& p, u
 // key's earliest closable window; the event proves it closable iff
 // q - close_back - (rem < wait_rem) >= q0 - d.  255 == "always re-examine".
 template <class C>
-__device__ __forceinline__ void bw_after_fold(const Table& t, const FoldParams& p, BlockSinks* sk, u64 s, i64 ts,
+__device__ __forceinline__ void bw_after_fold(const Table& t, const FoldParams& p, DirtySink* sk, u64 s, i64 ts,
                                               i64 mts, i64 tag0, bool created, i64 q, i64 rem) {
   HotSlot* hs = t.hot + s;
   if (C::wm(p)) {
@@ -234,11 +257,64 @@ __device__ __forceinline__ void bw_after_fold(const Table& t, const FoldParams& 
   }
 }
 
+// Shared-memory write-combining of the accumulator updates of one table segment
+// (k_fold_seg).  A block that owns every event whose home slot lies in
+// [slot_base, slot_base + BW_BKT_SLOTS) folds them into shared memory with
+// native 32-bit atomics and merges each touched slot into the table once.
+#define BW_BKT_SHIFT 12
+#define BW_BKT_SLOTS (1u << BW_BKT_SHIFT)
+__device__ __forceinline__ void bw_sm_apply(int op, u64* a, u64 operand) {
+  switch (op) {
+    case BW_OP_ADD_ONE: atomicAdd((u32*)a, 1u); break;  // < 2^32 events per activation
+    case BW_OP_ADD_U64: {
+      // exact 64-bit sum from two 32-bit atomics: each add carries its own overflow up
+      const u32 lo = (u32)operand, hi = (u32)(operand >> 32);
+      const u32 old = atomicAdd((u32*)a, lo);
+      const u32 carry = ((u32)(old + lo) < old) ? 1u : 0u;
+      if (hi | carry) atomicAdd((u32*)a + 1, hi + carry);
+      break;
+    }
+    case BW_OP_ADD_F64: atomicAdd((double*)a, __longlong_as_double((i64)operand)); break;
+    case BW_OP_MIN_S64: atomicMin((long long*)a, (long long)operand); break;
+    case BW_OP_MIN_U64: atomicMin((unsigned long long*)a, (unsigned long long)operand); break;
+    case BW_OP_MAX_S64: atomicMax((long long*)a, (long long)operand); break;
+    default: atomicMax((unsigned long long*)a, (unsigned long long)operand); break;
+  }
+}
+// merge a combined delta into a table accumulator
+__device__ __forceinline__ void bw_merge(int op, u64* acc, u64 d) {
+  if (op == BW_OP_ADD_ONE) bw_red_add_u64(acc, d);
+  else bw_apply(op, acc, d);
+}
+struct SegSink {
+  u64* acc0;   // [BW_BKT_SLOTS] pane-0 deltas (identity when untouched)
+  u64* acc1;   // [BW_BKT_SLOTS] pane-1 deltas
+  u32* mts;    // [BW_BKT_SLOTS] 1 + (max event ts - base_ts), 0 == untouched
+  u32* seq1;   // [BW_BKT_SLOTS] min arrival index of a pane-1 event, ~0 == none
+  u64 slot_base;
+  i64 base_ts;
+  __device__ __forceinline__ bool owns(u64 s) const { return (s - slot_base) < (u64)BW_BKT_SLOTS; }
+  __device__ __forceinline__ u32 local(u64 s) const { return (u32)(s - slot_base); }
+  __device__ __forceinline__ void fold0(int op, u32 ls, u64 operand) const { bw_sm_apply(op, acc0 + ls, operand); }
+  __device__ __forceinline__ void fold1(int op, u32 ls, u64 operand) const { bw_sm_apply(op, acc1 + ls, operand); }
+  __device__ __forceinline__ void open1(u32 ls, u32 g) const { atomicMin(seq1 + ls, g); }
+  __device__ __forceinline__ void touch(u32 ls, i64 ts) const { atomicMax(mts + ls, (u32)(ts - base_ts) + 1u); }
+};
+struct NoSeg {
+  __device__ __forceinline__ bool owns(u64) const { return false; }
+  __device__ __forceinline__ u32 local(u64) const { return 0u; }
+  __device__ __forceinline__ void fold0(int, u32, u64) const {}
+  __device__ __forceinline__ void fold1(int, u32, u64) const {}
+  __device__ __forceinline__ void open1(u32, u32) const {}
+  __device__ __forceinline__ void touch(u32, i64) const {}
+};
+
 // General path: any event (new key, displaced key, second / further pane).
-// `seq` = (batch_no << 32) | arrival index.
-template <class C>
-__device__ __noinline__ void bw_fold_event(const Table& t, const FoldParams& p, BlockSinks* sk, u64 key, i64 ts,
-                                           u64 operand, u64 seq, u32 batch_no, u32 known_slot = BW_NO_SLOT) {
+// `seq` = (batch_no << 32) | arrival index.  `sg`: updates of slots the calling
+// block owns go to its shared-memory segment (NoSeg: everything goes to the table).
+template <class C, class SG>
+__device__ __noinline__ void bw_fold_event(const Table& t, const FoldParams& p, DirtySink* sk, u64 key, i64 ts,
+                                           u64 operand, u64 seq, u32 batch_no, u32 known_slot, const SG sg) {
   i64 rem;
   const i64 q = bw_pane_of_r(ts, p, rem);
   if (q <= -BW_WID_LIMIT || q >= BW_WID_LIMIT) {
@@ -268,14 +344,22 @@ __device__ __noinline__ void bw_fold_event(const Table& t, const FoldParams& p, 
     i64 old = (i64)atomicCAS((unsigned long long*)&hs->wt0, (unsigned long long)BW_EMPTY_WIDTAG, (unsigned long long)mine);
     tag0 = (old == BW_EMPTY_WIDTAG) ? mine : old;
   }
+  const bool own = sg.owns(s);
+  const u32 ls = sg.local(s);
   bool created = false;
   if (bw_widtag_q(tag0) == q) {
-    bw_apply(C::op(p), &hs->acc0, operand);
+    if (own) sg.fold0(C::op(p), ls, operand);
+    else bw_apply(C::op(p), &hs->acc0, operand);
     if (C::cnt(p)) bw_red_add_u64(&t.aux[s].cnt0, 1ULL);
     if (((u32)tag0 & 0x7Fu) == born) bw_red_min_u64(&t.aux[s].seq0, seq);
   } else if (bw_widtag_q1(tag0) == q) {
-    bw_apply(C::op(p), &t.p1[s].acc1, operand);
-    if (!(tag0 & BW_TAG_P1_PREV)) bw_red_min_u64(&t.p1[s].seq1, seq);  // presence + first-open order
+    if (own) {
+      sg.fold1(C::op(p), ls, operand);
+      if (!(tag0 & BW_TAG_P1_PREV)) sg.open1(ls, (u32)seq);
+    } else {
+      bw_apply(C::op(p), &t.p1[s].acc1, operand);
+      if (!(tag0 & BW_TAG_P1_PREV)) bw_red_min_u64(&t.p1[s].seq1, seq);  // presence + first-open order
+    }
     if (C::cnt(p)) bw_red_add_u64(&t.aux[s].cnt1, 1ULL);
   } else {
     u32 n = bw_spill_node(t, p, s, q, batch_no, created);
@@ -284,7 +368,13 @@ __device__ __noinline__ void bw_fold_event(const Table& t, const FoldParams& p, 
     if (C::cnt(p)) bw_red_add_u64(&t.node_acc2[n], 1ULL);
     if (t.nodes[n].born == batch_no) bw_red_min_u64(&t.nodes[n].open_seq, seq);
   }
-  bw_after_fold<C>(t, p, sk, s, ts, mts, tag0, created, q, rem);
+  if (own) {
+    // the watermark and the closability test are applied once per slot when the segment is merged
+    sg.touch(ls, ts);
+    if (created && !(tag0 & BW_TAG_DIRTY)) bw_mark_dirty(t, sk, s);
+  } else {
+    bw_after_fold<C>(t, p, sk, s, ts, mts, tag0, created, q, rem);
+  }
 }
 
 // raw value bits -> accumulator operand
@@ -357,7 +447,7 @@ __device__ __forceinline__ i64 bw_event_ts(const BatchView& bv, const u64* seg_s
 // items (or when the clock never advances on data, wait == forever).
 template <class C>
 __global__ void __launch_bounds__(BW_FOLD_THREADS, BW_FOLD_MINB)
-k_fold(BatchView bv, Table t, FoldParams p, u32 batch_no, u64 g_base) {
+k_fold(BatchView bv, Table t, FoldParams p, u32 batch_no, u32 sub_i, u32 sub_n) {
   __shared__ u64 seg_start[BW_MAX_WORLD + 1];
   __shared__ BlockSinks sinks;
   bw_sinks_init(&sinks);
@@ -370,12 +460,16 @@ k_fold(BatchView bv, Table t, FoldParams p, u32 batch_no, u64 g_base) {
     seg_start[bv.nseg] = acc;
   }
   __syncthreads();
-  const u64 total = seg_start[bv.nseg];
+  // sub-range sub_i of sub_n of the activation, by arrival index (the caller closes between
+  // sub-ranges so that a key moving through several windows keeps hitting the two direct panes)
+  const u64 all = seg_start[bv.nseg];
+  const u64 range_lo = (sub_n > 1) ? (all * sub_i) / sub_n : 0;
+  const u64 total = (sub_n > 1) ? (all * (sub_i + 1ULL)) / sub_n : all;
   const u64 tile = (u64)BW_FOLD_THREADS * BW_FOLD_UNROLL;
   const u32 born = batch_no & 63u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   u32 iter = 0;
-  for (u64 base = (u64)blockIdx.x * tile; base < total; base += (u64)gridDim.x * tile) {
+  for (u64 base = range_lo + (u64)blockIdx.x * tile; base < total; base += (u64)gridDim.x * tile) {
     // a warp owns BW_FOLD_UNROLL runs of 32 consecutive events
     const u64 wbase = base + (u64)warp * (32 * BW_FOLD_UNROLL);
     // after an exchange the activation is up to 8 segments: resolve the segment once per warp-run
@@ -431,7 +525,7 @@ k_fold(BatchView bv, Table t, FoldParams p, u32 batch_no, u64 g_base) {
       if (hit0 || hit1) {
         u64 operand;
         bw_operand(p, raw[u], operand);
-        const u64 seq = ((u64)batch_no << 32) | (g_base + g);
+        const u64 seq = ((u64)batch_no << 32) | g;
         if (hit0) {
           bw_apply(C::op(p), &t.hot[slot[u]].acc0, operand);
           if (C::cnt(p)) bw_red_add_u64(&t.aux[slot[u]].cnt0, 1ULL);
@@ -460,7 +554,7 @@ k_fold(BatchView bv, Table t, FoldParams p, u32 batch_no, u64 g_base) {
       u64 kk, op, rw;
       i64 ts;
       bw_load_event(bv, seg, off, p, kk, ts, op, rw);
-      bw_fold_event<C>(t, p, &sinks, kk, ts, op, ((u64)batch_no << 32) | (g_base + g), batch_no, sinks.dq_slot[warp][i]);
+      bw_fold_event<C, NoSeg>(t, p, &sinks, kk, ts, op, ((u64)batch_no << 32) | g, batch_no, sinks.dq_slot[warp][i], NoSeg());
     }
     __syncwarp();
     if (lane == 0) sinks.n_defer[warp] = 0;

@@ -128,18 +128,24 @@ k_prepass_ranges(BatchView bv, FoldParams p, i64* range_min, i64* range_max, u32
 // one block: chain the ranges (and the previous batches through gmax_ts)
 __global__ void __launch_bounds__(1024)
 k_prepass_scan(BatchView bv, FoldParams p, const i64* range_min, const i64* range_max, const u32* range_bad,
-               Counters* ctr, u32* verdict_out) {
+               Counters* ctr, u32* verdict_out, i64* span_out) {
   __shared__ i64 strip_max[1024];
+  __shared__ unsigned long long span_min;  // i64 bits, biased by the sign bit so that unsigned min == signed min
   __shared__ int any_bad;
   u64 total = 0;
   for (int j = 0; j < bv.nseg; ++j) total += bw_seg_count(bv, j);
   const u64 nranges = (total + BW_RANGE_ROWS - 1) / BW_RANGE_ROWS;
   const u64 per = (nranges + blockDim.x - 1) / blockDim.x;
   const u64 lo = (u64)threadIdx.x * per, hi = (lo + per < nranges) ? lo + per : nranges;
-  if (threadIdx.x == 0) any_bad = 0;
-  i64 m = INT64_MIN;
-  for (u64 r = lo; r < hi; ++r)
+  if (threadIdx.x == 0) {
+    any_bad = 0;
+    span_min = ~0ULL;
+  }
+  i64 m = INT64_MIN, mn = INT64_MAX;
+  for (u64 r = lo; r < hi; ++r) {
     if (range_max[r] > m) m = range_max[r];
+    if (range_min[r] < mn) mn = range_min[r];
+  }
   strip_max[threadIdx.x] = m;
   __syncthreads();
   const i64 gprev = (i64)ctr->gmax_ts;
@@ -160,6 +166,7 @@ k_prepass_scan(BatchView bv, FoldParams p, const i64* range_min, const i64* rang
     if (range_max[r] > running) running = range_max[r];
   }
   if (bad) atomicExch(&any_bad, 1);
+  if (lo < hi) atomicMin(&span_min, (unsigned long long)mn ^ 0x8000000000000000ULL);
   __syncthreads();
   if (threadIdx.x == 0) {
     i64 tot = strip_max[blockDim.x - 1];
@@ -168,5 +175,10 @@ k_prepass_scan(BatchView bv, FoldParams p, const i64* range_min, const i64* rang
     u32 clean = any_bad ? 0u : 1u;
     ctr->batch_clean = clean;
     *verdict_out = clean;
+    // time span of this activation alone (the combining fold keeps timestamps relative to its minimum)
+    i64 amax = INT64_MIN;
+    amax = strip_max[blockDim.x - 1];
+    span_out[0] = (i64)(span_min ^ 0x8000000000000000ULL);
+    span_out[1] = amax;
   }
 }

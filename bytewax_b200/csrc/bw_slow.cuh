@@ -96,7 +96,7 @@ k_slow_fold(BatchView bv, Table t, FoldParams p, EmitBufs e, const unsigned char
       bw_load_event(bv, seg, off, p, key, ts, operand, raw);
       const u64 seq = ((u64)batch_no << 32) | g;
       if (!late[g]) {
-        bw_fold_event<FoldCfgRuntime>(t, p, &sinks, key, ts, operand, seq, batch_no);
+        bw_fold_event<FoldCfgRuntime, NoSeg>(t, p, &sinks, key, ts, operand, seq, batch_no, BW_NO_SLOT, NoSeg());
       } else {
         // late_for(ts) == intersects(ts): floor((d-length)/offset)+1 .. floor(d/offset)
         i64 d = ts - p.align_us;

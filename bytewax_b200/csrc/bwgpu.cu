@@ -26,6 +26,7 @@
 #include "bw_close.cuh"
 #include "bw_common.cuh"
 #include "bw_exchange.cuh"
+#include "bw_bucket.cuh"
 #include "bw_fold.cuh"
 #include "bw_keyed.cuh"
 #include "bw_prepass.cuh"
@@ -82,7 +83,7 @@ struct Stage {  // device staging for host-ingested batches
 // optional per-phase timing (env BW_TIMING=1): events on the streams, summed at destroy
 struct PhaseTimer {
   static const int NPH = 8;
-  const char* names[NPH] = {"part_hist+scan+scatter", "barrier", "prepass", "fold", "close", "", "", ""};
+  const char* names[NPH] = {"part_hist+scan+scatter", "barrier", "prepass", "fold", "close", "bucket (hist+scan+scatter)", "fold_seg", ""};
   std::vector<cudaEvent_t> ev[NPH][2];
   bool on = false;
   void mark(int ph, int which, cudaStream_t s) {
@@ -97,12 +98,20 @@ struct PhaseTimer {
     for (int p = 0; p < NPH; ++p) {
       size_t n = std::min(ev[p][0].size(), ev[p][1].size());
       if (!n) continue;
-      double tot = 0;
+      double tot = 0, mn = 1e30, mx = 0;
+      std::vector<float> all;
       for (size_t i = 0; i < n; ++i) {
         float ms = 0;
-        if (cudaEventElapsedTime(&ms, ev[p][0][i], ev[p][1][i]) == cudaSuccess) tot += ms;
+        if (cudaEventElapsedTime(&ms, ev[p][0][i], ev[p][1][i]) == cudaSuccess) {
+          tot += ms;
+          mn = std::min<double>(mn, ms);
+          mx = std::max<double>(mx, ms);
+          all.push_back(ms);
+        }
       }
-      fprintf(stderr, "[bwgpu rank %d] %-24s n=%zu avg %.3f ms\n", rank, names[p], n, tot / n);
+      std::sort(all.begin(), all.end());
+      fprintf(stderr, "[bwgpu rank %d] %-24s n=%zu avg %.3f ms (min %.3f, median %.3f, max %.3f)\n", rank, names[p], n, tot / n, mn,
+              all.empty() ? 0.0 : all[all.size() / 2], mx);
     }
   }
 };
@@ -160,7 +169,17 @@ struct bw_fold {
   bool have_epoch = false, have_pending = false;
   bool eof_done = false;
   int fold_grid = 0, close_grid = 0;
-  void (*fold_kernel)(BatchView, Table, FoldParams, u32, u64) = nullptr;
+  void (*fold_kernel)(BatchView, Table, FoldParams, u32, u32, u32) = nullptr;
+  // combining fold (bw_bucket.cuh): bucket by table segment, fold through shared memory
+  BktBufs bk{};
+  bool seg_ok = false;     // buffers allocated, fold type supported
+  int seg_mode = 0;        // env BW_SEG=1: use it for every clean activation of >= seg_min_rows (off by default: on C1 the
+                           // bucketing pass costs more than the combining saves, profiles/r01_notes.md)
+  u64 seg_min_rows = 1ULL << 20;
+  int seg_rpt = 16, seg_grid = 0;
+  void (*seg_kernel)(BktBufs, Table, FoldParams, u32, i64) = nullptr;
+  i64* d_span = nullptr;   // [min ts, max ts] of the activation (prepass)
+  bool sub_auto = true;     // env BW_SUB_AUTO=0: never split an activation by its event-time span
   u64 sub_rows = ~0ULL;  // optional fold + close granularity inside one activation (env BW_SUB_ROWS); measured slower on C1
   // multi-GPU exchange
   void* xchg_base = nullptr;  // one allocation, IPC-shared
@@ -353,7 +372,7 @@ static cudaError_t dmalloc(T** p, size_t n) {
 }
 
 // k_fold instantiations: accumulator op x watermark tracking (+ MEAN keeps counts)
-typedef void (*fold_kernel_t)(BatchView, Table, FoldParams, u32, u64);
+typedef void (*fold_kernel_t)(BatchView, Table, FoldParams, u32, u32, u32);
 template <int OP, int CNT>
 static fold_kernel_t pick_wm(bool wm) {
   return wm ? (fold_kernel_t)k_fold<FoldCfg<OP, 1, CNT>> : (fold_kernel_t)k_fold<FoldCfg<OP, 0, CNT>>;
@@ -369,6 +388,20 @@ static fold_kernel_t pick_fold_kernel(const FoldParams& p) {
     case BW_OP_MIN_U64: return pick_wm<BW_OP_MIN_U64, 0>(wm);
     case BW_OP_MAX_S64: return pick_wm<BW_OP_MAX_S64, 0>(wm);
     default: return pick_wm<BW_OP_MAX_U64, 0>(wm);
+  }
+}
+
+typedef void (*seg_kernel_t)(BktBufs, Table, FoldParams, u32, i64);
+static seg_kernel_t pick_seg_kernel(const FoldParams& p) {
+  if (!p.track_wm || p.need_count) return nullptr;
+  switch (p.op) {
+    case BW_OP_ADD_ONE: return (seg_kernel_t)k_fold_seg<FoldCfg<BW_OP_ADD_ONE, 1, 0>>;
+    case BW_OP_ADD_U64: return (seg_kernel_t)k_fold_seg<FoldCfg<BW_OP_ADD_U64, 1, 0>>;
+    case BW_OP_ADD_F64: return (seg_kernel_t)k_fold_seg<FoldCfg<BW_OP_ADD_F64, 1, 0>>;
+    case BW_OP_MIN_S64: return (seg_kernel_t)k_fold_seg<FoldCfg<BW_OP_MIN_S64, 1, 0>>;
+    case BW_OP_MIN_U64: return (seg_kernel_t)k_fold_seg<FoldCfg<BW_OP_MIN_U64, 1, 0>>;
+    case BW_OP_MAX_S64: return (seg_kernel_t)k_fold_seg<FoldCfg<BW_OP_MAX_S64, 1, 0>>;
+    default: return (seg_kernel_t)k_fold_seg<FoldCfg<BW_OP_MAX_U64, 1, 0>>;
   }
 }
 
@@ -427,6 +460,7 @@ static bw_status fold_alloc(bw_fold* f) {
   CU(ctx, dmalloc(&f->d_rmax, nranges));
   CU(ctx, dmalloc(&f->d_rbad, nranges));
   CU(ctx, dmalloc(&f->d_verdict, 1));
+  CU(ctx, dmalloc(&f->d_span, 2));
   CU(ctx, cudaHostAlloc((void**)&f->h_verdict, 64, cudaHostAllocDefault));
   CU(ctx, cudaStreamCreateWithFlags(&f->s_compute, cudaStreamNonBlocking));
   CU(ctx, cudaStreamCreateWithFlags(&f->s_copy, cudaStreamNonBlocking));
@@ -445,6 +479,7 @@ static bw_status fold_alloc(bw_fold* f) {
   int occ = 0;
   f->fold_kernel = pick_fold_kernel(f->p);
   f->pt.on = getenv("BW_TIMING") != nullptr;
+  if (const char* e = getenv("BW_SUB_AUTO")) f->sub_auto = atoi(e) != 0;
   if (const char* e = getenv("BW_SUB_ROWS")) {
     long long v = atoll(e);
     if (v >= 1024) f->sub_rows = (u64)v;
@@ -456,6 +491,39 @@ static bw_status fold_alloc(bw_fold* f) {
   // (NVLink-bound, on its own stream) can really run beside the fold instead of queueing behind it
   if (ctx->world > 1 && occ > 2 && !getenv("BW_FOLD_FULL")) f->fold_grid = ctx->sm_count * 2;
   f->close_grid = ctx->sm_count * 8;
+  // combining fold: needs the watermark prepass (time span of the activation), a plain accumulator,
+  // at most BW_BKT_MAX table segments and arrival indices that fit 31 bits
+  if (const char* e = getenv("BW_SEG")) f->seg_mode = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("BW_SEG_MIN_ROWS")) f->seg_min_rows = (u64)atoll(e);
+  {
+    const u64 nb = (cap + BW_BKT_SLOTS - 1) >> BW_BKT_SHIFT;
+    f->seg_kernel = pick_seg_kernel(f->p);
+    if (f->seg_mode != 0 && f->seg_kernel && nb <= BW_BKT_MAX && f->max_recv_rows < (1ULL << 31) &&
+        f->max_recv_rows >= f->seg_min_rows) {
+      const u64 rows = f->max_recv_rows;
+      f->seg_rpt = f->has_ts ? 8 : 16;
+      const u64 T = (u64)BW_BKT_THREADS * f->seg_rpt;
+      f->bk.nb = (u32)nb;
+      f->bk.tiles_cap = (u32)((rows + T - 1) / T + 1);
+      f->bk.val_bytes = f->has_vals ? f->val_bytes : 0;
+      CU(ctx, dmalloc(&f->bk.keys, rows));
+      if (f->has_vals) CU(ctx, cudaMalloc(&f->bk.vals, rows * (size_t)f->val_bytes));
+      if (f->has_ts) CU(ctx, dmalloc(&f->bk.ts, rows));
+      CU(ctx, dmalloc(&f->bk.g, rows));
+      CU(ctx, dmalloc(&f->bk.tile_counts, (size_t)nb * f->bk.tiles_cap));
+      CU(ctx, dmalloc(&f->bk.cnt, nb));
+      CU(ctx, dmalloc(&f->bk.off, nb + 1));
+      CU(ctx, cudaFuncSetAttribute((const void*)f->seg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BW_SEG_SMEM));
+      const int sm = (int)bw_bkt_scatter_smem(f->seg_rpt, f->bk.val_bytes, f->has_ts);
+      if (f->seg_rpt == 16) CU(ctx, cudaFuncSetAttribute((const void*)k_bkt_scatter<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+      else CU(ctx, cudaFuncSetAttribute((const void*)k_bkt_scatter<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+      int socc = 0;
+      CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&socc, (const void*)f->seg_kernel, BW_SEG_THREADS, BW_SEG_SMEM));
+      if (socc < 1) socc = 1;
+      f->seg_grid = ctx->sm_count * socc;
+      f->seg_ok = true;
+    }
+  }
   k_init_table<<<ctx->sm_count * 8, 256, 0, f->s_compute>>>(f->t, f->p.acc_identity);
   CU(ctx, cudaGetLastError());
   f->st.kernel_launches++;
@@ -634,7 +702,8 @@ void bw_fold_destroy(bw_fold* f) {
                  f->e.l_ts, f->e.l_seq, f->e.l_epoch, f->d_rmin, f->d_rmax, f->d_rbad, f->d_verdict, f->d_kflat,
                  f->d_ksorted, f->d_tsflat, f->d_tssorted, f->d_prefmax, f->d_idx, f->d_idxsorted, f->d_late, f->d_cub,
                  f->d_sk, f->d_sk2, f->d_gather, f->d_perm, f->d_perm2, f->xchg_base, f->d_tile_counts,
-                 f->d_send_counts, f->d_all_counts, f->send_keys, f->send_vals, f->send_ts};
+                 f->d_send_counts, f->d_all_counts, f->send_keys, f->send_vals, f->send_ts, f->d_span,
+                 f->bk.keys, f->bk.vals, f->bk.ts, f->bk.g, f->bk.tile_counts, f->bk.cnt, f->bk.off};
   for (void* p : dev)
     if (p) cudaFree(p);
   for (auto& s : f->stages) {
@@ -852,11 +921,12 @@ static bw_status run_batch(bw_fold* f, const u64* d_keys, const void* d_vals, co
     if (grid < 1) grid = 1;
     f->pt.mark(2, 0, pre_stream);
     k_prepass_ranges<<<grid, BW_PRE_THREADS, 0, pre_stream>>>(bv, f->p, f->d_rmin, f->d_rmax, f->d_rbad);
-    k_prepass_scan<<<1, 1024, 0, pre_stream>>>(bv, f->p, f->d_rmin, f->d_rmax, f->d_rbad, f->d_ctr, f->d_verdict);
+    k_prepass_scan<<<1, 1024, 0, pre_stream>>>(bv, f->p, f->d_rmin, f->d_rmax, f->d_rbad, f->d_ctr, f->d_verdict, f->d_span);
     CU(ctx, cudaGetLastError());
     f->st.kernel_launches += 2;
     f->pt.mark(2, 1, pre_stream);
     CU(ctx, cudaMemcpyAsync(f->h_verdict, f->d_verdict, sizeof(u32), cudaMemcpyDeviceToHost, pre_stream));
+    CU(ctx, cudaMemcpyAsync(f->h_verdict + 4, f->d_span, 2 * sizeof(i64), cudaMemcpyDeviceToHost, pre_stream));
     CU(ctx, cudaEventRecord(f->ev_pre, pre_stream));
     CU(ctx, cudaEventSynchronize(f->ev_pre));
     clean = (*f->h_verdict != 0);
@@ -867,31 +937,79 @@ static bw_status run_batch(bw_fold* f, const u64* d_keys, const void* d_vals, co
     CU(ctx, cudaStreamWaitEvent(f->s_compute, f->ev_xchg_done, 0));
   }
   if (max_total > 0) {
-    if (clean) {
-      const u64 tile = (u64)BW_FOLD_THREADS * BW_FOLD_UNROLL;
-      // Fold + close in sub-ranges of the activation (single GPU, host-known counts).
-      // Windows a key has left are closed -- and its new pane promoted into the hot slot --
-      // between sub-ranges, so events after a window boundary mostly take the one-sector
-      // path.  Rows are identical: a pane closed early would also close at the end (the
-      // watermark only grows, and the pane holding max_ts never closes).
-      const u64 step = (ctx->world == 1 && max_total > f->sub_rows) ? f->sub_rows : max_total;
-      for (u64 lo = 0; lo < max_total; lo += step) {
-        const u64 n = std::min<u64>(step, max_total - lo);
-        BatchView sub = bv;
-        if (step != max_total) {
-          sub.keys[0] = bv.keys[0] + lo;
-          if (bv.vals[0]) sub.vals[0] = (const char*)bv.vals[0] + lo * (u64)f->val_bytes;
-          if (bv.ts[0]) sub.ts[0] = bv.ts[0] + lo;
-          sub.h_counts[0] = n;
-          sub.max_rows = n;
-        }
+    bool seg = false;
+    if (clean && f->seg_ok && f->p.track_wm) {
+      const i64 tmin = ((const i64*)(f->h_verdict + 4))[0], tmax = ((const i64*)(f->h_verdict + 4))[1];
+      const u64 known = (ctx->world == 1) ? rows : max_total;
+      seg = f->seg_mode == 1 && known >= f->seg_min_rows && tmax >= tmin && (u64)(tmax - tmin) < 0xFFFFFFF0ULL;
+      if (seg) {
         EventPair* ep = next_timer(f);
         if (ep) {
-          ep->rows = (ctx->world > 1) ? 0 : n;
+          ep->rows = (ctx->world > 1) ? 0 : rows;
           CU(ctx, cudaEventRecord(ep->a, f->s_compute));
         }
-        int grid = (int)std::min<u64>((n + tile - 1) / tile, (u64)f->fold_grid);
-        f->fold_kernel<<<grid, BW_FOLD_THREADS, 0, f->s_compute>>>(sub, f->t, f->p, batch_no, lo);
+        const u64 T = (u64)BW_BKT_THREADS * f->seg_rpt;
+        BktBufs bk = f->bk;
+        if (!bv.vals[0]) bk.val_bytes = 0;  // counts may come without a value column
+        const int grid = (int)std::min<u64>((max_total + T - 1) / T, (u64)ctx->sm_count * 4);
+        const size_t sm = bw_bkt_scatter_smem(f->seg_rpt, bk.val_bytes, f->has_ts);
+        f->pt.mark(5, 0, f->s_compute);
+        if (f->seg_rpt == 16) k_bkt_hist<16><<<grid, BW_BKT_THREADS, 0, f->s_compute>>>(bv, f->t.cap, bk);
+        else k_bkt_hist<8><<<grid, BW_BKT_THREADS, 0, f->s_compute>>>(bv, f->t.cap, bk);
+        k_bkt_scan<<<bk.nb, 1024, 0, f->s_compute>>>(bv, bk, (u32)T);
+        k_bkt_base<<<1, 1024, 0, f->s_compute>>>(bk);
+        if (f->seg_rpt == 16) k_bkt_scatter<16><<<grid, BW_BKT_THREADS, sm, f->s_compute>>>(bv, f->t.cap, bk);
+        else k_bkt_scatter<8><<<grid, BW_BKT_THREADS, sm, f->s_compute>>>(bv, f->t.cap, bk);
+        f->pt.mark(5, 1, f->s_compute);
+        f->pt.mark(6, 0, f->s_compute);
+        const int sgrid = (int)std::min<u32>(bk.nb, (u32)f->seg_grid);
+        f->seg_kernel<<<sgrid, BW_SEG_THREADS, BW_SEG_SMEM, f->s_compute>>>(bk, f->t, f->p, batch_no, tmin);
+        f->pt.mark(6, 1, f->s_compute);
+        CU(ctx, cudaGetLastError());
+        if (ep) CU(ctx, cudaEventRecord(ep->b, f->s_compute));
+        f->st.kernel_launches += 5;
+        f->st.fold_launches++;
+        f->st.combined_folds++;
+        if (f->pt.on && ep) {
+          f->pt.ev[3][0].push_back(ep->a);
+          f->pt.ev[3][1].push_back(ep->b);
+        }
+      }
+    }
+    if (seg) {
+      // folded above
+    } else if (clean) {
+      const u64 tile = (u64)BW_FOLD_THREADS * BW_FOLD_UNROLL;
+      // Fold + close in sub-ranges of the activation (by arrival index, resolved on the device so
+      // that it also works on exchanged rows whose counts the host never sees).  Windows a key has
+      // left are closed -- and its newest pane promoted into the hot slot -- between sub-ranges, so
+      // an activation that spans several windows (8 ranks x 2^24 rows of C1 = 134 s of event time
+      // per activation) keeps hitting the two direct panes instead of the overflow list.  Rows are
+      // identical: a pane closed early would also close at the end (the watermark only grows, and
+      // the pane holding max_ts never closes).  One sub-range per pane of event-time span, for
+      // in-order streams; activations inside one pane (C1 on one GPU) are not split.
+      const u64 known = (ctx->world == 1) ? rows : max_total;
+      u32 n_sub = 1;
+      if (f->sub_rows != ~0ULL) {
+        n_sub = (u32)std::min<u64>((known + f->sub_rows - 1) / f->sub_rows, 64);
+      } else if (f->sub_auto && f->p.track_wm) {
+        const i64 tmin = ((const i64*)(f->h_verdict + 4))[0], tmax = ((const i64*)(f->h_verdict + 4))[1];
+        if (tmax > tmin) {
+          const u64 panes = (u64)(tmax - tmin) / (u64)f->p.pane_us + (((u64)(tmax - tmin) % (u64)f->p.pane_us) ? 1 : 0);
+          n_sub = (u32)std::min<u64>(panes, 8);
+          n_sub = (u32)std::min<u64>(n_sub, std::max<u64>(known >> 20, 1));  // keep sub-ranges >= 2^20 rows
+        }
+      }
+      if (n_sub < 1) n_sub = 1;
+      for (u32 i = 0; i < n_sub; ++i) {
+        const u64 n_hi = (known * (i + 1ULL)) / n_sub, n_lo = (known * (u64)i) / n_sub;
+        EventPair* ep = next_timer(f);
+        if (ep) {
+          ep->rows = (ctx->world > 1) ? 0 : (n_hi - n_lo);
+          CU(ctx, cudaEventRecord(ep->a, f->s_compute));
+        }
+        int grid = (int)std::min<u64>((n_hi - n_lo + tile - 1) / tile + 1, (u64)f->fold_grid);
+        f->fold_kernel<<<grid, BW_FOLD_THREADS, 0, f->s_compute>>>(bv, f->t, f->p, batch_no, i, n_sub);
         CU(ctx, cudaGetLastError());
         if (ep) CU(ctx, cudaEventRecord(ep->b, f->s_compute));
         f->st.kernel_launches++;
@@ -900,7 +1018,7 @@ static bw_status run_batch(bw_fold* f, const u64* d_keys, const void* d_vals, co
           f->pt.ev[3][0].push_back(ep->a);
           f->pt.ev[3][1].push_back(ep->b);
         }
-        if (lo + n < max_total) {
+        if (i + 1 < n_sub) {
           k_close_dirty<<<f->close_grid, 256, 0, f->s_compute>>>(f->t, f->p, f->e, ord);
           k_reset_dirty<<<1, 1, 0, f->s_compute>>>(f->t);
           f->st.kernel_launches += 2;
@@ -1261,6 +1379,7 @@ bw_status bw_fold_reset_timers(bw_fold* f) {
   f->st.last_fold_ms = 0;
   f->st.fold_rows = 0;
   f->st.fold_launches = 0;
+  f->st.combined_folds = 0;
   return BW_OK;
 }
 bw_status bw_fold_sync(bw_fold* f) {

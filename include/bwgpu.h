@@ -172,6 +172,7 @@ typedef struct bw_stats {
   float sum_fold_ms;        /* sum over fold kernels since bw_fold_create / reset */
   uint64_t fold_launches;
   uint64_t fold_rows;
+  uint64_t combined_folds;  /* fold launches that took the bucket + shared-memory combining path */
 } bw_stats;
 
 /* ---- context ---------------------------------------------------------- */

@@ -23,6 +23,24 @@ def ctx():
     c.close()
 
 
+@pytest.fixture(scope="module", params=["direct", "combine"], autouse=True)
+def fold_mode(request):
+    """Every parity test runs twice: with the direct fold kernel and with the bucket + shared-memory combining
+    fold forced on for every clean activation (BW_SEG is read when a fold is created)."""
+    old = {k: os.environ.get(k) for k in ("BW_SEG", "BW_SEG_MIN_ROWS")}
+    if request.param == "combine":
+        os.environ["BW_SEG"] = "1"
+        os.environ["BW_SEG_MIN_ROWS"] = "0"
+    else:
+        os.environ["BW_SEG"] = "0"
+    yield request.param
+    for k, v in old.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
+
+
 def _is_float(case):
     return any(isinstance(v, float) for b in case["batches"] for v in b[2])
 
@@ -113,7 +131,7 @@ def _random_batches(seed, nb, n, n_keys, span_us, jitter_us, start):
     ("count", 10, 3, 2, 2, True),          # ordered, indivisible offset
     ("sum", 10, None, None, 30, False),    # wait forever: everything closes at EOF
 ])
-def test_against_c_oracle_medium(ctx, red, length, offset, wait, jitter, ordered):
+def test_against_c_oracle_medium(ctx, fold_mode, red, length, offset, wait, jitter, ordered):
     S = 1_000_000
     spec = dict(reduction=red, length_us=length * S, offset_us=offset * S if offset else None,
                 align_us=1_640_995_200_000_000, wait_us=None if wait is None else wait * S, ordered=ordered)
@@ -138,6 +156,50 @@ def test_against_c_oracle_medium(ctx, red, length, offset, wait, jitter, ordered
     st = fold.stats()
     if jitter > (wait if wait is not None else 10**9):
         assert st.slow_batches > 0
+    if fold_mode == "combine" and wait is not None:
+        assert st.combined_folds == st.fold_launches and st.fold_launches + st.slow_batches == len(batches)
+    if fold_mode == "direct":
+        assert st.combined_folds == 0
+    fold.close()
+    orc.close()
+
+
+@pytest.mark.parametrize("sub_rows", [None, "20000"])
+def test_activation_spanning_several_windows(ctx, fold_mode, sub_rows):
+    """In-order activations that each span 3.5 windows: the direct kernel folds them in sub-ranges with a
+    close in between (by event-time span, or forced every 20000 rows); rows must not change."""
+    S = 1_000_000
+    A = 1_640_995_200_000_000
+    n, nb, n_keys = 1 << 21, 3, 5000
+    old = os.environ.get("BW_SUB_ROWS")
+    if sub_rows:
+        os.environ["BW_SUB_ROWS"] = sub_rows
+    try:
+        fold = _make_fold(ctx, dict(reduction="count", length_us=10 * S, offset_us=None, align_us=A, wait_us=2 * S, ordered=False),
+                          False, capacity_hint=8192, max_batch_rows=n, max_emit_rows=1 << 20)
+    finally:
+        if old is None:
+            os.environ.pop("BW_SUB_ROWS", None)
+        else:
+            os.environ["BW_SUB_ROWS"] = old
+    orc = coracle.COracle("count", 10 * S, None, A, 2 * S, False)
+    rnd = np.random.default_rng(11)
+    for b in range(nb):
+        keys = rnd.integers(0, n_keys, n).astype(np.uint64)
+        ts = (A + b * 35 * S + (np.arange(n) * 35 * S) // n + rnd.integers(-S, S + 1, n)).astype(np.int64)
+        orc.on_batch(keys, ts, np.ones(n, np.int64))
+        fold.ingest(keys, None, ts)
+    orc.on_eof()
+    em, em_eof = fold.advance(), fold.eof()
+    ck, cw, ca, _, cact = orc.closed()
+    assert np.concatenate([em.closed_key, em_eof.closed_key]).tolist() == ck.tolist()
+    assert np.concatenate([em.closed_window_id, em_eof.closed_window_id]).tolist() == cw.tolist()
+    assert np.concatenate([em.closed_acc, em_eof.closed_acc]).astype(np.int64).tolist() == ca.tolist()
+    assert em.closed_epoch.tolist() == (cact[: len(em.closed_epoch)] + 1).tolist()
+    st = fold.stats()
+    assert st.slow_batches == 0
+    if fold_mode == "direct":
+        assert st.fold_launches > nb  # the activations were split
     fold.close()
     orc.close()
 
@@ -222,7 +284,7 @@ def test_errors_are_loud(ctx):
     fold.close()
 
 
-def test_c1_properties_and_sampled_parity(ctx):
+def test_c1_properties_and_sampled_parity(ctx, fold_mode):
     """Config C1 at 2^24 rows x 4 batches: exact multiset vs the C oracle at 2M rows,
     then size-independent checks on the rest (sum of counts == N, per-window totals)."""
     from bytewax_b200 import gpu
@@ -261,7 +323,8 @@ def test_c1_properties_and_sampled_parity(ctx):
     nfull = (nb * B) // L
     assert (per_window[:nfull] == L).all() and per_window.sum() == nb * B
     st = fold.stats()
-    assert st.slow_batches == 0 and st.fold_launches == nb
+    assert st.slow_batches == 0 and st.fold_launches >= nb
+    assert st.combined_folds == (nb if fold_mode == "combine" else 0)
     ctx.dev_free(dk)
     ctx.dev_free(dv)
     fold.close()
