@@ -325,26 +325,9 @@ k_fold_seg(BktBufs B, Table t, FoldParams p, u32 batch_no, i64 base_ts) {
       for (int u = 0; u < BW_SEG_UNROLL; ++u) {
         const u32 e = wbase + (u32)u * 32 + lane;
         if (e >= e1) continue;
-        i64 rem;
-        const i64 ts = tsv[u];
-        const i64 q = bw_pane_of_r(ts, p, rem);
         const bool known = (k0[u] == key[u]);
-        const bool usable = known && sg.owns(slot[u]) && tag0[u] != BW_EMPTY_WIDTAG && (q > -BW_WID_LIMIT) && (q < BW_WID_LIMIT);
-        const bool hit0 = usable && bw_widtag_q(tag0[u]) == q;
-        const bool hit1 = usable && !hit0 && bw_widtag_q1(tag0[u]) == q;
-        if (hit0 || hit1) {
-          u64 operand;
-          bw_operand(p, raw[u], operand);
-          const u32 ls = sg.local(slot[u]);
-          if (hit0) {
-            sg.fold0(op, ls, operand);
-            if (((u32)tag0[u] & 0x7Fu) == born) bw_red_min_u64(&t.aux[slot[u]].seq0, ((u64)batch_no << 32) | gi[u]);
-          } else {
-            sg.fold1(op, ls, operand);
-            if (!(tag0[u] & BW_TAG_P1_PREV)) sg.open1(ls, gi[u]);
-          }
-          sg.touch(ls, ts);
-        } else {
+        if (!(known && bw_try_fast<C, SegSink>(t, p, &sinks, sg, slot[u], tag0[u], mts[u], tsv[u], raw[u],
+                                               ((u64)batch_no << 32) | gi[u], born))) {
           const u32 i = atomicAdd(&sinks.n_defer[warp], 1u);
           sinks.dq[warp][i] = e | (known ? 0x80000000u : 0u);
         }
@@ -359,11 +342,16 @@ k_fold_seg(BktBufs B, Table t, FoldParams p, u32 batch_no, i64 base_ts) {
         if (B.val_bytes == 8) rw = bw_ld_stream_u64((const u64*)B.vals + e);
         else if (B.val_bytes == 4) rw = (u64)bw_ld_stream_u32((const u32*)B.vals + e);
         const i64 ts = p.ts_from_value ? p.align_us + (i64)rw : (i64)bw_ld_stream_u64((const u64*)B.ts + e);
+        const u64 seq = ((u64)batch_no << 32) | bw_ld_stream_u32(B.g + e);
+        u32 ks = (w >> 31) ? (u32)bw_home_slot(t, kk) : BW_NO_SLOT;
+        if (ks == BW_NO_SLOT) {
+          i64 m2, w2;
+          ks = bw_lookup_slot(t, kk, m2, w2);
+          if (ks != BW_NO_SLOT && bw_try_fast<C, SegSink>(t, p, &sinks, sg, ks, w2, m2, ts, rw, seq, born)) continue;
+        }
         u64 operand;
         bw_operand(p, rw, operand);
-        const u32 gg = bw_ld_stream_u32(B.g + e);
-        const u32 known_slot = (w >> 31) ? (u32)bw_home_slot(t, kk) : BW_NO_SLOT;
-        bw_fold_event<C, SegSink>(t, p, &sinks, kk, ts, operand, ((u64)batch_no << 32) | gg, batch_no, known_slot, sg);
+        bw_fold_event<C, SegSink>(t, p, &sinks, kk, ts, operand, seq, batch_no, ks, sg);
       }
       __syncwarp();
       if (lane == 0) sinks.n_defer[warp] = 0;

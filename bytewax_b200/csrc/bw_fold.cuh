@@ -377,6 +377,87 @@ __device__ __noinline__ void bw_fold_event(const Table& t, const FoldParams& p, 
   }
 }
 
+__device__ __forceinline__ void bw_operand(const FoldParams& p, u64 raw, u64& operand);
+
+// Read-only lookup of a key that is not in its home slot (about a third of the keys at load
+// 0.5): the same 4-wide probe as bw_find_slot without the claim logic.  Returns BW_NO_SLOT when
+// the probe reaches a free slot (new key) or the window is exhausted: those go to bw_fold_event.
+__device__ __forceinline__ u32 bw_lookup_slot(const Table& t, u64 key, i64& max_ts, i64& wt0) {
+  u64 s = bw_home_slot(t, key);
+  if (key == BW_EMPTY_KEY) return BW_NO_SLOT;
+#pragma unroll 1
+  for (int round = 0; round < 4; ++round) {
+    u64 k[BW_PROBE_WIDTH], a[BW_PROBE_WIDTH];
+    i64 m[BW_PROBE_WIDTH], w[BW_PROBE_WIDTH];
+#pragma unroll
+    for (int j = 0; j < BW_PROBE_WIDTH; ++j) {
+      u64 sj = s + j;
+      if (sj >= t.cap) sj -= t.cap;
+      bw_ld_slot(t.hot + sj, k[j], m[j], w[j], a[j]);
+    }
+    int jm = BW_PROBE_WIDTH;
+    u64 kk = 0;
+    i64 mm = 0, ww = 0;
+#pragma unroll
+    for (int j = BW_PROBE_WIDTH - 1; j >= 0; --j) {
+      if (k[j] == key || k[j] == BW_EMPTY_KEY) {
+        jm = j;
+        kk = k[j];
+        mm = m[j];
+        ww = w[j];
+      }
+    }
+    if (jm < BW_PROBE_WIDTH) {
+      if (kk != key) return BW_NO_SLOT;
+      u64 sj = s + (u64)jm;
+      if (sj >= t.cap) sj -= t.cap;
+      max_ts = mm;
+      wt0 = ww;
+      return (u32)sj;
+    }
+    s += BW_PROBE_WIDTH;
+    if (s >= t.cap) s -= t.cap;
+  }
+  return BW_NO_SLOT;
+}
+
+// The common case, given the slot of a known key and the sector read from it: the event falls in
+// the key's pane 0 or pane 1.  Applies it (to the caller's shared-memory segment when it owns
+// the slot, else to the table) and returns true; returns false for every other case.
+template <class C, class SG>
+__device__ __forceinline__ bool bw_try_fast(const Table& t, const FoldParams& p, DirtySink* sk, const SG& sg, u32 slot,
+                                            i64 tag0, i64 mts, i64 ts, u64 raw, u64 seq, u32 born) {
+  i64 rem;
+  const i64 q = bw_pane_of_r(ts, p, rem);
+  const bool usable = tag0 != BW_EMPTY_WIDTAG && (q > -BW_WID_LIMIT) && (q < BW_WID_LIMIT);
+  const bool hit0 = usable && bw_widtag_q(tag0) == q;
+  const bool hit1 = usable && !hit0 && bw_widtag_q1(tag0) == q;
+  if (!(hit0 || hit1)) return false;
+  u64 operand;
+  bw_operand(p, raw, operand);
+  const bool own = sg.owns(slot);
+  const u32 ls = sg.local(slot);
+  if (hit0) {
+    if (own) sg.fold0(C::op(p), ls, operand);
+    else bw_apply(C::op(p), &t.hot[slot].acc0, operand);
+    if (C::cnt(p)) bw_red_add_u64(&t.aux[slot].cnt0, 1ULL);
+    if (((u32)tag0 & 0x7Fu) == born) bw_red_min_u64(&t.aux[slot].seq0, seq);
+  } else {
+    if (own) {
+      sg.fold1(C::op(p), ls, operand);
+      if (!(tag0 & BW_TAG_P1_PREV)) sg.open1(ls, (u32)seq);
+    } else {
+      P1Slot* ps = t.p1 + slot;
+      bw_apply(C::op(p), &ps->acc1, operand);
+      if (!(tag0 & BW_TAG_P1_PREV)) bw_red_min_u64(&ps->seq1, seq);
+    }
+    if (C::cnt(p)) bw_red_add_u64(&t.aux[slot].cnt1, 1ULL);
+  }
+  if (own) sg.touch(ls, ts);
+  else bw_after_fold<C>(t, p, sk, slot, ts, mts, tag0, false, q, rem);
+  return true;
+}
+
 // raw value bits -> accumulator operand
 __device__ __forceinline__ void bw_operand(const FoldParams& p, u64 raw, u64& operand) {
   if (p.val_dtype >= 2) {
@@ -515,36 +596,19 @@ k_fold(BatchView bv, Table t, FoldParams p, u32 batch_no, u32 sub_i, u32 sub_n) 
     for (int u = 0; u < BW_FOLD_UNROLL; ++u) {
       const u64 g = wbase + (u64)u * 32 + lane;
       if (g >= total) continue;
-      i64 rem;
       const i64 ts = bw_event_ts(bv, seg_start, p, g, raw[u]);
-      const i64 q = bw_pane_of_r(ts, p, rem);
       const bool known = (k0[u] == key[u]);
-      const bool usable = known && tag0[u] != BW_EMPTY_WIDTAG && (q > -BW_WID_LIMIT) && (q < BW_WID_LIMIT);
-      const bool hit0 = usable && bw_widtag_q(tag0[u]) == q;
-      const bool hit1 = usable && !hit0 && bw_widtag_q1(tag0[u]) == q;
-      if (hit0 || hit1) {
-        u64 operand;
-        bw_operand(p, raw[u], operand);
-        const u64 seq = ((u64)batch_no << 32) | g;
-        if (hit0) {
-          bw_apply(C::op(p), &t.hot[slot[u]].acc0, operand);
-          if (C::cnt(p)) bw_red_add_u64(&t.aux[slot[u]].cnt0, 1ULL);
-          if (((u32)tag0[u] & 0x7Fu) == born) bw_red_min_u64(&t.aux[slot[u]].seq0, seq);
-        } else {
-          P1Slot* ps = t.p1 + slot[u];
-          bw_apply(C::op(p), &ps->acc1, operand);
-          if (!(tag0[u] & BW_TAG_P1_PREV)) bw_red_min_u64(&ps->seq1, seq);
-          if (C::cnt(p)) bw_red_add_u64(&t.aux[slot[u]].cnt1, 1ULL);
-        }
-        bw_after_fold<C>(t, p, &sinks, slot[u], ts, mts[u], tag0[u], false, q, rem);
-      } else {
+      if (!(known && bw_try_fast<C, NoSeg>(t, p, &sinks, NoSeg(), slot[u], tag0[u], mts[u], ts, raw[u],
+                                           ((u64)batch_no << 32) | g, born))) {
         u32 i = atomicAdd(&sinks.n_defer[warp], 1u);
         sinks.dq_g[warp][i] = (u32)g;
         sinks.dq_slot[warp][i] = known ? slot[u] : BW_NO_SLOT;
       }
     }
     __syncwarp();
-    // phase C: the warp drains its own queue with dense lanes (no block barrier)
+    // phase C: the warp drains its own queue with dense lanes (no block barrier).  Most of the
+    // queue is known keys that simply do not sit in their home slot: a read-only probe plus the
+    // same fast apply; only new keys and third panes need the general path.
     const u32 nd = sinks.n_defer[warp];
     for (u32 i = lane; i < nd; i += 32) {
       const u64 g = sinks.dq_g[warp][i];
@@ -554,7 +618,14 @@ k_fold(BatchView bv, Table t, FoldParams p, u32 batch_no, u32 sub_i, u32 sub_n) 
       u64 kk, op, rw;
       i64 ts;
       bw_load_event(bv, seg, off, p, kk, ts, op, rw);
-      bw_fold_event<C, NoSeg>(t, p, &sinks, kk, ts, op, ((u64)batch_no << 32) | g, batch_no, sinks.dq_slot[warp][i], NoSeg());
+      const u64 seq = ((u64)batch_no << 32) | g;
+      u32 ks = sinks.dq_slot[warp][i];
+      if (ks == BW_NO_SLOT) {
+        i64 m2, w2;
+        ks = bw_lookup_slot(t, kk, m2, w2);
+        if (ks != BW_NO_SLOT && bw_try_fast<C, NoSeg>(t, p, &sinks, NoSeg(), ks, w2, m2, ts, rw, seq, born)) continue;
+      }
+      bw_fold_event<C, NoSeg>(t, p, &sinks, kk, ts, op, seq, batch_no, ks, NoSeg());
     }
     __syncwarp();
     if (lane == 0) sinks.n_defer[warp] = 0;

@@ -205,13 +205,14 @@ class WindowFold:
             return np.float64
         return np.int64 if self.val_dtype == "i64" else np.uint64
 
-    def _wrap(self, e: N.BwEmit) -> Emitted:
+    def _wrap(self, e: N.BwEmit, copy: bool = True) -> Emitted:
         nc, nl = int(e.n_closed), int(e.n_late)
 
         def arr(ptr, n, dt):
             if n == 0:
                 return np.zeros(0, dtype=dt)
-            return np.ctypeslib.as_array(ptr, shape=(n,)).view(dt).copy()
+            a = np.ctypeslib.as_array(ptr, shape=(n,)).view(dt)
+            return a.copy() if copy else a
 
         late_dt = np.float64 if self.val_dtype in ("f32", "f64") else (np.int64 if self.val_dtype == "i64" else np.uint64)
         return Emitted(
@@ -221,15 +222,17 @@ class WindowFold:
             arr(e.late_ts_us, nl, np.int64), arr(e.late_epoch, nl, np.uint64),
         )
 
-    def advance(self) -> Emitted:
+    def advance(self, copy: bool = True) -> Emitted:
+        """Rows emitted since the last call.  ``copy=False`` returns views of the library's pinned
+        output buffers (the C ABI's own contract: valid until the next ``advance``/``eof``)."""
         e = N.BwEmit()
         N.check(self.lib.bw_advance(self.h, 0, 0, C.byref(e)), self.ctx.h)
-        return self._wrap(e)
+        return self._wrap(e, copy)
 
-    def eof(self) -> Emitted:
+    def eof(self, copy: bool = True) -> Emitted:
         e = N.BwEmit()
         N.check(self.lib.bw_eof(self.h, C.byref(e)), self.ctx.h)
-        return self._wrap(e)
+        return self._wrap(e, copy)
 
     def window_bounds(self, window_id: int) -> Tuple[int, int]:
         o, c = C.c_int64(), C.c_int64()

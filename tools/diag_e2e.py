@@ -23,5 +23,5 @@ for s in range(K):
     print(f"commit {s}: {1e3*(time.perf_counter()-t):.2f} ms")
 fold.sync()
 print(f"total {1e3*(time.perf_counter()-t0):.1f} ms for {K} steps -> {K*B/(time.perf_counter()-t0)/1e9:.2f} G ev/s")
-t = time.perf_counter(); em = fold.advance(); print(f"advance {1e3*(time.perf_counter()-t):.1f} ms rows {len(em.closed_key)}")
-t = time.perf_counter(); em = fold.eof(); print(f"eof {1e3*(time.perf_counter()-t):.1f} ms rows {len(em.closed_key)}")
+t = time.perf_counter(); em = fold.advance(copy=False); print(f"advance {1e3*(time.perf_counter()-t):.1f} ms rows {len(em.closed_key)}")
+t = time.perf_counter(); em = fold.eof(copy=False); print(f"eof {1e3*(time.perf_counter()-t):.1f} ms rows {len(em.closed_key)}")
