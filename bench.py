@@ -374,6 +374,9 @@ def run_reference(args):
 
 
 def main():
+    # stdout carries exactly one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION in some images) goes to stdout too
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=60)

@@ -283,6 +283,9 @@ k_fold_seg(BktBufs B, Table t, FoldParams p, u32 batch_no, i64 base_ts) {
   const u32 born = batch_no & 63u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr u32 TILE = BW_SEG_THREADS * BW_SEG_UNROLL;
+  PaneCache pcache;
+  pcache.lo = INT64_MAX;
+  pcache.q = 0;
   for (u32 b = blockIdx.x; b < B.nb; b += gridDim.x) {
     sg.slot_base = (u64)b << BW_BKT_SHIFT;
     for (u32 i = threadIdx.x; i < BW_BKT_SLOTS; i += BW_SEG_THREADS) {
@@ -327,7 +330,7 @@ k_fold_seg(BktBufs B, Table t, FoldParams p, u32 batch_no, i64 base_ts) {
         if (e >= e1) continue;
         const bool known = (k0[u] == key[u]);
         if (!(known && bw_try_fast<C, SegSink>(t, p, &sinks, sg, slot[u], tag0[u], mts[u], tsv[u], raw[u],
-                                               ((u64)batch_no << 32) | gi[u], born))) {
+                                               ((u64)batch_no << 32) | gi[u], born, pcache))) {
           const u32 i = atomicAdd(&sinks.n_defer[warp], 1u);
           sinks.dq[warp][i] = e | (known ? 0x80000000u : 0u);
         }
@@ -347,7 +350,7 @@ k_fold_seg(BktBufs B, Table t, FoldParams p, u32 batch_no, i64 base_ts) {
         if (ks == BW_NO_SLOT) {
           i64 m2, w2;
           ks = bw_lookup_slot(t, kk, m2, w2);
-          if (ks != BW_NO_SLOT && bw_try_fast<C, SegSink>(t, p, &sinks, sg, ks, w2, m2, ts, rw, seq, born)) continue;
+          if (ks != BW_NO_SLOT && bw_try_fast<C, SegSink>(t, p, &sinks, sg, ks, w2, m2, ts, rw, seq, born, pcache)) continue;
         }
         u64 operand;
         bw_operand(p, rw, operand);

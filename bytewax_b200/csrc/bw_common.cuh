@@ -169,10 +169,19 @@ struct Counters {
 // GPUs).  One odd multiply moves the low bits up.
 __host__ __device__ __forceinline__ u64 bw_slot_of_hash(u64 h, u64 cap) {
   h *= 0x9E3779B97F4A7C15ULL;
+  if (cap >> 32) {  // never for the fold tables (capacity <= 2^31); kept exact for any caller
 #ifdef __CUDA_ARCH__
-  return __umul64hi(h, cap);
+    return __umul64hi(h, cap);
 #else
-  return (u64)(((unsigned __int128)h * cap) >> 64);
+    return (u64)(((unsigned __int128)h * cap) >> 64);
+#endif
+  }
+  // 32 x 32 -> high 32: one IMAD.HI instead of the ~10-instruction 64-bit multiply-high
+  // (profiles/r01_fold_ncu_final.md: the hash and the pane division were ~20 % of k_fold's instructions)
+#ifdef __CUDA_ARCH__
+  return (u64)__umulhi((u32)(h >> 32), (u32)cap);
+#else
+  return ((h >> 32) * (u64)(u32)cap) >> 32;
 #endif
 }
 __device__ __forceinline__ void bw_raise(Counters* c, u32 status) { atomicCAS(&c->err, 0u, status); }
@@ -273,6 +282,24 @@ __device__ __forceinline__ i64 bw_pane_of_r(i64 ts, const FoldParams& p, i64& re
   }
   rem = (i64)(n - qq * (u64)p.pane_us);
   return (i64)qq - p.div_bias_q;
+}
+// Pane of an event through a per-thread one-entry cache: streams are mostly in order, so the next
+// event of a thread nearly always falls in the pane of its previous one (two compares instead of
+// a 64-bit multiply-high).
+struct PaneCache {
+  i64 lo;  // start time of pane q; INT64_MAX == empty
+  i64 q;
+};
+__device__ __forceinline__ i64 bw_pane_cached(i64 ts, const FoldParams& p, i64& rem, PaneCache& c) {
+  const u64 d = (u64)(ts - c.lo);
+  if (d < (u64)p.pane_us) {
+    rem = (i64)d;
+    return c.q;
+  }
+  const i64 q = bw_pane_of_r(ts, p, rem);
+  c.lo = ts - rem;
+  c.q = q;
+  return q;
 }
 __device__ __forceinline__ i64 bw_pane_of(i64 ts, const FoldParams& p) {
   i64 r;

@@ -426,9 +426,9 @@ __device__ __forceinline__ u32 bw_lookup_slot(const Table& t, u64 key, i64& max_
 // the slot, else to the table) and returns true; returns false for every other case.
 template <class C, class SG>
 __device__ __forceinline__ bool bw_try_fast(const Table& t, const FoldParams& p, DirtySink* sk, const SG& sg, u32 slot,
-                                            i64 tag0, i64 mts, i64 ts, u64 raw, u64 seq, u32 born) {
+                                            i64 tag0, i64 mts, i64 ts, u64 raw, u64 seq, u32 born, PaneCache& pc) {
   i64 rem;
-  const i64 q = bw_pane_of_r(ts, p, rem);
+  const i64 q = bw_pane_cached(ts, p, rem, pc);
   const bool usable = tag0 != BW_EMPTY_WIDTAG && (q > -BW_WID_LIMIT) && (q < BW_WID_LIMIT);
   const bool hit0 = usable && bw_widtag_q(tag0) == q;
   const bool hit1 = usable && !hit0 && bw_widtag_q1(tag0) == q;
@@ -550,6 +550,9 @@ k_fold(BatchView bv, Table t, FoldParams p, u32 batch_no, u32 sub_i, u32 sub_n) 
   const u32 born = batch_no & 63u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   u32 iter = 0;
+  PaneCache pcache;
+  pcache.lo = INT64_MAX;
+  pcache.q = 0;
   for (u64 base = range_lo + (u64)blockIdx.x * tile; base < total; base += (u64)gridDim.x * tile) {
     // a warp owns BW_FOLD_UNROLL runs of 32 consecutive events
     const u64 wbase = base + (u64)warp * (32 * BW_FOLD_UNROLL);
@@ -599,7 +602,7 @@ k_fold(BatchView bv, Table t, FoldParams p, u32 batch_no, u32 sub_i, u32 sub_n) 
       const i64 ts = bw_event_ts(bv, seg_start, p, g, raw[u]);
       const bool known = (k0[u] == key[u]);
       if (!(known && bw_try_fast<C, NoSeg>(t, p, &sinks, NoSeg(), slot[u], tag0[u], mts[u], ts, raw[u],
-                                           ((u64)batch_no << 32) | g, born))) {
+                                           ((u64)batch_no << 32) | g, born, pcache))) {
         u32 i = atomicAdd(&sinks.n_defer[warp], 1u);
         sinks.dq_g[warp][i] = (u32)g;
         sinks.dq_slot[warp][i] = known ? slot[u] : BW_NO_SLOT;
@@ -623,7 +626,7 @@ k_fold(BatchView bv, Table t, FoldParams p, u32 batch_no, u32 sub_i, u32 sub_n) 
       if (ks == BW_NO_SLOT) {
         i64 m2, w2;
         ks = bw_lookup_slot(t, kk, m2, w2);
-        if (ks != BW_NO_SLOT && bw_try_fast<C, NoSeg>(t, p, &sinks, NoSeg(), ks, w2, m2, ts, rw, seq, born)) continue;
+        if (ks != BW_NO_SLOT && bw_try_fast<C, NoSeg>(t, p, &sinks, NoSeg(), ks, w2, m2, ts, rw, seq, born, pcache)) continue;
       }
       bw_fold_event<C, NoSeg>(t, p, &sinks, kk, ts, op, seq, batch_no, ks, NoSeg());
     }
