@@ -26,7 +26,7 @@ STATUS_NAMES = {
 BW_WAIT_FOREVER = (1 << 63) - 1
 RED = {"count": 0, "sum": 1, "min": 2, "max": 3, "mean": 4}
 VAL = {"u64": 0, "i64": 1, "f32": 2, "f64": 3}
-TS_COLUMN, TS_FROM_VALUE = 0, 1
+TS_COLUMN, TS_FROM_VALUE, TS_NONE = 0, 1, 2
 ORDER_REFERENCE, ORDER_NONE = 0, 1
 XCHG_P2P, XCHG_NCCL = 0, 1
 
@@ -67,6 +67,12 @@ class BwStats(C.Structure):
     ]
 
 
+class BwSnapshot(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("key", C.POINTER(C.c_uint64)), ("pane_id", C.POINTER(C.c_int64)), ("acc", C.POINTER(C.c_uint64)),
+                ("count", C.POINTER(C.c_uint64)), ("open_seq", C.POINTER(C.c_uint64)), ("max_ts_us", C.POINTER(C.c_int64)),
+                ("closed_upto", C.POINTER(C.c_int64)), ("batch_no", C.c_uint64), ("gmax_ts_us", C.c_int64), ("last_epoch", C.c_uint64)]
+
+
 class BwSmapSpec(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("window", C.c_int32), ("val_dtype", C.c_int32), ("reserved", C.c_int32),
                 ("threshold", C.c_double), ("capacity_hint", C.c_uint64), ("max_batch_rows", C.c_uint64)]
@@ -99,6 +105,8 @@ SYMBOLS = {
     "bw_ingest_device": (C.c_int32, [_P, _P, _P, _P, C.c_uint64, C.c_uint64]),
     "bw_advance": (C.c_int32, [_P, C.c_uint64, C.c_int64, C.POINTER(BwEmit)]),
     "bw_eof": (C.c_int32, [_P, C.POINTER(BwEmit)]),
+    "bw_snapshot_take": (C.c_int32, [_P, C.POINTER(BwSnapshot)]),
+    "bw_snapshot_load": (C.c_int32, [_P, C.POINTER(BwSnapshot)]),
     "bw_window_bounds": (None, [C.POINTER(BwFoldSpec), C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "bw_fold_stats": (C.c_int32, [_P, C.POINTER(BwStats)]),
     "bw_fold_reset_timers": (C.c_int32, [_P]),

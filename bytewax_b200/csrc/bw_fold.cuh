@@ -486,7 +486,7 @@ __device__ __forceinline__ void bw_load_event(const BatchView& bv, int seg, u64 
     }
   }
   if (p.ts_from_value) {
-    ts = p.align_us + (i64)raw;
+    ts = p.align_us + ((p.ts_from_value == 1) ? (i64)raw : 0);  // 2 == BW_TS_NONE: everything in window 0
   } else {
     ts = (i64)bw_ld_stream_u64((const u64*)bv.ts[seg] + i);
   }
@@ -517,7 +517,7 @@ __device__ __noinline__ bool bw_locate(const BatchView& bv, const u64* seg_start
 // Event time of arrival index g (value-derived, or re-read from the ts column: an L1/L2 hit).
 __device__ __forceinline__ i64 bw_event_ts(const BatchView& bv, const u64* seg_start, const FoldParams& p, u64 g,
                                            u64 raw) {
-  if (p.ts_from_value) return p.align_us + (i64)raw;
+  if (p.ts_from_value) return p.align_us + ((p.ts_from_value == 1) ? (i64)raw : 0);
   int seg = 0;
   u64 off = g;
   if (bv.nseg > 1) bw_locate(bv, seg_start, g, seg, off);
@@ -579,7 +579,7 @@ k_fold(BatchView bv, Table t, FoldParams p, u32 batch_no, u32 sub_i, u32 sub_n) 
         u64 off = g - seg_start[wseg];
         if (!wuni) bw_locate(bv, seg_start, g, seg, off);
         key[u] = bw_ld_stream_u64(bv.keys[seg] + off);
-        if (p.ts_from_value || bv.vals[seg]) {
+        if (p.ts_from_value == 1 || bv.vals[seg]) {
           raw[u] = (p.val_dtype == 2) ? (u64)bw_ld_stream_u32((const u32*)bv.vals[seg] + off)
                                       : bw_ld_stream_u64((const u64*)bv.vals[seg] + off);
         }

@@ -19,6 +19,7 @@
 #define BW_PRE_MLP 8        // independent loads in flight per lane
 
 __device__ __forceinline__ i64 bw_load_ts(const BatchView& bv, int seg, u64 off, const FoldParams& p) {
+  if (p.ts_from_value == 2) return p.align_us;
   if (p.ts_from_value) {
     u64 raw = (p.val_dtype == 2) ? (u64)bw_ld_stream_u32((const u32*)bv.vals[seg] + off)
                                  : bw_ld_stream_u64((const u64*)bv.vals[seg] + off);

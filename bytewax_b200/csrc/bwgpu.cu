@@ -27,6 +27,7 @@
 #include "bw_common.cuh"
 #include "bw_exchange.cuh"
 #include "bw_bucket.cuh"
+#include "bw_snapshot.cuh"
 #include "bw_fold.cuh"
 #include "bw_keyed.cuh"
 #include "bw_prepass.cuh"
@@ -179,6 +180,10 @@ struct bw_fold {
   int seg_rpt = 16, seg_grid = 0;
   void (*seg_kernel)(BktBufs, Table, FoldParams, u32, i64) = nullptr;
   i64* d_span = nullptr;   // [min ts, max ts] of the activation (prepass)
+  // snapshot staging (bw_snapshot_take)
+  void* snap_dev = nullptr;
+  void* snap_host = nullptr;
+  unsigned long long* d_snap_ctr = nullptr;
   bool sub_auto = true;     // env BW_SUB_AUTO=0: never split an activation by its event-time span
   u64 sub_rows = ~0ULL;  // optional fold + close granularity inside one activation (env BW_SUB_ROWS); measured slower on C1
   // multi-GPU exchange
@@ -610,8 +615,11 @@ bw_status bw_fold_create(bw_ctx* ctx, const bw_fold_spec* spec, bw_fold** out) {
   if (spec->length_us <= 0 || spec->offset_us <= 0 || spec->offset_us > spec->length_us)
     CTX_FAIL(ctx, BW_ERR_SPEC, "need 0 < offset_us <= length_us (windowing.py:880-883)");
   if (spec->wait_us < 0) CTX_FAIL(ctx, BW_ERR_SPEC, "wait_us must be >= 0");
+  if (spec->ts_source < BW_TS_COLUMN || spec->ts_source > BW_TS_NONE) CTX_FAIL(ctx, BW_ERR_SPEC, "bad ts_source %d", spec->ts_source);
   if (spec->ts_source == BW_TS_FROM_VALUE && spec->val_dtype > BW_VAL_I64)
     CTX_FAIL(ctx, BW_ERR_SPEC, "BW_TS_FROM_VALUE needs an integer val_dtype");
+  if (spec->ts_source == BW_TS_NONE && spec->wait_us != BW_WAIT_FOREVER)
+    CTX_FAIL(ctx, BW_ERR_SPEC, "BW_TS_NONE (the *_final folds) needs wait_us == BW_WAIT_FOREVER: nothing closes before bw_eof");
   if (spec->max_batch_rows == 0 || spec->max_batch_rows >= (1ULL << 32) / (u64)ctx->world)
     CTX_FAIL(ctx, BW_ERR_SPEC, "max_batch_rows * world must be in [1, 2^32)");
   CU(ctx, cudaSetDevice(ctx->device));
@@ -653,7 +661,7 @@ bw_status bw_fold_create(bw_ctx* ctx, const bw_fold_spec* spec, bw_fold** out) {
   }
   p.reduction = spec->reduction;
   p.val_dtype = spec->val_dtype;
-  p.ts_from_value = spec->ts_source == BW_TS_FROM_VALUE;
+  p.ts_from_value = spec->ts_source == BW_TS_FROM_VALUE ? 1 : (spec->ts_source == BW_TS_NONE ? 2 : 0);
   p.track_wm = spec->wait_us != BW_WAIT_FOREVER;
   p.ordered = spec->ordered;
   p.need_count = spec->reduction == BW_RED_MEAN;
@@ -702,7 +710,7 @@ void bw_fold_destroy(bw_fold* f) {
                  f->e.l_ts, f->e.l_seq, f->e.l_epoch, f->d_rmin, f->d_rmax, f->d_rbad, f->d_verdict, f->d_kflat,
                  f->d_ksorted, f->d_tsflat, f->d_tssorted, f->d_prefmax, f->d_idx, f->d_idxsorted, f->d_late, f->d_cub,
                  f->d_sk, f->d_sk2, f->d_gather, f->d_perm, f->d_perm2, f->xchg_base, f->d_tile_counts,
-                 f->d_send_counts, f->d_all_counts, f->send_keys, f->send_vals, f->send_ts, f->d_span,
+                 f->d_send_counts, f->d_all_counts, f->send_keys, f->send_vals, f->send_ts, f->d_span, f->snap_dev, f->d_snap_ctr,
                  f->bk.keys, f->bk.vals, f->bk.ts, f->bk.g, f->bk.tile_counts, f->bk.cnt, f->bk.off};
   for (void* p : dev)
     if (p) cudaFree(p);
@@ -717,7 +725,7 @@ void bw_fold_destroy(bw_fold* f) {
     if (s.h_vals) cudaFreeHost(s.h_vals);
     if (s.h_ts) cudaFreeHost(s.h_ts);
   }
-  void* host[] = {f->h_ctr, f->h_verdict, f->h_all_counts, f->ho_ckey, f->ho_cacc, f->ho_ccount, f->ho_cepoch,
+  void* host[] = {f->snap_host, f->h_ctr, f->h_verdict, f->h_all_counts, f->ho_ckey, f->ho_cacc, f->ho_ccount, f->ho_cepoch,
                   f->ho_cwid, f->ho_lkey, f->ho_lval, f->ho_lepoch, f->ho_lwid, f->ho_lts};
   for (void* p : host)
     if (p) cudaFreeHost(p);
@@ -1096,7 +1104,7 @@ bw_status bw_ingest_device(bw_fold* f, const uint64_t* d_keys, const void* d_val
   bw_ctx* ctx = f->ctx;
   if (f->eof_done) FAIL(f, BW_ERR_STATE, "ingest after eof");
   if (rows > f->spec.max_batch_rows) FAIL(f, BW_ERR_SPEC, "ingest: rows > max_batch_rows");
-  if (rows && (!d_keys || (!d_vals && (f->spec.reduction != BW_RED_COUNT || !f->has_ts)) || (f->has_ts && !d_ts_us)))
+  if (rows && (!d_keys || (!d_vals && (f->spec.reduction != BW_RED_COUNT || f->spec.ts_source == BW_TS_FROM_VALUE)) || (f->has_ts && !d_ts_us)))
     FAIL(f, BW_ERR_SPEC, "ingest: missing column");
   CU(ctx, cudaSetDevice(ctx->device));
   CU(ctx, cudaEventRecord(f->ev_in, f->s_compute));
@@ -1343,6 +1351,102 @@ bw_status bw_eof(bw_fold* f, bw_emit* out) {
   f->st.kernel_launches++;
   f->eof_done = true;
   return collect(f, out);
+}
+
+// ---------------------------------------------------------------------------
+// snapshot / restore
+// ---------------------------------------------------------------------------
+static SnapCols snap_cols(void* base, u64 n) {
+  SnapCols c;
+  u64* b = (u64*)base;
+  c.key = b;
+  c.pane = (i64*)(b + n);
+  c.acc = b + 2 * n;
+  c.cnt = b + 3 * n;
+  c.seq = b + 4 * n;
+  c.max_ts = (i64*)(b + 5 * n);
+  c.closed_upto = (i64*)(b + 6 * n);
+  c.cap = n;
+  return c;
+}
+
+bw_status bw_snapshot_take(bw_fold* f, bw_snapshot* out) {
+  if (!f || !out) return BW_ERR_SPEC;
+  bw_ctx* ctx = f->ctx;
+  CU(ctx, cudaSetDevice(ctx->device));
+  if (f->eof_done) FAIL(f, BW_ERR_STATE, "snapshot after eof");
+  cudaStream_t s = f->s_compute;
+  if (f->s_x) CU(ctx, cudaStreamSynchronize(f->s_x));
+  if (!f->d_snap_ctr) CU(ctx, dmalloc(&f->d_snap_ctr, 2));
+  CU(ctx, cudaMemsetAsync(f->d_snap_ctr, 0, 2 * sizeof(unsigned long long), s));
+  k_snap_count<<<f->close_grid, 256, 0, s>>>(f->t, f->d_snap_ctr);
+  unsigned long long n = 0;
+  CU(ctx, cudaMemcpyAsync(&n, f->d_snap_ctr, sizeof n, cudaMemcpyDeviceToHost, s));
+  CU(ctx, cudaMemcpyAsync(f->h_ctr, f->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+  CU(ctx, cudaStreamSynchronize(s));
+  if (f->h_ctr->err) FAIL(f, (bw_status)f->h_ctr->err, "a kernel reported status %u before the snapshot", f->h_ctr->err);
+  if (f->snap_dev) { cudaFree(f->snap_dev); f->snap_dev = nullptr; }
+  if (f->snap_host) { cudaFreeHost(f->snap_host); f->snap_host = nullptr; }
+  const u64 rows = n ? n : 1;
+  CU(ctx, cudaMalloc(&f->snap_dev, rows * 7 * 8));
+  CU(ctx, cudaHostAlloc(&f->snap_host, rows * 7 * 8, cudaHostAllocDefault));
+  SnapCols dc = snap_cols(f->snap_dev, rows), hc = snap_cols(f->snap_host, rows);
+  if (n) {
+    k_snap_fill<<<f->close_grid, 256, 0, s>>>(f->t, dc, f->d_snap_ctr + 1);
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaMemcpyAsync(f->snap_host, f->snap_dev, rows * 7 * 8, cudaMemcpyDeviceToHost, s));
+    CU(ctx, cudaStreamSynchronize(s));
+  }
+  f->st.kernel_launches += n ? 2 : 1;
+  memset(out, 0, sizeof *out);
+  out->n = n;
+  out->key = hc.key;
+  out->pane_id = hc.pane;
+  out->acc = hc.acc;
+  out->count = hc.cnt;
+  out->open_seq = hc.seq;
+  out->max_ts_us = hc.max_ts;
+  out->closed_upto = hc.closed_upto;
+  out->batch_no = f->batch_no;
+  out->gmax_ts_us = (i64)f->h_ctr->gmax_ts;
+  out->last_epoch = f->last_epoch;
+  return BW_OK;
+}
+
+bw_status bw_snapshot_load(bw_fold* f, const bw_snapshot* in) {
+  if (!f || !in) return BW_ERR_SPEC;
+  bw_ctx* ctx = f->ctx;
+  CU(ctx, cudaSetDevice(ctx->device));
+  if (f->batch_no != 0 || f->eof_done) FAIL(f, BW_ERR_STATE, "bw_snapshot_load needs a freshly created fold");
+  if (in->n && (!in->key || !in->pane_id || !in->acc || !in->count || !in->open_seq || !in->max_ts_us || !in->closed_upto))
+    FAIL(f, BW_ERR_SPEC, "bw_snapshot_load: missing column");
+  if (in->batch_no >= (1ULL << 32)) FAIL(f, BW_ERR_SPEC, "bw_snapshot_load: bad batch_no");
+  cudaStream_t s = f->s_compute;
+  const u64 n = in->n;
+  if (n) {
+    void* dev = nullptr;
+    CU(ctx, cudaMalloc(&dev, n * 7 * 8));
+    SnapCols dc = snap_cols(dev, n);
+    const void* src[7] = {in->key, in->pane_id, in->acc, in->count, in->open_seq, in->max_ts_us, in->closed_upto};
+    void* dst[7] = {dc.key, dc.pane, dc.acc, dc.cnt, dc.seq, dc.max_ts, dc.closed_upto};
+    for (int c = 0; c < 7; ++c) CU(ctx, cudaMemcpyAsync(dst[c], src[c], n * 8, cudaMemcpyHostToDevice, s));
+    k_snap_load<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(f->t, f->p, dc, n, (u32)in->batch_no, ctx->world, ctx->rank);
+    CU(ctx, cudaGetLastError());
+    // re-rank every restored key (newest pane into the hot slot); nothing is closable in a state dumped after an advance
+    k_close_dirty<<<f->close_grid, 256, 0, s>>>(f->t, f->p, f->e, in->last_epoch);
+    k_reset_dirty<<<1, 1, 0, s>>>(f->t);
+    f->st.kernel_launches += 3;
+    CU(ctx, cudaStreamSynchronize(s));
+    cudaFree(dev);
+  }
+  k_snap_set_gmax<<<1, 1, 0, s>>>(f->d_ctr, (i64)in->gmax_ts_us);
+  CU(ctx, cudaMemcpyAsync(f->h_ctr, f->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+  CU(ctx, cudaStreamSynchronize(s));
+  if (f->h_ctr->err) FAIL(f, (bw_status)f->h_ctr->err, "restore failed on the device with status %u (capacity_hint too small?)", f->h_ctr->err);
+  f->batch_no = (u32)in->batch_no;
+  f->last_epoch = in->last_epoch;
+  f->have_epoch = in->last_epoch != 0;
+  return BW_OK;
 }
 
 void bw_window_bounds(const bw_fold_spec* spec, int64_t window_id, int64_t* open_us, int64_t* close_us) {

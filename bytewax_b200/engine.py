@@ -201,6 +201,70 @@ class _GpuWindowStep:
         return rows
 
 
+def _gpu_step_for(step_id: str, plan):
+    from bytewax_b200.operators import GpuFinalPlan
+
+    return _GpuFinalStep(step_id, plan) if isinstance(plan, GpuFinalPlan) else _GpuWindowStep(step_id, plan)
+
+
+class _GpuFinalStep(_GpuWindowStep):
+    """One worker's ``stateful_batch`` of a numeric ``*_final`` fold (``reduce_final(add|max|min)``, ``count_final``,
+    ``max_final``, ``min_final``) on ``libbwgpu``: ``ts_source == BW_TS_NONE``, every key's accumulator is emitted at EOF in
+    ascending key-string order (``_FoldFinalLogic.on_eof`` under the engine's sorted-key EOF walk, src/operators.rs:862-894)."""
+
+    def __init__(self, step_id: str, plan):
+        import numpy as np
+
+        from bytewax_b200 import gpu
+
+        self.np, self.plan, self.step_id = np, plan, step_id
+        self.float_vals = False
+        self.fold = None
+        self._mk = lambda dtype: gpu.WindowFold(
+            _get_gpu_ctx(), plan.reduction, val_dtype=dtype, final=True,
+            capacity_hint=int(os.environ.get("BYTEWAX_B200_KEYS", 1 << 20)),
+            max_batch_rows=int(os.environ.get("BYTEWAX_B200_BATCH", 1 << 22)), max_emit_rows=1 << 22, max_late_rows=1 << 10)
+        self.key_ids: Dict[str, int] = {}
+        self.id_keys: Dict[int, str] = {}
+        self.resort = False
+
+    def on_epoch(self, epoch: int, items: list) -> list:
+        np = self.np
+        keys, vals = [], []
+        for item in items:
+            try:
+                key, value = item
+            except (TypeError, ValueError) as ex:
+                raise TypeError(f"step {self.step_id!r} requires `(key, value)` 2-tuple as upstream for routing; got a {type(item)!r} instead") from ex
+            if not isinstance(key, str):
+                raise TypeError(f"step {self.step_id!r} requires `str` keys in `(key, value)` from upstream; got a {type(key)!r} instead")
+            if isinstance(value, bool) or not isinstance(value, (int, float)):
+                raise TypeError(f"step {self.step_id!r}: the CUDA fold needs numeric values; got a {type(value)!r}")
+            keys.append(self._key_id(key))
+            vals.append(value)
+        if not keys:
+            return []
+        v = np.array(vals)
+        if self.fold is None:
+            self.float_vals = v.dtype.kind == "f"
+            self.fold = self._mk("f64" if self.float_vals else "i64")
+        if v.dtype.kind == "f" and not self.float_vals:
+            raise TypeError(f"step {self.step_id!r}: value type changed from integer to float mid-stream")
+        self.fold.ingest(np.array(keys, dtype=np.uint64), v, None, epoch)
+        return []
+
+    def on_eof(self) -> list:
+        if self.fold is None:
+            return []
+        em = self.fold.eof()
+        self.fold.close()
+        self.fold = None
+        rows = [(self._key_str(k), acc) for k, acc in zip(em.closed_key.tolist(), em.closed_acc.tolist())]
+        if self.resort:
+            rows.sort(key=lambda r: r[0])
+        return rows
+
+
 # ---------------------------------------------------------------------------
 # the engine proper
 # ---------------------------------------------------------------------------
@@ -403,7 +467,7 @@ class _Run:
         if S is None:
             S = self.state[st.step_id] = {
                 "logics": [dict() for _ in range(self.W)], "sched": [dict() for _ in range(self.W)],
-                "gpu": [(_GpuWindowStep(st.step_id, plan) if plan is not None else None) for _ in range(self.W)], "eof_done": False,
+                "gpu": [(_gpu_step_for(st.step_id, plan) if plan is not None else None) for _ in range(self.W)], "eof_done": False,
             }
         # exchange: route every item to the worker owning its key (src/operators.rs:582-591)
         routed: List[Dict[int, list]] = [defaultdict(list) for _ in range(self.W)]

@@ -112,14 +112,19 @@ class WindowFold:
         max_late_rows: int = 1 << 16,
         ring_slots: int = 3,
         exchange: int = N.XCHG_P2P,
+        final: bool = False,
     ):
+        """``final=True``: no event time and no windows -- one accumulator per key, emitted by
+        ``eof()`` in key order as window 0 (the ``*_final`` operators); ``ingest`` takes no ``ts``."""
         self.ctx, self.lib = ctx, ctx.lib
+        if final:
+            ts_from_value, wait_us = False, None
         self.reduction, self.val_dtype, self.ts_from_value = reduction, val_dtype, ts_from_value
         s = N.BwFoldSpec()
         s.struct_size = C.sizeof(N.BwFoldSpec)
         s.reduction = N.RED[reduction]
         s.val_dtype = N.VAL[val_dtype]
-        s.ts_source = N.TS_FROM_VALUE if ts_from_value else N.TS_COLUMN
+        s.ts_source = N.TS_NONE if final else (N.TS_FROM_VALUE if ts_from_value else N.TS_COLUMN)
         s.length_us = length_us
         s.offset_us = offset_us if offset_us is not None else length_us
         s.align_to_us = align_to_us
@@ -133,7 +138,7 @@ class WindowFold:
         s.max_emit_rows = max_emit_rows
         s.max_late_rows = max_late_rows
         self.spec = s
-        self.has_ts = not ts_from_value
+        self.has_ts = not ts_from_value and not final
         self.has_vals = True
         h = C.c_void_p()
         N.check(self.lib.bw_fold_create(ctx.h, C.byref(s), C.byref(h)), ctx.h)
@@ -233,6 +238,35 @@ class WindowFold:
         e = N.BwEmit()
         N.check(self.lib.bw_eof(self.h, C.byref(e)), self.ctx.h)
         return self._wrap(e, copy)
+
+    _SNAP_COLS = (("key", np.uint64), ("pane_id", np.int64), ("acc", np.uint64), ("count", np.uint64), ("open_seq", np.uint64),
+                  ("max_ts_us", np.int64), ("closed_upto", np.int64))
+
+    def snapshot(self) -> dict:
+        """State after the last ``advance`` as numpy columns (one row per live (key, pane)) plus three scalars:
+        the columnar form of ``_WindowLogic.snapshot`` (windowing.py:1182-1190) for every key at once."""
+        sn = N.BwSnapshot()
+        N.check(self.lib.bw_snapshot_take(self.h, C.byref(sn)), self.ctx.h)
+        n = int(sn.n)
+        out = {name: (np.ctypeslib.as_array(getattr(sn, name), shape=(n,)).view(dt).copy() if n else np.zeros(0, dt))
+               for name, dt in self._SNAP_COLS}
+        out.update(batch_no=int(sn.batch_no), gmax_ts_us=int(sn.gmax_ts_us), last_epoch=int(sn.last_epoch))
+        return out
+
+    def restore(self, snap: dict):
+        """Load ``snapshot()`` output into this freshly created fold (same window spec; any capacity / world size)."""
+        sn = N.BwSnapshot()
+        keep = []
+        n = len(snap["key"])
+        sn.n = n
+        for name, dt in self._SNAP_COLS:
+            a = np.ascontiguousarray(snap[name], dtype=dt)
+            keep.append(a)
+            ctype = C.c_int64 if dt is np.int64 else C.c_uint64
+            setattr(sn, name, a.ctypes.data_as(C.POINTER(ctype)))
+        sn.batch_no, sn.gmax_ts_us, sn.last_epoch = snap["batch_no"], snap["gmax_ts_us"], snap["last_epoch"]
+        N.check(self.lib.bw_snapshot_load(self.h, C.byref(sn)), self.ctx.h)
+        self._epoch = max(self._epoch, int(snap["last_epoch"]))
 
     def window_bounds(self, window_id: int) -> Tuple[int, int]:
         o, c = C.c_int64(), C.c_int64()

@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import copy
 import itertools
+import operator as _pyop
 from abc import ABC, abstractmethod
 from dataclasses import dataclass, field
 from datetime import datetime, timedelta, timezone
@@ -406,13 +407,24 @@ class _StatefulLogicShim(StatefulBatchLogic):
         return self.logic.snapshot()
 
 
+@dataclass(frozen=True)
+class GpuFinalPlan:
+    """What the engine needs to run a numeric ``*_final`` fold on ``libbwgpu`` (``bw_fold_spec.ts_source ==
+    BW_TS_NONE``): attached to the ``stateful_batch`` builder by ``count_final`` / ``reduce_final(add|max|min)`` /
+    ``max_final`` / ``min_final``; absent for arbitrary Python folders, which stay on the host path."""
+
+    reduction: str  # sum | min | max
+
+
 @operator
-def stateful(step_id: str, up: KeyedStream, builder: Callable[[Optional[Any]], StatefulLogic]) -> KeyedStream:
+def stateful(step_id: str, up: KeyedStream, builder: Callable[[Optional[Any]], StatefulLogic],
+             _gpu_plan: Optional[GpuFinalPlan] = None) -> KeyedStream:
     """operators/__init__.py:1065."""
 
     def shim_builder(resume_state):
         return _StatefulLogicShim(step_id, builder, builder(resume_state))
 
+    shim_builder._gpu_plan = _gpu_plan  # read by bytewax_b200.engine
     return stateful_batch("stateful_batch", up, shim_builder)
 
 
@@ -467,7 +479,7 @@ def collect(step_id: str, up: KeyedStream, timeout: timedelta, max_size: int) ->
 def count_final(step_id: str, up: Stream, key: Callable[[Any], str]) -> KeyedStream:
     """operators/__init__.py:1221: ``init_count`` then ``sum``."""
     down = map("init_count", up, lambda x: (key(x), 1))
-    return reduce_final("sum", down, lambda s, x: s + x)
+    return reduce_final("sum", down, lambda s, x: s + x, _gpu_plan=GpuFinalPlan("sum"))
 
 
 @dataclass
@@ -490,19 +502,27 @@ class _FoldFinalLogic(StatefulLogic):
 
 
 @operator
-def fold_final(step_id: str, up: KeyedStream, builder: Callable[[], Any], folder: Callable[[Any, Any], Any]) -> KeyedStream:
+def fold_final(step_id: str, up: KeyedStream, builder: Callable[[], Any], folder: Callable[[Any, Any], Any],
+               _gpu_plan: Optional[GpuFinalPlan] = None) -> KeyedStream:
     """operators/__init__.py:1953."""
 
     def shim_builder(resume_state):
         state = resume_state if resume_state is not None else builder()
         return _FoldFinalLogic(step_id, folder, state)
 
-    return stateful("stateful", up, shim_builder)
+    return stateful("stateful", up, shim_builder, _gpu_plan)
+
+
+_NUMERIC_FINAL_REDUCERS = {_pyop.add: "sum", max: "max", min: "min"}
 
 
 @operator
-def reduce_final(step_id: str, up: KeyedStream, reducer: Callable[[Any, Any], Any]) -> KeyedStream:
+def reduce_final(step_id: str, up: KeyedStream, reducer: Callable[[Any, Any], Any],
+                 _gpu_plan: Optional[GpuFinalPlan] = None) -> KeyedStream:
     """operators/__init__.py:2783: per-batch ``pre_reduce`` combiner, then ``fold_final``."""
+    plan = _gpu_plan
+    if plan is None and reducer in _NUMERIC_FINAL_REDUCERS:
+        plan = GpuFinalPlan(_NUMERIC_FINAL_REDUCERS[reducer])
 
     def pre_reducer(mixed_batch):
         states: Dict[str, Any] = {}
@@ -515,19 +535,19 @@ def reduce_final(step_id: str, up: KeyedStream, reducer: Callable[[Any, Any], An
     def shim_folder(s, v):
         return v if s is None else reducer(s, v)
 
-    return fold_final("fold_final", pre_up, _untyped_none, shim_folder)
+    return fold_final("fold_final", pre_up, _untyped_none, shim_folder, _gpu_plan=plan)
 
 
 @operator
 def max_final(step_id: str, up: KeyedStream, by: Callable[[Any], Any] = _identity) -> KeyedStream:
     """operators/__init__.py:2624."""
-    return reduce_final("reduce_final", up, partial(max, key=by))
+    return reduce_final("reduce_final", up, partial(max, key=by), _gpu_plan=GpuFinalPlan("max") if by is _identity else None)
 
 
 @operator
 def min_final(step_id: str, up: KeyedStream, by: Callable[[Any], Any] = _identity) -> KeyedStream:
     """operators/__init__.py:2685."""
-    return reduce_final("reduce_final", up, partial(min, key=by))
+    return reduce_final("reduce_final", up, partial(min, key=by), _gpu_plan=GpuFinalPlan("min") if by is _identity else None)
 
 
 @dataclass

@@ -90,8 +90,14 @@ typedef enum { BW_VAL_U64 = 0, BW_VAL_I64 = 1, BW_VAL_F32 = 2, BW_VAL_F64 = 3 } 
 
 typedef enum {
   BW_TS_COLUMN = 0,     /* ts_us column supplied with every batch */
-  BW_TS_FROM_VALUE = 1  /* ts_us = align_to_us + (int64)val: "the value is the
+  BW_TS_FROM_VALUE = 1, /* ts_us = align_to_us + (int64)val: "the value is the
                            event time", examples/benchmark_windowing.py:16-21 */
+  BW_TS_NONE = 2        /* no event time: one accumulator per key, emitted by
+                           bw_eof in key order as window 0 -- the `*_final`
+                           operators (`_FoldFinalLogic`, operators/__init__.py:
+                           1923-1950; `reduce_final` :2783-2857, `count_final`
+                           :1221-1272, `max_final`/`min_final` :2624-2742).
+                           Requires wait_us == BW_WAIT_FOREVER; no ts_us column */
 } bw_ts_source;
 
 typedef enum {
@@ -224,6 +230,35 @@ bw_status bw_advance(bw_fold* fold, uint64_t closed_epoch, int64_t system_now_us
 /* End of input: watermark := UTC_MAX, every open window closes (ascending key
  * order), all state is dropped.  Collective when world > 1. */
 bw_status bw_eof(bw_fold* fold, bw_emit* out);
+
+/* ---- snapshot / restore ------------------------------
+ * One row per live (key, pane): what `_WindowLogic.snapshot` captures per key
+ * (`_WindowSnapshot`, pysrc/bytewax/operators/windowing.py:1032-1037,
+ * 1182-1190: clock state, open windows, accumulators) in columnar form, for a
+ * recovery store to persist (src/operators.rs:931-1003 writes one snapshot per
+ * awoken key per epoch; src/recovery.rs:1520-1614 reads them back). */
+typedef struct bw_snapshot {
+  uint64_t n;                  /* rows */
+  const uint64_t* key;
+  const int64_t* pane_id;      /* window id for tumbling windows; pane (gcd(length, offset)) id for sliding */
+  const uint64_t* acc;         /* accumulator bits, as bw_emit.closed_acc before the float decoding of min/max */
+  const uint64_t* count;       /* folded values (MEAN divisor) */
+  const uint64_t* open_seq;    /* first-open order of the pane: activation << 32 | arrival index */
+  const int64_t* max_ts_us;    /* per key (repeated on each of its rows): the event clock's state */
+  const int64_t* closed_upto;  /* sliding: last window id already emitted for the key, INT64_MIN if none */
+  uint64_t batch_no;           /* activations folded so far (keeps open_seq ordered across a restore) */
+  int64_t gmax_ts_us;          /* running max event time over everything ingested (lateness verdict) */
+  uint64_t last_epoch;
+} bw_snapshot;
+
+/* Dump the state after the last bw_advance.  Host pointers into pinned memory
+ * owned by the library, valid until the next bw_snapshot_take / destroy. */
+bw_status bw_snapshot_take(bw_fold* fold, bw_snapshot* out);
+/* Load a dump into a freshly created fold with the same window spec (capacity
+ * and world size may differ: rows are re-inserted by key; with world > 1 every
+ * rank passes the full row set and keeps the keys it owns, the reference's
+ * rescale on resume, src/recovery.rs:1701-1781). */
+bw_status bw_snapshot_load(bw_fold* fold, const bw_snapshot* in);
 
 /* Window bounds for the `meta` stream: WindowMetadata(open_time, close_time),
  * windowing.py:620-623. */

@@ -102,3 +102,57 @@ def test_columnar_source_feeds_the_cuda_fold():
     assert wids == list(range(10))  # 1e6 events x 100 us = 100 s -> windows 0..9
     first_epoch_keys = [k for k, (w, _c) in out if w == 0]
     assert first_epoch_keys == sorted(first_epoch_keys)  # ascending key-string order within an activation
+
+
+def test_final_folds_on_gpu_match_the_reference_expectations():
+    # pytests/operators/test_count_final.py:6-16, test_reduce_final.py:6-17, test_max_min_final.py (sorted-key EOF order)
+    def build():
+        outs = [[], [], [], []]
+        flow = Dataflow("test_df")
+        s = op.input("inp", flow, TestingSource(["a", "a", "b", "c", "b", "a"]))
+        op.output("o0", op.count_final("count", s, lambda x: x), TestingSink(outs[0]))
+        nums = op.input("nums", flow, TestingSource([("b", 7), ("a", 1), ("a", 8), ("10", 1), ("9", 2), ("b", -3), ("a", 5)]))
+        op.output("o1", op.reduce_final("sum", nums, operator.add), TestingSink(outs[1]))
+        op.output("o2", op.max_final("max", nums), TestingSink(outs[2]))
+        op.output("o3", op.min_final("min", nums), TestingSink(outs[3]))
+        return flow, outs
+
+    host, gpu = _both(build)
+    assert gpu[0] == [("a", 3), ("b", 2), ("c", 1)]
+    assert gpu[1] == [("10", 1), ("9", 2), ("a", 14), ("b", 4)]
+    assert gpu[2] == [("10", 1), ("9", 2), ("a", 8), ("b", 7)]
+    assert gpu[3] == [("10", 1), ("9", 2), ("a", 1), ("b", -3)]
+    assert gpu == host
+
+
+def test_final_fold_large_against_numpy():
+    """count/sum/max per key over 3 activations of 2^20 rows through the C ABI (ts_source == BW_TS_NONE)."""
+    from bytewax_b200 import gpu
+
+    ctx = gpu.Context(0)
+    rnd = np.random.default_rng(3)
+    n, nk = 1 << 20, 50_000
+    for red in ("count", "sum", "max", "min"):
+        fold = gpu.WindowFold(ctx, red, val_dtype="i64", final=True, capacity_hint=nk, max_batch_rows=n, max_emit_rows=nk + 16)
+        allk, allv = [], []
+        for _ in range(3):
+            k = rnd.integers(0, nk, n).astype(np.uint64)
+            v = rnd.integers(-1000, 1000, n)
+            fold.ingest(k, None if red == "count" else v)
+            assert fold.advance().closed_key.size == 0  # nothing is emitted before EOF
+            allk.append(k)
+            allv.append(v)
+        em = fold.eof()
+        k, v = np.concatenate(allk), np.concatenate(allv)
+        order = np.argsort(k, kind="stable")
+        uk, start = np.unique(k[order], return_index=True)
+        if red == "count":
+            want = np.diff(np.append(start, k.size))
+        else:
+            want = {"sum": np.add, "max": np.maximum, "min": np.minimum}[red].reduceat(v[order], start)
+        got = dict(zip(em.closed_key.tolist(), em.closed_acc.astype(np.int64).tolist()))
+        assert got == dict(zip(uk.tolist(), want.tolist())), red
+        assert em.closed_key.tolist() == sorted(uk.tolist(), key=str)  # ascending key-string order
+        assert set(em.closed_window_id.tolist()) == {0}
+        fold.close()
+    ctx.close()

@@ -329,3 +329,43 @@ def test_c1_properties_and_sampled_parity(ctx, fold_mode):
     ctx.dev_free(dv)
     fold.close()
     orc.close()
+
+
+@pytest.mark.parametrize("red,length,offset,wait", [("count", 10, None, 2), ("sum", 10, 5, 3), ("max", 7, None, 0)])
+def test_snapshot_restore_resumes_identically(ctx, red, length, offset, wait):
+    """bw_snapshot_take after three activations, bw_snapshot_load into a fresh fold of a different capacity, then the
+    same remaining activations through both: identical rows from there on (and equal to the C oracle's), the contract
+    of the reference's resume tests (pytests/test_recovery.py, operators/test_stateful.py:151-291) at the fold level."""
+    S = 1_000_000
+    spec = dict(reduction=red, length_us=length * S, offset_us=offset * S if offset else None,
+                align_us=1_640_995_200_000_000, wait_us=wait * S, ordered=False)
+    batches = _random_batches(77, 6, 30_000, 2000, 12 * S, min(wait, 2) * S, spec["align_us"] - 3 * S)
+    orc = coracle.COracle(red, spec["length_us"], spec["offset_us"], spec["align_us"], wait * S, False)
+    a = _make_fold(ctx, spec, False, capacity_hint=8192, max_emit_rows=1 << 20)
+    rows_a, rows_b = [], []
+    for keys, ts, vals in batches[:3]:
+        orc.on_batch(keys, ts, vals)
+        a.ingest(keys, vals, ts)
+    first = a.advance()
+    snap = a.snapshot()
+    assert len(snap["key"]) > 0 and snap["batch_no"] == 3
+    b = _make_fold(ctx, spec, False, capacity_hint=3000, max_emit_rows=1 << 20)
+    b.restore(snap)
+    for keys, ts, vals in batches[3:]:
+        orc.on_batch(keys, ts, vals)
+        a.ingest(keys, vals, ts)
+        b.ingest(keys, vals, ts)
+    orc.on_eof()
+    for f, rows in ((a, rows_a), (b, rows_b)):
+        for em in (f.advance(), f.eof()):
+            rows.append((em.closed_key.tolist(), em.closed_window_id.tolist(), em.closed_acc.astype(np.int64).tolist(),
+                         em.late_key.tolist(), em.late_window_id.tolist()))
+    assert rows_a == rows_b
+    ck, cw, ca, _, _ = orc.closed()
+    got_k = first.closed_key.tolist() + rows_b[0][0] + rows_b[1][0]
+    got_w = first.closed_window_id.tolist() + rows_b[0][1] + rows_b[1][1]
+    got_a = first.closed_acc.astype(np.int64).tolist() + rows_b[0][2] + rows_b[1][2]
+    assert (got_k, got_w, got_a) == (ck.tolist(), cw.tolist(), ca.tolist())
+    a.close()
+    b.close()
+    orc.close()
