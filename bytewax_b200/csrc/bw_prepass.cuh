@@ -15,7 +15,7 @@
 #include "bw_fold.cuh"
 
 #define BW_RANGE_ROWS 2048  // rows per warp-range
-#define BW_PRE_THREADS 256
+#define BW_PRE_THREADS 128  // 128 x 62 registers fit beside three resident k_fold blocks: the verdict pass of the next activation co-runs with the fold
 #define BW_PRE_MLP 8        // independent loads in flight per lane
 
 __device__ __forceinline__ i64 bw_load_ts(const BatchView& bv, int seg, u64 off, const FoldParams& p) {

@@ -133,6 +133,8 @@ struct bw_fold {
   cudaStream_t s_compute = nullptr, s_copy = nullptr, s_pre = nullptr, s_x = nullptr;  // s_x: partition + exchange
   cudaEvent_t ev_fold_done = nullptr, ev_xchg_done = nullptr, ev_src_ready = nullptr;
   bool fold_recorded = false;
+  cudaEvent_t ev_gen = nullptr;      // last bw_gen_c1 (the only producer of device columns this library runs itself)
+  cudaEvent_t pre_wait = nullptr;    // what the verdict pass of the activation in flight has to wait for, if anything
   cudaEvent_t ev_in = nullptr, ev_pre = nullptr, ev_h2d = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
   int val_bytes = 8;
   bool has_vals = true, has_ts = false;
@@ -469,7 +471,12 @@ static bw_status fold_alloc(bw_fold* f) {
   CU(ctx, cudaHostAlloc((void**)&f->h_verdict, 64, cudaHostAllocDefault));
   CU(ctx, cudaStreamCreateWithFlags(&f->s_compute, cudaStreamNonBlocking));
   CU(ctx, cudaStreamCreateWithFlags(&f->s_copy, cudaStreamNonBlocking));
-  CU(ctx, cudaStreamCreateWithFlags(&f->s_pre, cudaStreamNonBlocking));
+  {
+    // the verdict pass gates the next fold: let its blocks be placed first whenever an SM has room
+    int prio_lo = 0, prio_hi = 0;
+    CU(ctx, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CU(ctx, cudaStreamCreateWithPriority(&f->s_pre, cudaStreamNonBlocking, prio_hi));
+  }
   if (getenv("BW_NO_OVERLAP")) f->s_x = f->s_compute;  // diagnostic: serialise exchange and fold
   else CU(ctx, cudaStreamCreateWithFlags(&f->s_x, cudaStreamNonBlocking));
   CU(ctx, cudaEventCreateWithFlags(&f->ev_fold_done, cudaEventDisableTiming));
@@ -738,6 +745,7 @@ void bw_fold_destroy(bw_fold* f) {
   if (f->s_pre) cudaStreamDestroy(f->s_pre);
   if (f->s_x && f->s_x != f->s_compute) cudaStreamDestroy(f->s_x);
   if (f->ev_in) cudaEventDestroy(f->ev_in);
+  if (f->ev_gen) cudaEventDestroy(f->ev_gen);
   if (f->ev_pre) cudaEventDestroy(f->ev_pre);
   if (f->ev_h2d) cudaEventDestroy(f->ev_h2d);
   delete f;
@@ -923,7 +931,7 @@ static bw_status run_batch(bw_fold* f, const u64* d_keys, const void* d_vals, co
   }
   bool clean = true;
   if (f->p.track_wm && max_total > 0) {
-    if (pre_stream != f->s_compute && ctx->world == 1) CU(ctx, cudaStreamWaitEvent(pre_stream, f->ev_in, 0));
+    if (pre_stream != f->s_compute && ctx->world == 1 && f->pre_wait) CU(ctx, cudaStreamWaitEvent(pre_stream, f->pre_wait, 0));
     const u64 nranges = (max_total + BW_RANGE_ROWS - 1) / BW_RANGE_ROWS;
     int grid = (int)std::min<u64>((nranges * 32 + BW_PRE_THREADS - 1) / BW_PRE_THREADS, (u64)ctx->sm_count * 8);
     if (grid < 1) grid = 1;
@@ -1087,6 +1095,7 @@ bw_status bw_ingest_commit(bw_fold* f, const bw_batch* batch, uint64_t rows, uin
   CU(ctx, cudaEventRecord(f->ev_h2d, f->s_copy));
   CU(ctx, cudaStreamWaitEvent(f->s_compute, f->ev_h2d, 0));
   CU(ctx, cudaEventRecord(f->ev_in, f->s_copy));
+  f->pre_wait = f->ev_in;
   CU(ctx, cudaEventRecord(f->ev_src_ready, f->s_copy));
   bw_status st = run_batch(f, sg.d_keys, sg.d_vals, sg.d_ts, rows, epoch);
   if (st != BW_OK) return st;
@@ -1107,7 +1116,10 @@ bw_status bw_ingest_device(bw_fold* f, const uint64_t* d_keys, const void* d_val
   if (rows && (!d_keys || (!d_vals && (f->spec.reduction != BW_RED_COUNT || f->spec.ts_source == BW_TS_FROM_VALUE)) || (f->has_ts && !d_ts_us)))
     FAIL(f, BW_ERR_SPEC, "ingest: missing column");
   CU(ctx, cudaSetDevice(ctx->device));
-  CU(ctx, cudaEventRecord(f->ev_in, f->s_compute));
+  // The caller's columns are complete (bwgpu.h): the verdict pass takes no ordering from the fold's stream, so
+  // it runs beside the previous activation's fold instead of behind it.  Columns written by this library's own
+  // generator are ordered through its event.
+  f->pre_wait = f->ev_gen;
   // multi-GPU: the caller's columns must already be complete (see bwgpu.h); no ordering with the fold's
   // stream is taken, so that this activation's exchange can overlap the previous activation's fold
   CU(ctx, cudaEventRecord(f->ev_src_ready, f->s_x));
@@ -1529,6 +1541,8 @@ bw_status bw_gen_c1(bw_fold* f, uint64_t* d_keys, uint64_t* d_vals, uint64_t sta
   CU(f->ctx, cudaSetDevice(f->ctx->device));
   k_gen_c1<<<f->ctx->sm_count * 8, 256, 0, f->s_compute>>>(d_keys, d_vals, start, rows, n_keys);
   CU(f->ctx, cudaGetLastError());
+  if (!f->ev_gen) CU(f->ctx, cudaEventCreateWithFlags(&f->ev_gen, cudaEventDisableTiming));
+  CU(f->ctx, cudaEventRecord(f->ev_gen, f->s_compute));
   f->st.kernel_launches++;
   return BW_OK;
 }

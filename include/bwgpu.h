@@ -212,12 +212,16 @@ bw_status bw_ingest_acquire(bw_fold* fold, uint64_t max_rows, bw_batch* out);
  * sequence of epochs (a rank with no data commits rows == 0). */
 bw_status bw_ingest_commit(bw_fold* fold, const bw_batch* batch, uint64_t rows, uint64_t epoch);
 
-/* Same as acquire+commit for columns already resident in device memory
- * (they must stay valid until the next bw_ingest_* / bw_advance / bw_eof
- * call on this fold returns).  When world > 1 the columns must be completely
- * written before the call: the exchange runs on its own stream so that it can
- * overlap the previous activation's fold, and takes no ordering from the
- * fold's stream. */
+/* Same as acquire+commit for columns already resident in device memory.
+ * Lifetime: with world == 1 the fold reads the columns in place, so they must
+ * stay valid and unchanged until bw_fold_sync / bw_advance / bw_eof returns
+ * (or be overwritten only by work enqueued on bw_fold_stream, which is ordered
+ * behind the fold); with world > 1 they are consumed by the exchange before
+ * the call returns.  The columns must be completely written before the call:
+ * the lateness pass (and, when world > 1, the exchange) runs on its own stream
+ * so that it overlaps the previous activation's fold, and takes no ordering
+ * from the fold's stream (columns produced by bw_gen_c1 on this fold are
+ * ordered by the library itself). */
 bw_status bw_ingest_device(bw_fold* fold, const uint64_t* d_keys, const void* d_vals,
                            const int64_t* d_ts_us, uint64_t rows, uint64_t epoch);
 
