@@ -273,8 +273,8 @@ class _GpuFinalStep(_GpuWindowStep):
 class _InputPart:
     __slots__ = ("part", "worker", "epoch", "started", "eof", "awake_at")
 
-    def __init__(self, part, worker):
-        self.part, self.worker, self.epoch, self.started, self.eof, self.awake_at = part, worker, 1, time.monotonic(), False, None
+    def __init__(self, part, worker, started):
+        self.part, self.worker, self.epoch, self.started, self.eof, self.awake_at = part, worker, 1, started, False, None
 
 
 class _Run:
@@ -285,9 +285,9 @@ class _Run:
         self.steps = _core_steps(flow)
         names = [type(s).__name__ for s in self.steps]
         if "input" not in names:
-            raise ValueError("Dataflow needs to contain at least one input step; add with `bytewax.operators.input`")
+            _reraise("error building Dataflow", ValueError("Dataflow needs to contain at least one input step; add with `bytewax.operators.input`"))
         if "output" not in names and "inspect_debug" not in names:
-            raise ValueError("Dataflow needs to contain at least one output or inspect step; add with `bytewax.operators.output` or `bytewax.operators.inspect`")
+            _reraise("error building Dataflow", ValueError("Dataflow needs to contain at least one output or inspect step; add with `bytewax.operators.output` or `bytewax.operators.inspect`"))
         seen = set()
         for st in self.steps:
             for name in st.dwn_names:
@@ -324,10 +324,10 @@ class _Run:
             try:
                 if isinstance(src, FixedPartitionedSource):
                     for i, name in enumerate(src.list_parts()):
-                        parts.append(_InputPart(src.build_part(st.step_id, name, None), i % self.W))
+                        parts.append(_InputPart(src.build_part(st.step_id, name, None), i % self.W, now_mono))
                 elif isinstance(src, DynamicSource):
                     for w in range(self.W):
-                        parts.append(_InputPart(src.build(st.step_id, w, self.W), w))
+                        parts.append(_InputPart(src.build(st.step_id, w, self.W), w, now_mono))
                 else:
                     raise TypeError("unknown source type; must subclass `FixedPartitionedSource` or `DynamicSource`")
             except Exception as ex:
@@ -487,21 +487,31 @@ class _Run:
                             f"step {st.step_id!r} requires `str` keys in `(key, value)` from upstream; got a {type(key)!r} instead"))
                     routed[_route(key, self.W)][epoch].append(item)
         now = datetime.now(timezone.utc)
+        last_out = S.setdefault("last_out", [0] * self.W)
         for w in range(self.W):
             g = S["gpu"][w]
+            # Epochs of this activation, in order; the epoch of the previous activation is walked again (without items) so
+            # that notifications which came due since then fire BEFORE this activation's new items, as the reference does by
+            # re-inserting `last_output_epoch` into `process_epochs` (src/operators.rs:698-707, notify phase :808-858).
+            epochs = sorted(set(routed[w]) | ({last_out[w]} if last_out[w] else set()))
             last_epoch = 0
-            for epoch in sorted(routed[w]):
+            for epoch in epochs:
                 last_epoch = epoch
-                items = routed[w][epoch]
+                items = routed[w].get(epoch)
                 if g is not None:
-                    try:
-                        self._emit(st.down, w, epoch, g.on_epoch(epoch, items))
-                    except Exception as ex:
-                        _reraise(f"error in the CUDA fold of step {st.step_id}", ex)
+                    if items:
+                        try:
+                            self._emit(st.down, w, epoch, g.on_epoch(epoch, items))
+                        except Exception as ex:
+                            _reraise(f"error in the CUDA fold of step {st.step_id}", ex)
                     continue
-                self._host_on_batch(st, S, w, epoch, items)
-            if g is None:
+                if items:
+                    self._host_on_batch(st, S, w, epoch, items)
+                self._host_notify(st, S, w, epoch, now)
+            if g is None and not epochs:
                 self._host_notify(st, S, w, last_epoch, now)
+            if last_epoch:
+                last_out[w] = last_epoch
             if eof and not S["eof_done"]:
                 ep = last_epoch or max((ip.epoch for parts in self.inputs.values() for ip in parts), default=1)
                 if g is not None:

@@ -10,6 +10,7 @@ Python objects.
 from __future__ import annotations
 
 import asyncio
+import queue
 from abc import ABC, abstractmethod
 from dataclasses import dataclass
 from datetime import datetime, timedelta, timezone
@@ -66,16 +67,20 @@ class DynamicSource(Source[X]):
     def build(self, step_id: str, worker_index: int, worker_count: int) -> StatelessSourcePartition[X]: ...
 
 
-class _SimplePollingPartition(StatefulSourcePartition):
-    def __init__(self, now: datetime, interval: timedelta, align_to: Optional[datetime], getter: Callable[[], Any]):
-        self._interval, self._getter = interval, getter
+Sn = TypeVar("Sn")
+
+
+class _SimplePollingPartition(StatefulSourcePartition[X, S]):
+    """inputs.py:285-331: one getter call per awake time; the awake times sit on the ``align_to`` grid."""
+
+    def __init__(self, now: datetime, interval: timedelta, align_to: Optional[datetime], getter: Callable[[], Any],
+                 snapshot: Callable[[], Any] = lambda: None):
+        self._interval, self._getter, self._snapshot = interval, getter, snapshot
+        self._next_awake = now
         if align_to is not None:
-            if align_to > now:
-                raise ValueError("`align_to` must be in the past")
-            # next tick on the align_to grid
-            self._next_awake = align_to + ((now - align_to) // interval + 1) * interval
-        else:
-            self._next_awake = now
+            past_tick = (now - align_to) % interval
+            if past_tick > timedelta(0):  # exactly on a tick: poll right away, not a whole interval later
+                self._next_awake = now + (interval - past_tick)
 
     def next_batch(self):
         try:
@@ -90,10 +95,10 @@ class _SimplePollingPartition(StatefulSourcePartition):
         return self._next_awake
 
     def snapshot(self):
-        return None
+        return self._snapshot()
 
 
-class SimplePollingSource(FixedPartitionedSource):
+class SimplePollingSource(FixedPartitionedSource[X, Sn]):
     """Call ``next_item`` every ``interval`` on one worker (inputs.py:333-452)."""
 
     @dataclass
@@ -108,10 +113,20 @@ class SimplePollingSource(FixedPartitionedSource):
 
     def build_part(self, step_id, for_part, resume_state):
         now = datetime.now(timezone.utc)
-        return _SimplePollingPartition(now, self._interval, self._align_to, self.next_item)
+        if resume_state is not None:
+            self.resume(resume_state)
+        return _SimplePollingPartition(now, self._interval, self._align_to, self.next_item, self.snapshot)
 
     @abstractmethod
     def next_item(self): ...
+
+    def snapshot(self):
+        """Position of the next read, handed back to ``resume`` (inputs.py:417-431)."""
+        return None
+
+    def resume(self, resume_state) -> None:
+        """Called once before ``next_item`` when resuming (inputs.py:433-441)."""
+        return None
 
 
 def batch(ib: Iterable[X], batch_size: int) -> Iterator[List[X]]:
@@ -125,27 +140,43 @@ def batch(ib: Iterable[X], batch_size: int) -> Iterator[List[X]]:
 
 
 def batch_getter(getter: Callable[[], X], batch_size: int, yield_on: Optional[X] = None) -> Iterator[List[X]]:
-    """inputs.py:477."""
+    """Batch from a getter that returns ``yield_on`` when nothing is ready and raises ``StopIteration`` at EOF
+    (inputs.py:477): a partial batch is handed out first, then the generator ends."""
     while True:
-        chunk = []
+        chunk, eof = [], False
         while len(chunk) < batch_size:
-            item = getter()
+            try:
+                item = getter()
+            except StopIteration:
+                eof = True
+                break
             if item == yield_on:
                 break
             chunk.append(item)
+        if eof and not chunk:
+            return
         yield chunk
+        if eof:
+            return
 
 
-def batch_getter_ex(getter: Callable[[], X], batch_size: int, yield_ex=Exception) -> Iterator[List[X]]:
-    """inputs.py:512."""
+def batch_getter_ex(getter: Callable[[], X], batch_size: int, yield_ex=queue.Empty) -> Iterator[List[X]]:
+    """Same for a getter that raises ``yield_ex`` (default ``queue.Empty``) when nothing is ready (inputs.py:512)."""
     while True:
-        chunk = []
+        chunk, eof = [], False
         while len(chunk) < batch_size:
             try:
                 chunk.append(getter())
             except yield_ex:
                 break
+            except StopIteration:
+                eof = True
+                break
+        if eof and not chunk:
+            return
         yield chunk
+        if eof:
+            return
 
 
 def batch_async(aib, timeout: timedelta, batch_size: int, loop=None) -> Iterator[List[X]]:

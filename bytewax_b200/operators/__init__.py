@@ -228,8 +228,8 @@ def inspect(step_id: str, up: Stream, inspector: Callable[[str, Any], None] = No
         def inspector(step, item):
             print(f"{step}: {item!r}", flush=True)
 
-    def shim_inspector(step, item, _epoch, _worker):
-        inspector(step, item)
+    def shim_inspector(_fq_step_id, item, _epoch, _worker):
+        inspector(step_id, item)  # this step's own id, not the inner inspect_debug's (operators/__init__.py:2064-2067)
 
     return inspect_debug("inspect_debug", up, shim_inspector)
 

@@ -136,3 +136,31 @@ def poll_next_batch(part, timeout=timedelta(seconds=5)):
             raise TimeoutError()
         batch = part.next_batch()
     return batch
+
+
+def _main(argv=None) -> None:
+    """``python -m bytewax_b200.testing <import_str> -p P -w W``: the reference's local test cluster
+    (pysrc/bytewax/testing.py ``__main__``: P processes x W workers over localhost TCP).  Here the P x W workers are
+    logical workers of this one process -- state is sharded by key the same way, no sockets."""
+    import argparse
+
+    from bytewax_b200.run import _locate_dataflow, _parse_timedelta, _prepare_import
+
+    p = argparse.ArgumentParser(prog="python -m bytewax_b200.testing", description="Test a dataflow on a local cluster")
+    p.add_argument("import_str", type=str)
+    p.add_argument("-w", "--workers-per-process", type=int, default=1)
+    p.add_argument("-p", "--processes", type=int, default=1)
+    p.add_argument("-s", "--snapshot-interval", type=_parse_timedelta, default=None)
+    p.add_argument("-b", "--backup-interval", type=_parse_timedelta, default=None)
+    p.add_argument("-r", "--recovery-directory", default=None)
+    args = p.parse_args(argv)
+    if args.recovery_directory is not None:
+        raise NotImplementedError("recovery is out of scope of this engine (SURVEY.md section 2 row 12)")
+    mod_str, _, attr_str = _prepare_import(args.import_str).partition(":")
+    flow = _locate_dataflow(mod_str, attr_str)
+    cluster_main(flow, [], 0, epoch_interval=args.snapshot_interval,
+                 worker_count_per_proc=max(1, args.processes) * max(1, args.workers_per_process))
+
+
+if __name__ == "__main__":
+    _main()

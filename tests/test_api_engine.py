@@ -84,11 +84,13 @@ def test_inspect_debug_epoch_and_worker():
 def test_needs_input_and_output():
     # pytests/test_inputs.py:30-36, test_outputs.py:9-18
     flow = Dataflow("df")
-    with pytest.raises(ValueError, match="at least one input"):
+    with pytest.raises(RuntimeError) as e:  # BytewaxRuntimeError chained to the ValueError (pytests/test_inputs.py:30-36)
         run_main(flow)
+    assert isinstance(e.value.__cause__, ValueError) and "at least one input" in str(e.value.__cause__)
     op.input("inp", flow, TestingSource([1]))
-    with pytest.raises(ValueError, match="at least one output"):
+    with pytest.raises(RuntimeError) as e2:  # pytests/test_outputs.py:8-18
         run_main(flow)
+    assert isinstance(e2.value.__cause__, ValueError) and "at least one output" in str(e2.value.__cause__)
 
 
 def test_user_exception_is_chained():
