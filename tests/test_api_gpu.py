@@ -156,3 +156,32 @@ def test_final_fold_large_against_numpy():
         assert set(em.closed_window_id.tolist()) == {0}
         fold.close()
     ctx.close()
+
+
+def test_max_min_window_numeric_on_gpu():
+    # the shape of pytests/operators/windowing/test_max_min_window.py:14-67 with numeric values (the recogniser's domain):
+    # values 1, 9, 3 in window 0 and 10, 4 in window 1
+    class N(int):
+        pass
+
+    def num(val, sec):
+        x = N(val)
+        x.ts = ALIGN + timedelta(seconds=sec)
+        return x
+
+    inp = [("a", num(1, 0)), ("a", num(9, 4)), ("a", num(3, 8)), ("a", num(10, 12)), ("a", num(4, 13))]
+
+    def build():
+        outs = [[], []]
+        flow = Dataflow("test_df")
+        s = op.input("inp", flow, TestingSource(inp))
+        clock = EventClock(lambda v: v.ts, ZERO_TD, now_getter=lambda: FROZEN)
+        windower = TumblingWindower(timedelta(seconds=10), ALIGN)
+        op.output("o0", win.max_window("max", s, clock, windower).down, TestingSink(outs[0]))
+        op.output("o1", win.min_window("min", s, clock, windower).down, TestingSink(outs[1]))
+        return flow, outs
+
+    host, gpu = _both(build)
+    assert [(k, (w, int(v))) for k, (w, v) in gpu[0]] == [("a", (0, 9)), ("a", (1, 10))]
+    assert [(k, (w, int(v))) for k, (w, v) in gpu[1]] == [("a", (0, 1)), ("a", (1, 4))]
+    assert [[(k, (w, int(v))) for k, (w, v) in o] for o in host] == [[(k, (w, int(v))) for k, (w, v) in o] for o in gpu]
