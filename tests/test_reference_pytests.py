@@ -39,5 +39,5 @@ def test_reference_operator_tests_pass_unmodified():
 
 def test_reference_dataflow_io_and_execution_tests_pass_unmodified():
     # pytests/test_dataflow.py, test_inputs.py, test_outputs.py, test_testing.py, test_execution.py (incl. the ctrl-c
-    # sub-process tests through `python -m bytewax.run` / `python -m bytewax.testing`), connectors/test_demo.py
-    _run(["test_dataflow.py", "test_inputs.py", "test_outputs.py", "test_testing.py", "test_execution.py", "connectors/test_demo.py"], 43)
+    # sub-process tests through `python -m bytewax.run` / `python -m bytewax.testing`), connectors/test_demo.py, connectors/test_files.py
+    _run(["test_dataflow.py", "test_inputs.py", "test_outputs.py", "test_testing.py", "test_execution.py", "connectors/test_demo.py", "connectors/test_files.py"], 53)
