@@ -41,3 +41,20 @@ def test_reference_dataflow_io_and_execution_tests_pass_unmodified():
     # pytests/test_dataflow.py, test_inputs.py, test_outputs.py, test_testing.py, test_execution.py (incl. the ctrl-c
     # sub-process tests through `python -m bytewax.run` / `python -m bytewax.testing`), connectors/test_demo.py, connectors/test_files.py
     _run(["test_dataflow.py", "test_inputs.py", "test_outputs.py", "test_testing.py", "test_execution.py", "connectors/test_demo.py", "connectors/test_files.py"], 53)
+
+
+def test_reference_wordcount_example_runs_unmodified():
+    """Config C0 (BASELINE.json configs[0]): the reference's own `examples/wordcount.py`, as it is, through
+    `python -m bytewax.run` on one CPU worker; stdout must be the word counts in ascending word order
+    (EOF emission order of `count_final`, pytests/operators/test_count_final.py:16)."""
+    import collections
+
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "compat"), ROOT]))
+    r = subprocess.run([sys.executable, "-m", "bytewax.run", "examples.wordcount:flow"], capture_output=True, text=True,
+                       timeout=120, cwd=REF, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    # independent restatement of the example's pipeline: lower-case, split on the example's token pattern, count, sort
+    text = open(os.path.join(REF, "examples", "sample_data", "wordcount.txt")).read()
+    words = [w for line in text.splitlines() for w in re.findall(r'[^\s!,.?":;0-9]+', line.lower())]
+    want = [repr(kv) for kv in sorted(collections.Counter(words).items())]
+    assert r.stdout.splitlines() == want
