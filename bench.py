@@ -56,8 +56,34 @@ class ClockSampler:
 
     def __init__(self, device=0):
         self.device, self.proc, self.lines = device, None, []
+        self.nvml_samples, self._stop = [], threading.Event()
+
+    def _nvml_loop(self):
+        """NVML polled every ~2 ms beside nvidia-smi's 100 ms loop: the timed region is only tens of milliseconds long."""
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.device)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            bits = (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40), ("sw_power_cap", 0x4))
+            while not self._stop.is_set():
+                try:
+                    sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    self.nvml_samples.append((float(sm), float(mx), [n for n, b in bits if r & b]))
+                except Exception:
+                    pass
+                time.sleep(0.002)
+        except Exception:
+            return
 
     def start(self):
+        try:
+            self.tn = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.tn.start()
+        except Exception:
+            pass
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.device)],
@@ -72,14 +98,20 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
-        if not self.proc:
+        self._stop.set()
+        if not self.proc and not self.nvml_samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
         sm, mx, reasons = [], [], set()
+        for c, m, rs in self.nvml_samples:
+            sm.append(c)
+            mx.append(m)
+            reasons.update(rs)
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
