@@ -74,8 +74,13 @@ def input(step_id: str, flow: Dataflow, source) -> Stream:  # noqa: A001
     return Stream(f"{step_id}.down", flow._scope)
 
 
+def _default_debug_inspector(step_id: str, item: Any, epoch: int, worker: int) -> None:
+    """What ``inspect_debug`` prints when no inspector is given (operators/__init__.py:292-293)."""
+    print(f"{step_id} W{worker} @{epoch}: {item!r}", flush=True)
+
+
 @operator(_core=True)
-def inspect_debug(step_id: str, up: Stream, inspector: Callable[[str, Any, int, int], None] = None) -> Stream:
+def inspect_debug(step_id: str, up: Stream, inspector: Callable[[str, Any, int, int], None] = _default_debug_inspector) -> Stream:
     """``inspector(step_id, item, epoch, worker)`` per item (operators/__init__.py:296; src/operators.rs:242-317)."""
     return Stream(f"{step_id}.down", up._scope)
 

@@ -1,0 +1,69 @@
+"""Run the `{testcode}` / `{testoutput}` examples of the reference's operator docstrings against this package.
+
+The reference documents every operator with a runnable example and its expected stdout (Sphinx doctest blocks in
+pysrc/bytewax/operators/__init__.py and windowing.py).  This extracts them from the reference tree in place, runs each
+example with `bytewax` aliased to `bytewax_b200`, and compares stdout.  Build container only.
+
+    python tools/ref_doctests.py            # summary; exit code 1 if any example differs
+"""
+import ast
+import contextlib
+import io
+import os
+import re
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference/pysrc/bytewax"
+sys.path.insert(0, os.path.join(ROOT, "compat"))
+sys.path.insert(0, ROOT)
+
+BLOCK = re.compile(r"```\{(testcode|testoutput)\}\n(.*?)```", re.S)
+
+
+def examples(path):
+    """(qualified name, code, expected stdout) for every docstring that has at least one testoutput block."""
+    tree = ast.parse(open(path).read())
+    for node in ast.walk(tree):
+        if not isinstance(node, (ast.FunctionDef, ast.ClassDef, ast.Module)):
+            continue
+        doc = ast.get_docstring(node, clean=True)
+        if not doc or "{testoutput}" not in doc:
+            continue
+        code, want = [], []
+        for kind, body in BLOCK.findall(doc):
+            body = "\n".join(ln for ln in body.split("\n") if not ln.strip().startswith(":hide:"))
+            (code if kind == "testcode" else want).append(body)
+        yield getattr(node, "name", "<module>"), "\n".join(code), "\n".join(want)
+
+
+def norm(s):
+    return [ln.rstrip() for ln in s.strip().split("\n") if ln.strip()]
+
+
+def main():
+    ok, bad = 0, []
+    for rel in ("operators/__init__.py", "operators/windowing.py", "operators/helpers.py", "dataflow.py", "inputs.py", "testing.py"):
+        path = os.path.join(REF, rel)
+        if not os.path.exists(path):
+            continue
+        for name, code, want in examples(path):
+            buf = io.StringIO()
+            try:
+                with contextlib.redirect_stdout(buf):
+                    exec(compile(code, f"<{rel}:{name}>", "exec"), {"__name__": "__doctest__"})
+                got = buf.getvalue()
+                if norm(got) == norm(want):
+                    ok += 1
+                else:
+                    bad.append((rel, name, "stdout differs", norm(got)[:6], norm(want)[:6]))
+            except Exception as ex:  # noqa: BLE001
+                bad.append((rel, name, f"{type(ex).__name__}: {ex}"[:200], [], []))
+    print(f"{ok} docstring examples reproduce the documented output; {len(bad)} do not")
+    for b in bad:
+        print("  ", b)
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
