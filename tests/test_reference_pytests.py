@@ -66,8 +66,11 @@ def test_reference_wordcount_example_runs_unmodified():
 def test_reference_docstring_examples_reproduce_documented_output():
     """Every `{testcode}` / `{testoutput}` example in the reference's operator docstrings (33 of them: one per operator,
     SURVEY 8c "docstring doctests of every operator"), run against this package, prints the documented output."""
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ref_doctests.py")], capture_output=True, text=True,
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ref_doctests.py"), "--guides"], capture_output=True, text=True,
                        timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
     m = re.search(r"(\d+) docstring examples reproduce the documented output; 0 do not", r.stdout)
     assert m and int(m.group(1)) >= 30, r.stdout[-2000:]
+    # and the user guide's pages (joins, dataflow programming, the wordcount / windowing / join / simple walk-throughs)
+    g = re.search(r"(\d+) guide-page examples reproduce the documented output; 0 do not", r.stdout)
+    assert g and int(g.group(1)) >= 30, r.stdout[-2000:]

@@ -37,6 +37,45 @@ def examples(path):
         yield getattr(node, "name", "<module>"), "\n".join(code), "\n".join(want)
 
 
+def md_examples(path):
+    """A guide page is one running session: code blocks accumulate; each testoutput block checks the stdout produced since
+    the previous one."""
+    text = open(path).read()
+    code = []
+    for kind, body in BLOCK.findall(text):
+        body = "\n".join(ln for ln in body.split("\n") if not ln.strip().startswith(":hide:"))
+        if kind == "testcode":
+            code.append(body)
+        else:
+            yield "\n".join(code), body
+            code = []
+
+
+def run_guides(names):
+    """(ok, bad) over the guide pages: every page runs in one namespace, cwd = docs/fixtures (pages read sample files)."""
+    ok, bad = 0, []
+    docs = "/root/reference/docs/guide"
+    cwd = os.getcwd()
+    os.chdir("/root/reference/docs/fixtures")  # the pages' doctests run beside their fixture files
+    try:
+        for rel in names:
+            ns = {"__name__": "__doctest__"}
+            for i, (code, want) in enumerate(md_examples(os.path.join(docs, rel))):
+                buf = io.StringIO()
+                try:
+                    with contextlib.redirect_stdout(buf):
+                        exec(compile(code, f"<{rel}#{i}>", "exec"), ns)
+                    if norm(buf.getvalue()) == norm(want):
+                        ok += 1
+                    else:
+                        bad.append((rel, i, "stdout differs", norm(buf.getvalue())[:5], norm(want)[:5]))
+                except Exception as ex:  # noqa: BLE001
+                    bad.append((rel, i, f"{type(ex).__name__}: {ex}"[:200], [], []))
+    finally:
+        os.chdir(cwd)
+    return ok, bad
+
+
 def norm(s):
     return [ln.rstrip() for ln in s.strip().split("\n") if ln.strip()]
 
@@ -62,6 +101,14 @@ def main():
     print(f"{ok} docstring examples reproduce the documented output; {len(bad)} do not")
     for b in bad:
         print("  ", b)
+    if "--guides" in sys.argv:
+        gok, gbad = run_guides(["concepts/joins.md", "concepts/dataflow-programming.md", "getting-started/wordcount-example.md",
+                                "getting-started/collecting-windowing-example.md", "getting-started/join-example.md",
+                                "getting-started/simple-example.md"])
+        print(f"{gok} guide-page examples reproduce the documented output; {len(gbad)} do not")
+        for b in gbad:
+            print("  ", b)
+        bad += gbad
     return 1 if bad else 0
 
 
