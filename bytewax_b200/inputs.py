@@ -67,7 +67,12 @@ class DynamicSource(Source[X]):
     def build(self, step_id: str, worker_index: int, worker_count: int) -> StatelessSourcePartition[X]: ...
 
 
-Sn = TypeVar("Sn")
+try:  # a defaulted type variable lets `SimplePollingSource[int]` stand for "no resume state" (inputs.py:43-44)
+    from typing_extensions import TypeVar as _DefaultedTypeVar
+
+    Sn = _DefaultedTypeVar("Sn", default=None)
+except Exception:  # pragma: no cover - typing_extensions too old
+    Sn = TypeVar("Sn")
 
 
 class _SimplePollingPartition(StatefulSourcePartition[X, S]):

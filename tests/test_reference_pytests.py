@@ -74,3 +74,16 @@ def test_reference_docstring_examples_reproduce_documented_output():
     # and the user guide's pages (joins, dataflow programming, the wordcount / windowing / join / simple walk-throughs)
     g = re.search(r"(\d+) guide-page examples reproduce the documented output; 0 do not", r.stdout)
     assert g and int(g.group(1)) >= 30, r.stdout[-2000:]
+
+
+@pytest.mark.parametrize("example", ["wordcount", "basic", "join", "apriori", "csv_input", "partials", "search_session",
+                                     "benchmark_windowing"])
+def test_reference_examples_run_unmodified(example):
+    """The reference's own `examples/<name>.py` (those that need no network or third-party service), as they are, through
+    `python -m bytewax.run`: they load, run to EOF and print."""
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "compat"), ROOT]))
+    r = subprocess.run([sys.executable, "-m", "bytewax.run", f"examples.{example}"], capture_output=True, text=True,
+                       timeout=300, cwd=REF, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    if example != "benchmark_windowing":  # that one ends in a null sink
+        assert r.stdout.strip()
