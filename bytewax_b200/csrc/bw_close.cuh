@@ -80,7 +80,7 @@ struct PaneRec {
 // the two direct panes.  Same result as the general routine below without its 64-entry
 // per-thread scratch (which lives in local memory and dominated K4: 0.26 ms for 250 k keys).
 __device__ __forceinline__ bool bw_close_key_simple(const Table& t, const FoldParams& p, const EmitBufs& e, u64 s, bool eof,
-                                                    u64 epoch) {
+                                                    u64 epoch, u32 close_batch) {
   if (!(p.panes_per_offset == 1 && p.panes_per_window == 1)) return false;
   AuxSlot* ax = t.aux + s;
   if (ax->spill_head != 0) return false;
@@ -104,11 +104,10 @@ __device__ __forceinline__ bool bw_close_key_simple(const Table& t, const FoldPa
   const bool has1 = seq1 != ~0ULL;
   const bool dead0 = wm >= bw_pane_release(q0, p);
   const bool dead1 = has1 && wm >= bw_pane_release(q1, p);
-  const bool ordered_seq = p.ordered != 0;
-  if (dead0)
-    bw_emit_closed(e, t.ctr, key, q0, bw_finish_acc(p, acc0), cnt0, ordered_seq ? (u64)(q0 + (1LL << 62)) : seq0, epoch);
-  if (dead1)
-    bw_emit_closed(e, t.ctr, key, q1, bw_finish_acc(p, acc1), cnt1, ordered_seq ? (u64)(q1 + (1LL << 62)) : seq1, epoch);
+  // seq_by_id: rows of one key are ordered by (closing activation, window id); the id pass is order_rows'
+  const bool ordered_seq = p.seq_by_id != 0;
+  if (dead0) bw_emit_closed(e, t.ctr, key, q0, bw_finish_acc(p, acc0), cnt0, ordered_seq ? (u64)close_batch : seq0, epoch);
+  if (dead1) bw_emit_closed(e, t.ctr, key, q1, bw_finish_acc(p, acc1), cnt1, ordered_seq ? (u64)close_batch : seq1, epoch);
   const bool alive0 = !dead0, alive1 = has1 && !dead1;
   bool keep1 = false;  // pane 1 keeps a survivor (as "the pane before pane 0")
   if (!alive0 && !alive1) {
@@ -123,7 +122,7 @@ __device__ __forceinline__ bool bw_close_key_simple(const Table& t, const FoldPa
     const bool newest_is_1 = alive1 && (!alive0 || q1 > q0);
     const bool both = alive0 && alive1;  // |q1 - q0| == 1: the older one is exactly "newest - 1"
     const i64 rq = newest_is_1 ? q1 : q0;
-    hs->wt0 = bw_pack_widtag(rq, both ? 1u : 0u, BW_TAG_STALE, both);
+    hs->wt0 = bw_pack_widtag(rq, both ? 1u : 0u, BW_TAG_STALE, both, both);
     hs->acc0 = newest_is_1 ? acc1 : acc0;
     ax->cnt0 = newest_is_1 ? cnt1 : cnt0;
     ax->seq0 = newest_is_1 ? seq1 : seq0;
@@ -146,8 +145,8 @@ __device__ __forceinline__ bool bw_close_key_simple(const Table& t, const FoldPa
 // the hot slot; pane 1 becomes the pane right before it when that one is still
 // alive (P1_PREV), else it is left empty for the pane right after it; the
 // rest goes on the list.
-__device__ void bw_close_key(const Table& t, const FoldParams& p, const EmitBufs& e, u64 s, bool eof, u64 epoch) {
-  if (bw_close_key_simple(t, p, e, s, eof, epoch)) return;
+__device__ void bw_close_key(const Table& t, const FoldParams& p, const EmitBufs& e, u64 s, bool eof, u64 epoch, u32 close_batch) {
+  if (bw_close_key_simple(t, p, e, s, eof, epoch, close_batch)) return;
   HotSlot* hs = t.hot + s;
   P1Slot* ps = t.p1 + s;
   AuxSlot* ax = t.aux + s;
@@ -177,13 +176,12 @@ __device__ void bw_close_key(const Table& t, const FoldParams& p, const EmitBufs
     P[n++] = PaneRec{t.nodes[nd].wid, t.nodes[nd].acc, t.node_acc2[nd], t.nodes[nd].open_seq, BW_TAG_STALE, false};
   }
   const i64 a = p.panes_per_offset, b = p.panes_per_window;
-  const bool ordered_seq = p.ordered != 0;
+  const bool ordered_seq = p.seq_by_id != 0;
   if (a == 1 && b == 1) {
     // tumbling: window id == pane id; a closed pane is emitted and dropped
     for (int i = 0; i < n; ++i)
       if (wm >= bw_pane_release(P[i].q, p)) {
-        bw_emit_closed(e, t.ctr, key, P[i].q, bw_finish_acc(p, P[i].acc), P[i].cnt,
-                       ordered_seq ? (u64)(P[i].q + (1LL << 62)) : P[i].seq, epoch);
+        bw_emit_closed(e, t.ctr, key, P[i].q, bw_finish_acc(p, P[i].acc), P[i].cnt, ordered_seq ? (u64)close_batch : P[i].seq, epoch);
         P[i].dead = true;
       }
   } else {
@@ -215,8 +213,7 @@ __device__ void bw_close_key(const Table& t, const FoldParams& p, const EmitBufs
             seq = P[j].seq < seq ? P[j].seq : seq;
           }
           if (smallest)
-            bw_emit_closed(e, t.ctr, key, w, bw_finish_acc(p, acc), cnt, ordered_seq ? (u64)(w + (1LL << 62)) : seq,
-                           epoch);
+            bw_emit_closed(e, t.ctr, key, w, bw_finish_acc(p, acc), cnt, ordered_seq ? (u64)close_batch : seq, epoch);
         }
       }
       t.closed_upto[s] = c_new;
@@ -256,7 +253,7 @@ __device__ void bw_close_key(const Table& t, const FoldParams& p, const EmitBufs
     const i64 dq = r0.q - w_first * a;
     const u64 delta = dq < 0 ? 0 : (u64)dq;
     // K4 runs after the batch that created a pane, so its open_seq is final: mark stale
-    hs->wt0 = bw_pack_widtag(r0.q, delta > BW_TAG_DELTA_MAX ? BW_TAG_DELTA_MAX : (u32)delta, BW_TAG_STALE, prev);
+    hs->wt0 = bw_pack_widtag(r0.q, delta > BW_TAG_DELTA_MAX ? BW_TAG_DELTA_MAX : (u32)delta, BW_TAG_STALE, prev, prev, m > (prev ? 2 : 1));
     hs->acc0 = r0.acc;
     ax->cnt0 = r0.cnt;
     ax->seq0 = r0.seq;
@@ -307,17 +304,17 @@ __device__ void bw_close_key(const Table& t, const FoldParams& p, const EmitBufs
   }
 }
 
-__global__ void k_close_dirty(Table t, FoldParams p, EmitBufs e, u64 epoch) {
+__global__ void k_close_dirty(Table t, FoldParams p, EmitBufs e, u64 epoch, u32 close_batch) {
   const u32 n = t.ctr->dirty_count;
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    bw_close_key(t, p, e, t.dirty[i], false, epoch);
+    bw_close_key(t, p, e, t.dirty[i], false, epoch, close_batch);
 }
 // EOF: every slot (including the BW_EMPTY_KEY alias slot at index capacity)
-__global__ void k_close_all(Table t, FoldParams p, EmitBufs e, u64 epoch) {
+__global__ void k_close_all(Table t, FoldParams p, EmitBufs e, u64 epoch, u32 close_batch) {
   const u64 n = t.cap + 1;
   for (u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += (u64)gridDim.x * blockDim.x) {
     if (s < t.cap && t.hot[s].key == BW_EMPTY_KEY) continue;
-    bw_close_key(t, p, e, s, true, epoch);
+    bw_close_key(t, p, e, s, true, epoch, close_batch);
   }
 }
 __global__ void k_reset_dirty(Table t) { t.ctr->dirty_count = 0; }

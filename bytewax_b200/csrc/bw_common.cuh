@@ -40,7 +40,7 @@ __host__ __device__ __forceinline__ u32 bw_route_hash(u64 h, u32 world) {
 struct __align__(32) HotSlot {
   u64 key;      // BW_EMPTY_KEY when free
   i64 max_ts;   // max event ts seen since the key was (re)created; INT64_MIN when none
-  i64 wt0;      // pane 0 (newest after K4): pane_id << 16 | p1_prev << 15 | delta << 8 | dirty << 7 | stale << 6 | born & 63
+  i64 wt0;      // pane 0 (newest after K4): pane_id << 18 | has_list << 17 | has_p1 << 16 | p1_prev << 15 | delta << 8 | dirty << 7 | stale << 6 | born & 63
   u64 acc0;     // pane 0 accumulator (bits)
 };
 // Pane 1 is implicit: the pane right after pane 0 (the one an in-order key moves
@@ -68,17 +68,24 @@ struct __align__(32) PaneNode {
 #define BW_UTC_MIN_US_DEV (-62135596800000000LL)
 #define BW_EMPTY_KEY 0xFFFFFFFFFFFFFFFFULL
 #define BW_EMPTY_WIDTAG INT64_MIN
-#define BW_WID_SHIFT 16
-#define BW_WID_LIMIT (1LL << 46)  // |pane id| must stay below this
+#define BW_WID_SHIFT 18
+#define BW_WID_LIMIT (1LL << 44)  // |pane id| must stay below this
 #define BW_TAG_DIRTY 0x80LL
 #define BW_TAG_BORN_MASK 0x7FLL  // bits 5:0 = creating batch & 63, bit 6 = "not fresh" (set by K4)
 #define BW_TAG_STALE 0x40u
 #define BW_TAG_DELTA_SHIFT 8
 #define BW_TAG_DELTA_MAX 127u     // 7 bits; the maximum means "always re-examine"
 #define BW_TAG_P1_PREV 0x8000LL   // pane 1 is pane0 - 1 (else pane0 + 1)
+// What the key holds beyond the hot slot, so that a pass that owns the slot (bw_stream.cuh) knows
+// without touching the other arrays: HAS_P1 == the P1 slot is present (seq1 != ~0), HAS_LIST ==
+// the overflow list is not empty.  Set by whoever creates them, recomputed by K4.
+#define BW_TAG_HAS_P1 0x10000LL
+#define BW_TAG_HAS_LIST 0x20000LL
 
-__host__ __device__ __forceinline__ i64 bw_pack_widtag(i64 q, u32 delta, u32 born, bool p1_prev = false) {
-  return (i64)((u64)q << BW_WID_SHIFT) | (p1_prev ? BW_TAG_P1_PREV : 0LL) |
+__host__ __device__ __forceinline__ i64 bw_pack_widtag(i64 q, u32 delta, u32 born, bool p1_prev = false, bool has_p1 = false,
+                                                       bool has_list = false) {
+  return (i64)((u64)q << BW_WID_SHIFT) | (p1_prev ? BW_TAG_P1_PREV : 0LL) | (has_p1 ? BW_TAG_HAS_P1 : 0LL) |
+         (has_list ? BW_TAG_HAS_LIST : 0LL) |
          ((i64)(delta > BW_TAG_DELTA_MAX ? BW_TAG_DELTA_MAX : delta) << BW_TAG_DELTA_SHIFT) | (i64)(born & 0x7Fu);
 }
 __host__ __device__ __forceinline__ i64 bw_widtag_q1(i64 tag) {
@@ -131,6 +138,8 @@ struct FoldParams {
   int track_wm;          // 0 when wait == forever (nothing is ever late or closed before EOF)
   int ordered;
   int need_count;        // maintain acc2 (MEAN)
+  int seq_by_id;         // first-opened order == ascending window id (ordered flush, or wait == 0: a key's accepted
+                         // timestamps never decrease), so emission order needs no arrival sequence
   u64 acc_identity;
 };
 
@@ -143,8 +152,10 @@ struct Table {
   u64* node_acc2;
   u32* free_stack;
   u32* dirty;      // list of slot indices with possibly closable panes
-  u64 cap;         // number of slots (any size); slot `cap` is the BW_EMPTY_KEY alias slot
+  u64 cap;         // number of slots (a multiple of the segment size); slot `cap` is the BW_EMPTY_KEY alias slot
   u32 pool_cap;
+  u32 seg_mask;    // segment size - 1 (power of two): linear probing wraps inside the segment of the home slot,
+                   // so a block that owns a segment owns every key that hashes into it (bw_stream.cuh)
   // device counters
   struct Counters* ctr;
 };
@@ -159,7 +170,7 @@ struct Counters {
   unsigned long long n_late;     // rows in the late emit buffer
   unsigned long long gmax_ts;    // i64 bits: max event ts over everything ingested (prepass chain)
   u32 batch_clean;       // verdict of the prepass for the batch in flight
-  u32 pad;
+  u32 n_spill;           // rows in the partial-spill list (bw_stream.cuh)
 };
 
 // home slot = high part of (scrambled hash) * capacity (no power-of-two constraint on the table).

@@ -19,6 +19,7 @@
 // -1 means "read it from FoldParams at run time" (exact slow path).
 template <int OP_, int WM_, int CNT_>
 struct FoldCfg {
+  static constexpr int kOp = OP_, kWm = WM_, kCnt = CNT_;
   __device__ __forceinline__ static int op(const FoldParams& p) { return OP_ >= 0 ? OP_ : p.op; }
   __device__ __forceinline__ static bool wm(const FoldParams& p) { return WM_ >= 0 ? (WM_ != 0) : (p.track_wm != 0); }
   __device__ __forceinline__ static bool cnt(const FoldParams& p) { return CNT_ >= 0 ? (CNT_ != 0) : (p.need_count != 0); }
@@ -93,6 +94,11 @@ __device__ __forceinline__ i64 bw_ld_i64_coherent(const i64* p) {
 __device__ __forceinline__ u64 bw_home_slot(const Table& t, u64 key) {
   return (key == BW_EMPTY_KEY) ? t.cap : bw_slot_of_hash(bw_mix64(key), t.cap);
 }
+// Linear probing wraps inside the segment of the home slot (Table::seg_mask): slot number `i`
+// positions after `s` in probe order.
+__device__ __forceinline__ u64 bw_probe_next(const Table& t, u64 s, u32 i) {
+  return (s & ~(u64)t.seg_mask) | ((s + i) & (u64)t.seg_mask);
+}
 
 // Find (or create) the slot of `key`, starting at its home slot.  Four
 // consecutive slots are fetched per round trip (independent LDG.256s), so a
@@ -105,17 +111,13 @@ __device__ __forceinline__ u64 bw_find_slot(const Table& t, DirtySink* sk, u64 k
     bw_ld_slot(t.hot + s, k, max_ts, wt0, a);
     return s;
   }
-  for (u64 probe = 0; probe < t.cap;) {
+  for (u64 probe = 0; probe <= (u64)t.seg_mask;) {
     // four independent sector loads, then pick the first slot that holds the key or is free
     // (constant indices only: the probe state stays in registers)
     u64 k[BW_PROBE_WIDTH], a[BW_PROBE_WIDTH];
     i64 m[BW_PROBE_WIDTH], w[BW_PROBE_WIDTH];
 #pragma unroll
-    for (int j = 0; j < BW_PROBE_WIDTH; ++j) {
-      u64 sj = s + j;
-      if (sj >= t.cap) sj -= t.cap;
-      bw_ld_slot(t.hot + sj, k[j], m[j], w[j], a[j]);
-    }
+    for (int j = 0; j < BW_PROBE_WIDTH; ++j) bw_ld_slot(t.hot + bw_probe_next(t, s, j), k[j], m[j], w[j], a[j]);
     int jm = BW_PROBE_WIDTH;
     u64 kk = 0;
     i64 mm = 0, ww = 0;
@@ -129,13 +131,11 @@ __device__ __forceinline__ u64 bw_find_slot(const Table& t, DirtySink* sk, u64 k
       }
     }
     if (jm == BW_PROBE_WIDTH) {
-      s += BW_PROBE_WIDTH;
-      if (s >= t.cap) s -= t.cap;
+      s = bw_probe_next(t, s, BW_PROBE_WIDTH);
       probe += BW_PROBE_WIDTH;
       continue;
     }
-    u64 sj = s + (u64)jm;
-    if (sj >= t.cap) sj -= t.cap;
+    const u64 sj = bw_probe_next(t, s, (u32)jm);
     if (kk == key) {
       max_ts = mm;
       wt0 = ww;
@@ -156,8 +156,7 @@ __device__ __forceinline__ u64 bw_find_slot(const Table& t, DirtySink* sk, u64 k
       return sj;
     }
     // another key took it: resume right after it
-    s = sj + 1;
-    if (s >= t.cap) s -= t.cap;
+    s = bw_probe_next(t, sj, 1);
     probe += (u64)jm + 1;
   }
   return ~0ULL;
@@ -220,6 +219,7 @@ __device__ __noinline__ u32 bw_spill_node(const Table& t, const FoldParams& p, u
           t.node_acc2[n] = 0;
           __threadfence();
           atomicExch(&ax->spill_head, n);
+          if (!head) atomicOr((unsigned long long*)&t.hot[s].wt0, (unsigned long long)BW_TAG_HAS_LIST);
           created = true;
         }
       }
@@ -257,64 +257,19 @@ __device__ __forceinline__ void bw_after_fold(const Table& t, const FoldParams& 
   }
 }
 
-// Shared-memory write-combining of the accumulator updates of one table segment
-// (k_fold_seg).  A block that owns every event whose home slot lies in
-// [slot_base, slot_base + BW_BKT_SLOTS) folds them into shared memory with
-// native 32-bit atomics and merges each touched slot into the table once.
-#define BW_BKT_SHIFT 12
-#define BW_BKT_SLOTS (1u << BW_BKT_SHIFT)
-__device__ __forceinline__ void bw_sm_apply(int op, u64* a, u64 operand) {
-  switch (op) {
-    case BW_OP_ADD_ONE: atomicAdd((u32*)a, 1u); break;  // < 2^32 events per activation
-    case BW_OP_ADD_U64: {
-      // exact 64-bit sum from two 32-bit atomics: each add carries its own overflow up
-      const u32 lo = (u32)operand, hi = (u32)(operand >> 32);
-      const u32 old = atomicAdd((u32*)a, lo);
-      const u32 carry = ((u32)(old + lo) < old) ? 1u : 0u;
-      if (hi | carry) atomicAdd((u32*)a + 1, hi + carry);
-      break;
-    }
-    case BW_OP_ADD_F64: atomicAdd((double*)a, __longlong_as_double((i64)operand)); break;
-    case BW_OP_MIN_S64: atomicMin((long long*)a, (long long)operand); break;
-    case BW_OP_MIN_U64: atomicMin((unsigned long long*)a, (unsigned long long)operand); break;
-    case BW_OP_MAX_S64: atomicMax((long long*)a, (long long)operand); break;
-    default: atomicMax((unsigned long long*)a, (unsigned long long)operand); break;
-  }
-}
 // merge a combined delta into a table accumulator
 __device__ __forceinline__ void bw_merge(int op, u64* acc, u64 d) {
   if (op == BW_OP_ADD_ONE) bw_red_add_u64(acc, d);
   else bw_apply(op, acc, d);
 }
-struct SegSink {
-  u64* acc0;   // [BW_BKT_SLOTS] pane-0 deltas (identity when untouched)
-  u64* acc1;   // [BW_BKT_SLOTS] pane-1 deltas
-  u32* mts;    // [BW_BKT_SLOTS] 1 + (max event ts - base_ts), 0 == untouched
-  u32* seq1;   // [BW_BKT_SLOTS] min arrival index of a pane-1 event, ~0 == none
-  u64 slot_base;
-  i64 base_ts;
-  __device__ __forceinline__ bool owns(u64 s) const { return (s - slot_base) < (u64)BW_BKT_SLOTS; }
-  __device__ __forceinline__ u32 local(u64 s) const { return (u32)(s - slot_base); }
-  __device__ __forceinline__ void fold0(int op, u32 ls, u64 operand) const { bw_sm_apply(op, acc0 + ls, operand); }
-  __device__ __forceinline__ void fold1(int op, u32 ls, u64 operand) const { bw_sm_apply(op, acc1 + ls, operand); }
-  __device__ __forceinline__ void open1(u32 ls, u32 g) const { atomicMin(seq1 + ls, g); }
-  __device__ __forceinline__ void touch(u32 ls, i64 ts) const { atomicMax(mts + ls, (u32)(ts - base_ts) + 1u); }
-};
-struct NoSeg {
-  __device__ __forceinline__ bool owns(u64) const { return false; }
-  __device__ __forceinline__ u32 local(u64) const { return 0u; }
-  __device__ __forceinline__ void fold0(int, u32, u64) const {}
-  __device__ __forceinline__ void fold1(int, u32, u64) const {}
-  __device__ __forceinline__ void open1(u32, u32) const {}
-  __device__ __forceinline__ void touch(u32, i64) const {}
-};
 
 // General path: any event (new key, displaced key, second / further pane).
-// `seq` = (batch_no << 32) | arrival index.  `sg`: updates of slots the calling
-// block owns go to its shared-memory segment (NoSeg: everything goes to the table).
-template <class C, class SG>
+// `seq` = (batch_no << 32) | arrival index.  PARTIAL: the "event" is a pre-combined partial
+// (bw_stream.cuh: a delta of `weight` values whose newest timestamp is `ts`): the operand is
+// merged instead of applied and the value count grows by `weight`.
+template <class C, bool PARTIAL = false>
 __device__ __noinline__ void bw_fold_event(const Table& t, const FoldParams& p, DirtySink* sk, u64 key, i64 ts,
-                                           u64 operand, u64 seq, u32 batch_no, u32 known_slot, const SG sg) {
+                                           u64 operand, u64 seq, u32 batch_no, u32 known_slot, u64 weight = 1ULL) {
   i64 rem;
   const i64 q = bw_pane_of_r(ts, p, rem);
   if (q <= -BW_WID_LIMIT || q >= BW_WID_LIMIT) {
@@ -344,37 +299,28 @@ __device__ __noinline__ void bw_fold_event(const Table& t, const FoldParams& p, 
     i64 old = (i64)atomicCAS((unsigned long long*)&hs->wt0, (unsigned long long)BW_EMPTY_WIDTAG, (unsigned long long)mine);
     tag0 = (old == BW_EMPTY_WIDTAG) ? mine : old;
   }
-  const bool own = sg.owns(s);
-  const u32 ls = sg.local(s);
+  const int op = C::op(p);
   bool created = false;
   if (bw_widtag_q(tag0) == q) {
-    if (own) sg.fold0(C::op(p), ls, operand);
-    else bw_apply(C::op(p), &hs->acc0, operand);
-    if (C::cnt(p)) bw_red_add_u64(&t.aux[s].cnt0, 1ULL);
+    if (PARTIAL) bw_merge(op, &hs->acc0, operand);
+    else bw_apply(op, &hs->acc0, operand);
+    if (C::cnt(p)) bw_red_add_u64(&t.aux[s].cnt0, weight);
     if (((u32)tag0 & 0x7Fu) == born) bw_red_min_u64(&t.aux[s].seq0, seq);
   } else if (bw_widtag_q1(tag0) == q) {
-    if (own) {
-      sg.fold1(C::op(p), ls, operand);
-      if (!(tag0 & BW_TAG_P1_PREV)) sg.open1(ls, (u32)seq);
-    } else {
-      bw_apply(C::op(p), &t.p1[s].acc1, operand);
-      if (!(tag0 & BW_TAG_P1_PREV)) bw_red_min_u64(&t.p1[s].seq1, seq);  // presence + first-open order
-    }
-    if (C::cnt(p)) bw_red_add_u64(&t.aux[s].cnt1, 1ULL);
+    if (PARTIAL) bw_merge(op, &t.p1[s].acc1, operand);
+    else bw_apply(op, &t.p1[s].acc1, operand);
+    if (!(tag0 & BW_TAG_P1_PREV)) bw_red_min_u64(&t.p1[s].seq1, seq);  // presence + first-open order
+    if (!(tag0 & BW_TAG_HAS_P1)) atomicOr((unsigned long long*)&hs->wt0, (unsigned long long)BW_TAG_HAS_P1);
+    if (C::cnt(p)) bw_red_add_u64(&t.aux[s].cnt1, weight);
   } else {
     u32 n = bw_spill_node(t, p, s, q, batch_no, created);
     if (!n) return;
-    bw_apply(C::op(p), &t.nodes[n].acc, operand);
-    if (C::cnt(p)) bw_red_add_u64(&t.node_acc2[n], 1ULL);
+    if (PARTIAL) bw_merge(op, &t.nodes[n].acc, operand);
+    else bw_apply(op, &t.nodes[n].acc, operand);
+    if (C::cnt(p)) bw_red_add_u64(&t.node_acc2[n], weight);
     if (t.nodes[n].born == batch_no) bw_red_min_u64(&t.nodes[n].open_seq, seq);
   }
-  if (own) {
-    // the watermark and the closability test are applied once per slot when the segment is merged
-    sg.touch(ls, ts);
-    if (created && !(tag0 & BW_TAG_DIRTY)) bw_mark_dirty(t, sk, s);
-  } else {
-    bw_after_fold<C>(t, p, sk, s, ts, mts, tag0, created, q, rem);
-  }
+  bw_after_fold<C>(t, p, sk, s, ts, mts, tag0, created, q, rem);
 }
 
 __device__ __forceinline__ void bw_operand(const FoldParams& p, u64 raw, u64& operand);
@@ -390,11 +336,7 @@ __device__ __forceinline__ u32 bw_lookup_slot(const Table& t, u64 key, i64& max_
     u64 k[BW_PROBE_WIDTH], a[BW_PROBE_WIDTH];
     i64 m[BW_PROBE_WIDTH], w[BW_PROBE_WIDTH];
 #pragma unroll
-    for (int j = 0; j < BW_PROBE_WIDTH; ++j) {
-      u64 sj = s + j;
-      if (sj >= t.cap) sj -= t.cap;
-      bw_ld_slot(t.hot + sj, k[j], m[j], w[j], a[j]);
-    }
+    for (int j = 0; j < BW_PROBE_WIDTH; ++j) bw_ld_slot(t.hot + bw_probe_next(t, s, j), k[j], m[j], w[j], a[j]);
     int jm = BW_PROBE_WIDTH;
     u64 kk = 0;
     i64 mm = 0, ww = 0;
@@ -409,24 +351,20 @@ __device__ __forceinline__ u32 bw_lookup_slot(const Table& t, u64 key, i64& max_
     }
     if (jm < BW_PROBE_WIDTH) {
       if (kk != key) return BW_NO_SLOT;
-      u64 sj = s + (u64)jm;
-      if (sj >= t.cap) sj -= t.cap;
       max_ts = mm;
       wt0 = ww;
-      return (u32)sj;
+      return (u32)bw_probe_next(t, s, (u32)jm);
     }
-    s += BW_PROBE_WIDTH;
-    if (s >= t.cap) s -= t.cap;
+    s = bw_probe_next(t, s, BW_PROBE_WIDTH);
   }
   return BW_NO_SLOT;
 }
 
 // The common case, given the slot of a known key and the sector read from it: the event falls in
-// the key's pane 0 or pane 1.  Applies it (to the caller's shared-memory segment when it owns
-// the slot, else to the table) and returns true; returns false for every other case.
-template <class C, class SG>
-__device__ __forceinline__ bool bw_try_fast(const Table& t, const FoldParams& p, DirtySink* sk, const SG& sg, u32 slot,
-                                            i64 tag0, i64 mts, i64 ts, u64 raw, u64 seq, u32 born, PaneCache& pc) {
+// the key's pane 0 or pane 1.  Applies it to the table and returns true; returns false for every other case.
+template <class C>
+__device__ __forceinline__ bool bw_try_fast(const Table& t, const FoldParams& p, DirtySink* sk, u32 slot, i64 tag0, i64 mts,
+                                            i64 ts, u64 raw, u64 seq, u32 born, PaneCache& pc) {
   i64 rem;
   const i64 q = bw_pane_cached(ts, p, rem, pc);
   const bool usable = tag0 != BW_EMPTY_WIDTAG && (q > -BW_WID_LIMIT) && (q < BW_WID_LIMIT);
@@ -435,26 +373,18 @@ __device__ __forceinline__ bool bw_try_fast(const Table& t, const FoldParams& p,
   if (!(hit0 || hit1)) return false;
   u64 operand;
   bw_operand(p, raw, operand);
-  const bool own = sg.owns(slot);
-  const u32 ls = sg.local(slot);
   if (hit0) {
-    if (own) sg.fold0(C::op(p), ls, operand);
-    else bw_apply(C::op(p), &t.hot[slot].acc0, operand);
+    bw_apply(C::op(p), &t.hot[slot].acc0, operand);
     if (C::cnt(p)) bw_red_add_u64(&t.aux[slot].cnt0, 1ULL);
     if (((u32)tag0 & 0x7Fu) == born) bw_red_min_u64(&t.aux[slot].seq0, seq);
   } else {
-    if (own) {
-      sg.fold1(C::op(p), ls, operand);
-      if (!(tag0 & BW_TAG_P1_PREV)) sg.open1(ls, (u32)seq);
-    } else {
-      P1Slot* ps = t.p1 + slot;
-      bw_apply(C::op(p), &ps->acc1, operand);
-      if (!(tag0 & BW_TAG_P1_PREV)) bw_red_min_u64(&ps->seq1, seq);
-    }
+    P1Slot* ps = t.p1 + slot;
+    bw_apply(C::op(p), &ps->acc1, operand);
+    if (!(tag0 & BW_TAG_P1_PREV)) bw_red_min_u64(&ps->seq1, seq);
+    if (!(tag0 & BW_TAG_HAS_P1)) atomicOr((unsigned long long*)&t.hot[slot].wt0, (unsigned long long)BW_TAG_HAS_P1);
     if (C::cnt(p)) bw_red_add_u64(&t.aux[slot].cnt1, 1ULL);
   }
-  if (own) sg.touch(ls, ts);
-  else bw_after_fold<C>(t, p, sk, slot, ts, mts, tag0, false, q, rem);
+  bw_after_fold<C>(t, p, sk, slot, ts, mts, tag0, false, q, rem);
   return true;
 }
 
@@ -601,7 +531,7 @@ k_fold(BatchView bv, Table t, FoldParams p, u32 batch_no, u32 sub_i, u32 sub_n) 
       if (g >= total) continue;
       const i64 ts = bw_event_ts(bv, seg_start, p, g, raw[u]);
       const bool known = (k0[u] == key[u]);
-      if (!(known && bw_try_fast<C, NoSeg>(t, p, &sinks, NoSeg(), slot[u], tag0[u], mts[u], ts, raw[u],
+      if (!(known && bw_try_fast<C>(t, p, &sinks, slot[u], tag0[u], mts[u], ts, raw[u],
                                            ((u64)batch_no << 32) | g, born, pcache))) {
         u32 i = atomicAdd(&sinks.n_defer[warp], 1u);
         sinks.dq_g[warp][i] = (u32)g;
@@ -626,9 +556,9 @@ k_fold(BatchView bv, Table t, FoldParams p, u32 batch_no, u32 sub_i, u32 sub_n) 
       if (ks == BW_NO_SLOT) {
         i64 m2, w2;
         ks = bw_lookup_slot(t, kk, m2, w2);
-        if (ks != BW_NO_SLOT && bw_try_fast<C, NoSeg>(t, p, &sinks, NoSeg(), ks, w2, m2, ts, rw, seq, born, pcache)) continue;
+        if (ks != BW_NO_SLOT && bw_try_fast<C>(t, p, &sinks, ks, w2, m2, ts, rw, seq, born, pcache)) continue;
       }
-      bw_fold_event<C, NoSeg>(t, p, &sinks, kk, ts, op, seq, batch_no, ks, NoSeg());
+      bw_fold_event<C>(t, p, &sinks, kk, ts, op, seq, batch_no, ks);
     }
     __syncwarp();
     if (lane == 0) sinks.n_defer[warp] = 0;

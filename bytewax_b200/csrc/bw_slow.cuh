@@ -45,12 +45,13 @@ __global__ void k_gather_i64(const i64* src, const u32* idx, i64* dst, u64 n) {
 
 // read-only lookup of a key's running max ts (INT64_MIN when the key has no state)
 __device__ __forceinline__ i64 bw_lookup_max_ts(const Table& t, u64 key) {
-  u64 s = (key == BW_EMPTY_KEY) ? t.cap : bw_slot_of_hash(bw_mix64(key), t.cap);
-  for (u64 probe = 0; probe < t.cap; ++probe) {
+  u64 s = bw_home_slot(t, key);
+  if (key == BW_EMPTY_KEY) return t.hot[s].max_ts;
+  for (u64 probe = 0; probe <= (u64)t.seg_mask; ++probe) {
     u64 k = t.hot[s].key;
     if (k == key) return t.hot[s].max_ts;
     if (k == BW_EMPTY_KEY) return INT64_MIN;
-    if (++s >= t.cap) s = 0;
+    s = bw_probe_next(t, s, 1);
   }
   return INT64_MIN;
 }
@@ -96,7 +97,7 @@ k_slow_fold(BatchView bv, Table t, FoldParams p, EmitBufs e, const unsigned char
       bw_load_event(bv, seg, off, p, key, ts, operand, raw);
       const u64 seq = ((u64)batch_no << 32) | g;
       if (!late[g]) {
-        bw_fold_event<FoldCfgRuntime, NoSeg>(t, p, &sinks, key, ts, operand, seq, batch_no, BW_NO_SLOT, NoSeg());
+        bw_fold_event<FoldCfgRuntime>(t, p, &sinks, key, ts, operand, seq, batch_no, BW_NO_SLOT);
       } else {
         // late_for(ts) == intersects(ts): floor((d-length)/offset)+1 .. floor(d/offset)
         i64 d = ts - p.align_us;

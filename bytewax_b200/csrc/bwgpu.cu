@@ -26,7 +26,7 @@
 #include "bw_close.cuh"
 #include "bw_common.cuh"
 #include "bw_exchange.cuh"
-#include "bw_bucket.cuh"
+#include "bw_stream.cuh"
 #include "bw_snapshot.cuh"
 #include "bw_fold.cuh"
 #include "bw_keyed.cuh"
@@ -84,7 +84,7 @@ struct Stage {  // device staging for host-ingested batches
 // optional per-phase timing (env BW_TIMING=1): events on the streams, summed at destroy
 struct PhaseTimer {
   static const int NPH = 8;
-  const char* names[NPH] = {"part_hist+scan+scatter", "barrier", "prepass", "fold", "close", "bucket (hist+scan+scatter)", "fold_seg", ""};
+  const char* names[NPH] = {"part_hist+scan+scatter", "barrier", "prepass", "fold", "close", "scatter + verdict", "segfold", "spill + close"};
   std::vector<cudaEvent_t> ev[NPH][2];
   bool on = false;
   void mark(int ph, int which, cudaStream_t s) {
@@ -120,6 +120,24 @@ struct PhaseTimer {
 struct EventPair {
   cudaEvent_t a, b;
   u64 rows;
+  int kind;  // 0: fold stage (k_fold / k_segfold), 1: scatter stage (k_scatter + k_verdict)
+};
+
+typedef void (*scatter_kernel_t)(ScatterArgs, FoldParams);
+typedef void (*segfold_kernel_t)(SegArgs, Table, FoldParams, EmitBufs);
+
+struct Stage;
+// An activation whose scatter + verdict are queued but whose fold stage is not: the host looks at a
+// verdict only after the NEXT activation's scatter is queued, so the device never waits for the host.
+struct Deferred {
+  bool valid = false;
+  int side = 0;
+  const u64* d_keys = nullptr;
+  const void* d_vals = nullptr;
+  const i64* d_ts = nullptr;
+  u64 rows = 0, ord = 0;
+  u32 batch_no = 0;
+  Stage* stage = nullptr;  // device staging buffer to release once the fold has read it
 };
 
 struct bw_fold {
@@ -173,14 +191,18 @@ struct bw_fold {
   bool eof_done = false;
   int fold_grid = 0, close_grid = 0;
   void (*fold_kernel)(BatchView, Table, FoldParams, u32, u32, u32) = nullptr;
-  // combining fold (bw_bucket.cuh): bucket by table segment, fold through shared memory
-  BktBufs bk{};
-  bool seg_ok = false;     // buffers allocated, fold type supported
-  int seg_mode = 0;        // env BW_SEG=1: use it for every clean activation of >= seg_min_rows (off by default: on C1 the
-                           // bucketing pass costs more than the combining saves, profiles/r01_notes.md)
-  u64 seg_min_rows = 1ULL << 20;
-  int seg_rpt = 16, seg_grid = 0;
-  void (*seg_kernel)(BktBufs, Table, FoldParams, u32, i64) = nullptr;
+  // streaming fold (bw_stream.cuh): fused verdict + bucket scatter, shared-memory segment fold
+  StreamBufs sb{};
+  bool stream_ok = false;   // buffers allocated, fold type supported
+  int stream_mode = 1;      // env BW_STREAM=0: always take the direct kernel (k_fold)
+  int scatter_grid = 0, segfold_grid = 0;
+  scatter_kernel_t scatter_kernel = nullptr;
+  segfold_kernel_t segfold_kernel = nullptr;
+  size_t segfold_smem = 0, scatter_smem = 0;
+  int scatter_rpt = 16;
+  cudaEvent_t ev_sv[2] = {nullptr, nullptr};
+  StreamVerdict* h_sv = nullptr;  // pinned mirror of the two sides' verdicts
+  Deferred dq{};            // the activation whose fold has not been launched yet
   i64* d_span = nullptr;   // [min ts, max ts] of the activation (prepass)
   // snapshot staging (bw_snapshot_take)
   void* snap_dev = nullptr;
@@ -398,34 +420,106 @@ static fold_kernel_t pick_fold_kernel(const FoldParams& p) {
   }
 }
 
-typedef void (*seg_kernel_t)(BktBufs, Table, FoldParams, u32, i64);
-static seg_kernel_t pick_seg_kernel(const FoldParams& p) {
-  if (!p.track_wm || p.need_count) return nullptr;
+// k_segfold instantiations: accumulator op (+ counts for MEAN) x first-open indices
+template <int OP, int CNT>
+static segfold_kernel_t pick_seq(bool seq) {
+  return seq ? (segfold_kernel_t)k_segfold<FoldCfg<OP, -1, CNT>, true> : (segfold_kernel_t)k_segfold<FoldCfg<OP, -1, CNT>, false>;
+}
+static segfold_kernel_t pick_segfold_kernel(const FoldParams& p) {
+  const bool seq = !p.seq_by_id;
+  if (p.need_count) return pick_seq<BW_OP_ADD_F64, 1>(seq);
   switch (p.op) {
-    case BW_OP_ADD_ONE: return (seg_kernel_t)k_fold_seg<FoldCfg<BW_OP_ADD_ONE, 1, 0>>;
-    case BW_OP_ADD_U64: return (seg_kernel_t)k_fold_seg<FoldCfg<BW_OP_ADD_U64, 1, 0>>;
-    case BW_OP_ADD_F64: return (seg_kernel_t)k_fold_seg<FoldCfg<BW_OP_ADD_F64, 1, 0>>;
-    case BW_OP_MIN_S64: return (seg_kernel_t)k_fold_seg<FoldCfg<BW_OP_MIN_S64, 1, 0>>;
-    case BW_OP_MIN_U64: return (seg_kernel_t)k_fold_seg<FoldCfg<BW_OP_MIN_U64, 1, 0>>;
-    case BW_OP_MAX_S64: return (seg_kernel_t)k_fold_seg<FoldCfg<BW_OP_MAX_S64, 1, 0>>;
-    default: return (seg_kernel_t)k_fold_seg<FoldCfg<BW_OP_MAX_U64, 1, 0>>;
+    case BW_OP_ADD_ONE: return pick_seq<BW_OP_ADD_ONE, 0>(seq);
+    case BW_OP_ADD_U64: return pick_seq<BW_OP_ADD_U64, 0>(seq);
+    case BW_OP_ADD_F64: return pick_seq<BW_OP_ADD_F64, 0>(seq);
+    case BW_OP_MIN_S64: return pick_seq<BW_OP_MIN_S64, 0>(seq);
+    case BW_OP_MIN_U64: return pick_seq<BW_OP_MIN_U64, 0>(seq);
+    case BW_OP_MAX_S64: return pick_seq<BW_OP_MAX_S64, 0>(seq);
+    default: return pick_seq<BW_OP_MAX_U64, 0>(seq);
   }
+}
+// k_scatter instantiations: timestamp source x value bytes read / stored
+static scatter_kernel_t pick_scatter_kernel(int tsm, int vb_in, int vb_out, int* rpt) {
+  *rpt = vb_out ? 8 : 16;
+  if (tsm == 1) return vb_out ? (scatter_kernel_t)k_scatter<1, 8, 8, 8> : (scatter_kernel_t)k_scatter<1, 8, 0, 16>;
+  if (tsm == 0) {
+    if (!vb_out) return (scatter_kernel_t)k_scatter<0, 0, 0, 16>;
+    return vb_in == 4 ? (scatter_kernel_t)k_scatter<0, 4, 4, 8> : (scatter_kernel_t)k_scatter<0, 8, 8, 8>;
+  }
+  if (!vb_out) return (scatter_kernel_t)k_scatter<2, 0, 0, 16>;
+  return vb_in == 4 ? (scatter_kernel_t)k_scatter<2, 4, 4, 8> : (scatter_kernel_t)k_scatter<2, 8, 8, 8>;
+}
+
+static bw_status stream_alloc(bw_fold* f) {
+  bw_ctx* ctx = f->ctx;
+  StreamBufs& sb = f->sb;
+  const u64 rows = f->spec.max_batch_rows;
+  const u64 nb = f->t.cap >> BW_SEG_SHIFT;
+  if (const char* e = getenv("BW_STREAM")) f->stream_mode = atoi(e) ? 1 : 0;
+  if (!f->stream_mode || ctx->world != 1 || nb > BW_STREAM_MAX_NB || rows >= (1ULL << 32)) return BW_OK;
+  // wait == forever with event time: nothing closes before EOF, every key grows an overflow list of panes --
+  // the shape the direct kernel's general path is for
+  if (!f->p.track_wm && f->p.ts_from_value != 2) return BW_OK;
+  sb.nb = (u32)nb;
+  // one region per bucket: mean + 6 sigma + slack of a uniform split, where the variance of a bucket's row count is that of
+  // its rows (Poisson) plus that of its number of distinct keys (a fuller bucket overflows into the spill list)
+  const double mean = (double)rows / (double)nb;
+  const double keys_per_bucket = std::max(1.0, (double)std::max<u64>(f->spec.capacity_hint, 1) / (double)nb);
+  const double sigma = std::sqrt(mean + mean * mean / keys_per_bucket);
+  sb.region_cap = (u32)std::min<double>((double)rows, mean + 6.0 * sigma + 64.0);
+  sb.region_cap = (sb.region_cap + 7u) & ~7u;
+  sb.spill_cap = (u32)std::min<u64>(std::max<u64>(rows / 4, 8192), 1u << 24);
+  sb.val_bytes = (f->p.op == BW_OP_ADD_ONE && !f->p.need_count) ? 0 : f->val_bytes;
+  const size_t region_rows = (size_t)sb.nb * sb.region_cap;
+  for (int i = 0; i < 2; ++i) {
+    CU(ctx, dmalloc(&sb.side[i].rec, region_rows));
+    if (sb.val_bytes) CU(ctx, cudaMalloc(&sb.side[i].val, region_rows * (size_t)sb.val_bytes));
+    CU(ctx, dmalloc(&sb.side[i].cursor, sb.nb));
+    CU(ctx, cudaMemsetAsync(sb.side[i].cursor, 0, sizeof(u32) * sb.nb, f->s_compute));
+    CU(ctx, dmalloc(&sb.side[i].spill, sb.spill_cap));
+    CU(ctx, dmalloc(&sb.side[i].sv, 1));
+    CU(ctx, cudaMemsetAsync(sb.side[i].sv, 0, sizeof(StreamVerdict), f->s_compute));
+    CU(ctx, cudaEventCreateWithFlags(&f->ev_sv[i], cudaEventDisableTiming));
+  }
+  CU(ctx, cudaHostAlloc((void**)&f->h_sv, 2 * sizeof(StreamVerdict), cudaHostAllocDefault));
+  const int tsm = f->p.ts_from_value ? f->p.ts_from_value : 0;
+  const int vb_in = (tsm == 1) ? 8 : (sb.val_bytes ? f->val_bytes : 0);
+  f->scatter_kernel = pick_scatter_kernel(tsm, vb_in, sb.val_bytes, &f->scatter_rpt);
+  const u64 T = (u64)BW_SC_THREADS * f->scatter_rpt;
+  sb.tiles_cap = (u32)((rows + T - 1) / T + 1);
+  CU(ctx, dmalloc(&sb.tile_min, sb.tiles_cap));
+  CU(ctx, dmalloc(&sb.tile_max, sb.tiles_cap));
+  CU(ctx, dmalloc(&sb.tile_bad, sb.tiles_cap));
+  f->scatter_smem = 2 * sizeof(u32) * sb.nb;
+  // the attribute belongs to the kernel, not to this fold: folds with other table sizes share it
+  CU(ctx, cudaFuncSetAttribute((const void*)f->scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sizeof(u32) * BW_STREAM_MAX_NB)));
+  int occ = 0;
+  CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)f->scatter_kernel, BW_SC_THREADS, f->scatter_smem));
+  f->scatter_grid = ctx->sm_count * std::max(occ, 1);
+  f->segfold_kernel = pick_segfold_kernel(f->p);
+  f->segfold_smem = bw_segfold_smem(f->p.op, !f->p.seq_by_id, f->p.need_count != 0);
+  CU(ctx, cudaFuncSetAttribute((const void*)f->segfold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->segfold_smem));
+  CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)f->segfold_kernel, BW_SF_THREADS, f->segfold_smem));
+  f->segfold_grid = ctx->sm_count * std::max(occ, 1);
+  f->stream_ok = true;
+  return BW_OK;
 }
 
 static bw_status fold_alloc(bw_fold* f) {
   bw_ctx* ctx = f->ctx;
   const bw_fold_spec& s = f->spec;
-  // table: capacity_hint / load factor slots (any size; load 0.5 by default, env BW_LOAD_PCT),
-  // rounded up to a multiple of 4 slots (one 128-byte line of hot slots)
+  // table: capacity_hint / load factor slots (load 0.5 by default, env BW_LOAD_PCT), a whole number of
+  // segments of BW_SEG_SLOTS slots: linear probing wraps inside a segment (bw_stream.cuh owns whole segments)
   int load_pct = 50;
   if (const char* e = getenv("BW_LOAD_PCT")) {
     int v = atoi(e);
     if (v >= 10 && v <= 90) load_pct = v;
   }
-  u64 cap = std::max<u64>(1024, (std::max<u64>(s.capacity_hint, 1) * 100 + load_pct - 1) / load_pct);
-  cap = (cap + 3) & ~3ULL;
+  u64 cap = std::max<u64>(BW_SEG_SLOTS, (std::max<u64>(s.capacity_hint, 1) * 100 + load_pct - 1) / load_pct);
+  cap = (cap + BW_SEG_SLOTS - 1) & ~(u64)(BW_SEG_SLOTS - 1);
   if (cap > (1ULL << 31)) FAIL(f, BW_ERR_SPEC, "capacity_hint too large");
   f->t.cap = cap;
+  f->t.seg_mask = BW_SEG_SLOTS - 1;
   {
     // overflow pane nodes: panes a key can hold beyond its two direct slots
     const i64 per_window = f->p.panes_per_window;
@@ -503,38 +597,9 @@ static bw_status fold_alloc(bw_fold* f) {
   // (NVLink-bound, on its own stream) can really run beside the fold instead of queueing behind it
   if (ctx->world > 1 && occ > 2 && !getenv("BW_FOLD_FULL")) f->fold_grid = ctx->sm_count * 2;
   f->close_grid = ctx->sm_count * 8;
-  // combining fold: needs the watermark prepass (time span of the activation), a plain accumulator,
-  // at most BW_BKT_MAX table segments and arrival indices that fit 31 bits
-  if (const char* e = getenv("BW_SEG")) f->seg_mode = atoi(e) ? 1 : 0;
-  if (const char* e = getenv("BW_SEG_MIN_ROWS")) f->seg_min_rows = (u64)atoll(e);
   {
-    const u64 nb = (cap + BW_BKT_SLOTS - 1) >> BW_BKT_SHIFT;
-    f->seg_kernel = pick_seg_kernel(f->p);
-    if (f->seg_mode != 0 && f->seg_kernel && nb <= BW_BKT_MAX && f->max_recv_rows < (1ULL << 31) &&
-        f->max_recv_rows >= f->seg_min_rows) {
-      const u64 rows = f->max_recv_rows;
-      f->seg_rpt = f->has_ts ? 8 : 16;
-      const u64 T = (u64)BW_BKT_THREADS * f->seg_rpt;
-      f->bk.nb = (u32)nb;
-      f->bk.tiles_cap = (u32)((rows + T - 1) / T + 1);
-      f->bk.val_bytes = f->has_vals ? f->val_bytes : 0;
-      CU(ctx, dmalloc(&f->bk.keys, rows));
-      if (f->has_vals) CU(ctx, cudaMalloc(&f->bk.vals, rows * (size_t)f->val_bytes));
-      if (f->has_ts) CU(ctx, dmalloc(&f->bk.ts, rows));
-      CU(ctx, dmalloc(&f->bk.g, rows));
-      CU(ctx, dmalloc(&f->bk.tile_counts, (size_t)nb * f->bk.tiles_cap));
-      CU(ctx, dmalloc(&f->bk.cnt, nb));
-      CU(ctx, dmalloc(&f->bk.off, nb + 1));
-      CU(ctx, cudaFuncSetAttribute((const void*)f->seg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BW_SEG_SMEM));
-      const int sm = (int)bw_bkt_scatter_smem(f->seg_rpt, f->bk.val_bytes, f->has_ts);
-      if (f->seg_rpt == 16) CU(ctx, cudaFuncSetAttribute((const void*)k_bkt_scatter<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-      else CU(ctx, cudaFuncSetAttribute((const void*)k_bkt_scatter<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-      int socc = 0;
-      CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&socc, (const void*)f->seg_kernel, BW_SEG_THREADS, BW_SEG_SMEM));
-      if (socc < 1) socc = 1;
-      f->seg_grid = ctx->sm_count * socc;
-      f->seg_ok = true;
-    }
+    bw_status st = stream_alloc(f);
+    if (st != BW_OK) return st;
   }
   k_init_table<<<ctx->sm_count * 8, 256, 0, f->s_compute>>>(f->t, f->p.acc_identity);
   CU(ctx, cudaGetLastError());
@@ -672,6 +737,10 @@ bw_status bw_fold_create(bw_ctx* ctx, const bw_fold_spec* spec, bw_fold** out) {
   p.track_wm = spec->wait_us != BW_WAIT_FOREVER;
   p.ordered = spec->ordered;
   p.need_count = spec->reduction == BW_RED_MEAN;
+  // first-opened order of a key's windows == ascending id when flushes are ordered, when nothing is
+  // accepted out of order (wait == 0: an accepted timestamp is never below the key's maximum), or when
+  // there is a single window (the *_final folds)
+  p.seq_by_id = (spec->ordered || spec->ts_source == BW_TS_NONE || spec->wait_us == 0) ? 1 : 0;
   const bool is_float = spec->val_dtype >= BW_VAL_F32, is_signed = spec->val_dtype == BW_VAL_I64;
   switch (spec->reduction) {
     case BW_RED_COUNT: p.op = BW_OP_ADD_ONE; p.acc_identity = 0; break;
@@ -705,9 +774,12 @@ bw_status bw_fold_create(bw_ctx* ctx, const bw_fold_spec* spec, bw_fold** out) {
   return BW_OK;
 }
 
+static bw_status stream_resolve(bw_fold* f);
+
 void bw_fold_destroy(bw_fold* f) {
   if (!f) return;
   cudaSetDevice(f->ctx->device);
+  stream_resolve(f);
   cudaDeviceSynchronize();
   f->pt.report(f->ctx->rank);
   for (int r = 0; r < f->ctx->world; ++r)
@@ -717,10 +789,21 @@ void bw_fold_destroy(bw_fold* f) {
                  f->e.l_ts, f->e.l_seq, f->e.l_epoch, f->d_rmin, f->d_rmax, f->d_rbad, f->d_verdict, f->d_kflat,
                  f->d_ksorted, f->d_tsflat, f->d_tssorted, f->d_prefmax, f->d_idx, f->d_idxsorted, f->d_late, f->d_cub,
                  f->d_sk, f->d_sk2, f->d_gather, f->d_perm, f->d_perm2, f->xchg_base, f->d_tile_counts,
-                 f->d_send_counts, f->d_all_counts, f->send_keys, f->send_vals, f->send_ts, f->d_span, f->snap_dev, f->d_snap_ctr,
-                 f->bk.keys, f->bk.vals, f->bk.ts, f->bk.g, f->bk.tile_counts, f->bk.cnt, f->bk.off};
+                 f->d_send_counts, f->d_all_counts, f->send_keys, f->send_vals, f->send_ts, f->d_span, f->snap_dev, f->d_snap_ctr};
   for (void* p : dev)
     if (p) cudaFree(p);
+  for (int i = 0; i < 2; ++i) {
+    void* sp[] = {f->sb.side[i].rec, f->sb.side[i].val, f->sb.side[i].cursor, f->sb.side[i].spill, f->sb.side[i].sv};
+    for (void* q : sp)
+      if (q) cudaFree(q);
+    if (f->ev_sv[i]) cudaEventDestroy(f->ev_sv[i]);
+  }
+  {
+    void* sp[] = {f->sb.tile_min, f->sb.tile_max, f->sb.tile_bad};
+    for (void* q : sp)
+      if (q) cudaFree(q);
+    if (f->h_sv) cudaFreeHost(f->h_sv);
+  }
   for (auto& s : f->stages) {
     if (s.d_keys) cudaFree(s.d_keys);
     if (s.d_vals) cudaFree(s.d_vals);
@@ -793,12 +876,12 @@ static EventPair* next_timer(bw_fold* f) {
     EventPair ep;
     if (cudaEventCreate(&ep.a) != cudaSuccess || cudaEventCreate(&ep.b) != cudaSuccess) return nullptr;
     ep.rows = 0;
+    ep.kind = 0;
     f->timers.push_back(ep);
   }
   return &f->timers[f->timers_used++];
 }
 
-static bw_status slow_path(bw_fold* f, const BatchView& bv, u64 total, u64 epoch_ord);
 
 // Partition + exchange of this rank's rows; fills `bv` with the received segments.
 static bw_status exchange(bw_fold* f, const u64* d_keys, const void* d_vals, const i64* d_ts, u64 rows, BatchView* bv) {
@@ -901,16 +984,241 @@ static bw_status exchange(bw_fold* f, const u64* d_keys, const void* d_vals, con
   return BW_OK;
 }
 
-// Everything after the columns are on the device (on s_compute's dependency chain).
-static bw_status run_batch(bw_fold* f, const u64* d_keys, const void* d_vals, const i64* d_ts, u64 rows, u64 epoch) {
+// K4 for the keys the fold marked, then the end-of-activation resets
+static bw_status close_stage(bw_fold* f, u64 ord, u32 batch_no, StreamVerdict* sv) {
   bw_ctx* ctx = f->ctx;
-  const u32 batch_no = f->batch_no++;
+  f->pt.mark(4, 0, f->s_compute);
+  k_close_dirty<<<f->close_grid, 256, 0, f->s_compute>>>(f->t, f->p, f->e, ord, batch_no);
+  k_stream_reset<<<1, 1, 0, f->s_compute>>>(f->t, sv);
+  CU(ctx, cudaGetLastError());
+  f->st.kernel_launches += 2;
+  f->pt.mark(4, 1, f->s_compute);
+  return BW_OK;
+}
+
+// The direct fold kernel over a clean activation, in sub-ranges when it spans several panes.
+static bw_status direct_fold(bw_fold* f, const BatchView& bv, u64 known, u32 batch_no, u64 ord, i64 tmin, i64 tmax) {
+  bw_ctx* ctx = f->ctx;
+  const u64 tile = (u64)BW_FOLD_THREADS * BW_FOLD_UNROLL;
+  // Fold + close in sub-ranges of the activation (by arrival index, resolved on the device so
+  // that it also works on exchanged rows whose counts the host never sees).  Windows a key has
+  // left are closed -- and its newest pane promoted into the hot slot -- between sub-ranges, so
+  // an activation that spans several windows (8 ranks x 2^24 rows of C1 = 134 s of event time
+  // per activation) keeps hitting the two direct panes instead of the overflow list.  Rows are
+  // identical: a pane closed early would also close at the end (the watermark only grows, and
+  // the pane holding max_ts never closes).  One sub-range per pane of event-time span, for
+  // in-order streams; activations inside one pane (C1 on one GPU) are not split.
+  u32 n_sub = 1;
+  if (f->sub_rows != ~0ULL) {
+    n_sub = (u32)std::min<u64>((known + f->sub_rows - 1) / f->sub_rows, 64);
+  } else if (f->sub_auto && f->p.track_wm) {
+    if (tmax > tmin) {
+      const u64 panes = (u64)(tmax - tmin) / (u64)f->p.pane_us + (((u64)(tmax - tmin) % (u64)f->p.pane_us) ? 1 : 0);
+      n_sub = (u32)std::min<u64>(panes, 8);
+      n_sub = (u32)std::min<u64>(n_sub, std::max<u64>(known >> 20, 1));  // keep sub-ranges >= 2^20 rows
+    }
+  }
+  if (n_sub < 1) n_sub = 1;
+  for (u32 i = 0; i < n_sub; ++i) {
+    const u64 n_hi = (known * (i + 1ULL)) / n_sub, n_lo = (known * (u64)i) / n_sub;
+    EventPair* ep = next_timer(f);
+    if (ep) {
+      ep->rows = (ctx->world > 1) ? 0 : (n_hi - n_lo);
+      ep->kind = 0;
+      CU(ctx, cudaEventRecord(ep->a, f->s_compute));
+    }
+    int grid = (int)std::min<u64>((n_hi - n_lo + tile - 1) / tile + 1, (u64)f->fold_grid);
+    f->fold_kernel<<<grid, BW_FOLD_THREADS, 0, f->s_compute>>>(bv, f->t, f->p, batch_no, i, n_sub);
+    CU(ctx, cudaGetLastError());
+    if (ep) CU(ctx, cudaEventRecord(ep->b, f->s_compute));
+    f->st.kernel_launches++;
+    f->st.fold_launches++;
+    if (f->pt.on && ep) {
+      f->pt.ev[3][0].push_back(ep->a);
+      f->pt.ev[3][1].push_back(ep->b);
+    }
+    if (i + 1 < n_sub) {
+      k_close_dirty<<<f->close_grid, 256, 0, f->s_compute>>>(f->t, f->p, f->e, ord, batch_no);
+      k_reset_dirty<<<1, 1, 0, f->s_compute>>>(f->t);
+      f->st.kernel_launches += 2;
+    }
+  }
+  return BW_OK;
+}
+
+// ---- streaming path (bw_stream.cuh): queue scatter + verdict now, the fold stage one activation later ----
+static bool stream_usable(const bw_fold* f, const u64* d_keys, const void* d_vals, const i64* d_ts, u64 rows) {
+  if (!f->stream_ok || rows == 0 || rows > f->spec.max_batch_rows) return false;
+  // 128-bit loads of column pairs
+  if (((uintptr_t)d_keys & 15) || ((uintptr_t)d_vals & 15) || ((uintptr_t)d_ts & 15)) return false;
+  if (f->p.ts_from_value == 1 && !d_vals) return false;
+  if (f->sb.val_bytes && !d_vals) return false;
+  return true;
+}
+
+static bw_status stream_front(bw_fold* f, const u64* d_keys, const void* d_vals, const i64* d_ts, u64 rows, u32 batch_no, int side) {
+  bw_ctx* ctx = f->ctx;
+  const StreamBufs& sb = f->sb;
+  cudaStream_t s = f->s_compute;
+  ScatterArgs A;
+  memset(&A, 0, sizeof A);
+  A.keys = d_keys;
+  A.vals = d_vals;
+  A.ts = f->has_ts ? d_ts : nullptr;
+  A.n = rows;
+  A.out = sb.side[side];
+  A.nb = sb.nb;
+  A.region_cap = sb.region_cap;
+  A.spill_cap = sb.spill_cap;
+  A.tile_min = sb.tile_min;
+  A.tile_max = sb.tile_max;
+  A.tile_bad = sb.tile_bad;
+  A.cap = f->t.cap;
+  A.batch_no = batch_no;
+  const u64 T = (u64)BW_SC_THREADS * f->scatter_rpt;
+  const u64 ntiles = (rows + T - 1) / T;
+  const int grid = (int)std::min<u64>(ntiles, (u64)f->scatter_grid);
+  EventPair* ep = next_timer(f);
+  if (ep) {
+    ep->rows = rows;
+    ep->kind = 1;
+    CU(ctx, cudaEventRecord(ep->a, s));
+  }
+  f->pt.mark(5, 0, s);
+  f->scatter_kernel<<<grid, BW_SC_THREADS, f->scatter_smem, s>>>(A, f->p);
+  if (f->p.ts_from_value == 2) k_verdict_none<<<1, 1, 0, s>>>(f->p, f->d_ctr, sb.side[side].sv);
+  else
+    k_verdict<<<1, 1024, 0, s>>>(sb.tile_min, sb.tile_max, sb.tile_bad, (u32)ntiles, f->p, f->d_ctr, sb.side[side].sv,
+                                 f->has_ts ? d_ts : nullptr, (const u64*)d_vals);
+  CU(ctx, cudaGetLastError());
+  f->pt.mark(5, 1, s);
+  if (ep) CU(ctx, cudaEventRecord(ep->b, s));
+  f->st.kernel_launches += 2;
+  CU(ctx, cudaMemcpyAsync(&f->h_sv[side], sb.side[side].sv, sizeof(StreamVerdict), cudaMemcpyDeviceToHost, s));
+  CU(ctx, cudaEventRecord(f->ev_sv[side], s));
+  return BW_OK;
+}
+
+static bw_status slow_path(bw_fold* f, const BatchView& bv, u64 total, u64 epoch_ord, u32 batch_no);
+
+// The fold stage of the deferred activation: the segment fold when its verdict allows, else what the
+// direct path would have done (its scatter output is dropped; the input columns are still there).
+static bw_status stream_resolve(bw_fold* f) {
+  bw_ctx* ctx = f->ctx;
+  Deferred d = f->dq;
+  if (!d.valid) return BW_OK;
+  f->dq.valid = false;
+  const StreamBufs& sb = f->sb;
+  cudaStream_t s = f->s_compute;
+  CU(ctx, cudaEventSynchronize(f->ev_sv[d.side]));
+  const StreamVerdict sv = f->h_sv[d.side];
+  const FoldParams& p = f->p;
+  i64 q_lo = 0, q_hi = 0;
+  if (sv.tmax >= sv.tmin) {
+    q_lo = bw_floordiv(sv.tmin - p.align_us, p.pane_us);
+    q_hi = bw_floordiv(sv.tmax - p.align_us, p.pane_us);
+  }
+  const bool fits = sv.clean && !sv.flags && (q_hi - q_lo) < 2 * 64;
+  bw_status st = BW_OK;
+  if (fits) {
+    SegArgs A;
+    memset(&A, 0, sizeof A);
+    A.in = sb.side[d.side];
+    A.nb = sb.nb;
+    A.region_cap = sb.region_cap;
+    A.spill_cap = sb.spill_cap;
+    A.val_bytes = sb.val_bytes;
+    A.ts0 = sv.ts0;
+    A.q_lo = q_lo;
+    A.npass = (u32)((q_hi - q_lo) / 2 + 1);
+    A.batch_no = d.batch_no;
+    A.epoch = d.ord;
+    EventPair* ep = next_timer(f);
+    if (ep) {
+      ep->rows = d.rows;
+      ep->kind = 0;
+      CU(ctx, cudaEventRecord(ep->a, s));
+    }
+    const u32 n_pre = std::min<u32>(sv.n_spill, sb.spill_cap);  // rows the scatter set aside: fold them first
+    if (n_pre) {
+      k_spill<<<(int)std::min<u32>((n_pre + 255) / 256, (u32)ctx->sm_count * 4), 256, 0, s>>>(f->t, f->p, sb.side[d.side].spill, sb.side[d.side].sv,
+                                                                                           sb.spill_cap, d.batch_no, 0u, n_pre);
+      f->st.kernel_launches++;
+    }
+    f->pt.mark(6, 0, s);
+    const int grid = (int)std::min<u32>(sb.nb, (u32)f->segfold_grid);
+    f->segfold_kernel<<<grid, BW_SF_THREADS, f->segfold_smem, s>>>(A, f->t, f->p, f->e);
+    CU(ctx, cudaGetLastError());
+    f->pt.mark(6, 1, s);
+    if (ep) CU(ctx, cudaEventRecord(ep->b, s));
+    f->pt.mark(7, 0, s);
+    k_spill<<<ctx->sm_count, 256, 0, s>>>(f->t, f->p, sb.side[d.side].spill, sb.side[d.side].sv, sb.spill_cap, d.batch_no, n_pre, 0xFFFFFFFFu);
+    f->st.kernel_launches += 2;
+    f->st.fold_launches++;
+    f->st.combined_folds++;
+    st = close_stage(f, d.ord, d.batch_no, sb.side[d.side].sv);
+    f->pt.mark(7, 1, s);
+  } else {
+    // drop the scatter output of this activation
+    CU(ctx, cudaMemsetAsync(sb.side[d.side].cursor, 0, sizeof(u32) * sb.nb, s));
+    BatchView bv;
+    memset(&bv, 0, sizeof bv);
+    bv.nseg = 1;
+    bv.keys[0] = d.d_keys;
+    bv.vals[0] = d.d_vals;
+    bv.ts[0] = f->has_ts ? d.d_ts : nullptr;
+    bv.h_counts[0] = d.rows;
+    bv.max_rows = d.rows;
+    if (sv.clean) {
+      st = direct_fold(f, bv, d.rows, d.batch_no, d.ord, sv.tmin, sv.tmax);
+    } else {
+      st = slow_path(f, bv, d.rows, d.ord, d.batch_no);
+      f->st.slow_batches++;
+    }
+    if (st == BW_OK) st = close_stage(f, d.ord, d.batch_no, sb.side[d.side].sv);
+  }
+  if (d.stage) {
+    CU(ctx, cudaEventRecord(d.stage->consumed, s));
+    d.stage->used = true;
+  }
+  return st;
+}
+
+// Everything after the columns are on the device (on s_compute's dependency chain).
+static bw_status run_batch(bw_fold* f, const u64* d_keys, const void* d_vals, const i64* d_ts, u64 rows, u64 epoch, Stage* stage) {
+  bw_ctx* ctx = f->ctx;
   if (f->have_epoch && epoch < f->last_epoch) FAIL(f, BW_ERR_STATE, "epochs must not decrease (got %llu after %llu)", (unsigned long long)epoch, (unsigned long long)f->last_epoch);
+  const u32 batch_no = f->batch_no++;
   if (!f->have_pending) { f->min_epoch = epoch; f->have_pending = true; }
   f->last_epoch = epoch;
   f->have_epoch = true;
   const u64 ord = epoch;
   f->st.rows_ingested += rows;
+  if (ctx->world == 1 && stream_usable(f, d_keys, d_vals, d_ts, rows)) {
+    // queue this activation's scatter + verdict BEFORE looking at the previous verdict: the device
+    // always has the next stage waiting while the host decides
+    const int side = (int)(batch_no & 1u);
+    f->st.rows_received += rows;
+    bw_status st = stream_front(f, d_keys, d_vals, d_ts, rows, batch_no, side);
+    if (st != BW_OK) return st;
+    st = stream_resolve(f);
+    if (st != BW_OK) return st;
+    Deferred& d = f->dq;
+    d.valid = true;
+    d.side = side;
+    d.d_keys = d_keys;
+    d.d_vals = d_vals;
+    d.d_ts = d_ts;
+    d.rows = rows;
+    d.ord = ord;
+    d.batch_no = batch_no;
+    d.stage = stage;
+    return BW_OK;
+  }
+  {  // activations fold in order
+    bw_status st = stream_resolve(f);
+    if (st != BW_OK) return st;
+  }
   BatchView bv;
   memset(&bv, 0, sizeof bv);
   u64 max_total = rows;
@@ -954,93 +1262,11 @@ static bw_status run_batch(bw_fold* f, const u64* d_keys, const void* d_vals, co
     CU(ctx, cudaStreamWaitEvent(f->s_compute, f->ev_xchg_done, 0));
   }
   if (max_total > 0) {
-    bool seg = false;
-    if (clean && f->seg_ok && f->p.track_wm) {
+    if (clean) {
+      const u64 known = (ctx->world == 1) ? rows : max_total;
       const i64 tmin = ((const i64*)(f->h_verdict + 4))[0], tmax = ((const i64*)(f->h_verdict + 4))[1];
-      const u64 known = (ctx->world == 1) ? rows : max_total;
-      seg = f->seg_mode == 1 && known >= f->seg_min_rows && tmax >= tmin && (u64)(tmax - tmin) < 0xFFFFFFF0ULL;
-      if (seg) {
-        EventPair* ep = next_timer(f);
-        if (ep) {
-          ep->rows = (ctx->world > 1) ? 0 : rows;
-          CU(ctx, cudaEventRecord(ep->a, f->s_compute));
-        }
-        const u64 T = (u64)BW_BKT_THREADS * f->seg_rpt;
-        BktBufs bk = f->bk;
-        if (!bv.vals[0]) bk.val_bytes = 0;  // counts may come without a value column
-        const int grid = (int)std::min<u64>((max_total + T - 1) / T, (u64)ctx->sm_count * 4);
-        const size_t sm = bw_bkt_scatter_smem(f->seg_rpt, bk.val_bytes, f->has_ts);
-        f->pt.mark(5, 0, f->s_compute);
-        if (f->seg_rpt == 16) k_bkt_hist<16><<<grid, BW_BKT_THREADS, 0, f->s_compute>>>(bv, f->t.cap, bk);
-        else k_bkt_hist<8><<<grid, BW_BKT_THREADS, 0, f->s_compute>>>(bv, f->t.cap, bk);
-        k_bkt_scan<<<bk.nb, 1024, 0, f->s_compute>>>(bv, bk, (u32)T);
-        k_bkt_base<<<1, 1024, 0, f->s_compute>>>(bk);
-        if (f->seg_rpt == 16) k_bkt_scatter<16><<<grid, BW_BKT_THREADS, sm, f->s_compute>>>(bv, f->t.cap, bk);
-        else k_bkt_scatter<8><<<grid, BW_BKT_THREADS, sm, f->s_compute>>>(bv, f->t.cap, bk);
-        f->pt.mark(5, 1, f->s_compute);
-        f->pt.mark(6, 0, f->s_compute);
-        const int sgrid = (int)std::min<u32>(bk.nb, (u32)f->seg_grid);
-        f->seg_kernel<<<sgrid, BW_SEG_THREADS, BW_SEG_SMEM, f->s_compute>>>(bk, f->t, f->p, batch_no, tmin);
-        f->pt.mark(6, 1, f->s_compute);
-        CU(ctx, cudaGetLastError());
-        if (ep) CU(ctx, cudaEventRecord(ep->b, f->s_compute));
-        f->st.kernel_launches += 5;
-        f->st.fold_launches++;
-        f->st.combined_folds++;
-        if (f->pt.on && ep) {
-          f->pt.ev[3][0].push_back(ep->a);
-          f->pt.ev[3][1].push_back(ep->b);
-        }
-      }
-    }
-    if (seg) {
-      // folded above
-    } else if (clean) {
-      const u64 tile = (u64)BW_FOLD_THREADS * BW_FOLD_UNROLL;
-      // Fold + close in sub-ranges of the activation (by arrival index, resolved on the device so
-      // that it also works on exchanged rows whose counts the host never sees).  Windows a key has
-      // left are closed -- and its newest pane promoted into the hot slot -- between sub-ranges, so
-      // an activation that spans several windows (8 ranks x 2^24 rows of C1 = 134 s of event time
-      // per activation) keeps hitting the two direct panes instead of the overflow list.  Rows are
-      // identical: a pane closed early would also close at the end (the watermark only grows, and
-      // the pane holding max_ts never closes).  One sub-range per pane of event-time span, for
-      // in-order streams; activations inside one pane (C1 on one GPU) are not split.
-      const u64 known = (ctx->world == 1) ? rows : max_total;
-      u32 n_sub = 1;
-      if (f->sub_rows != ~0ULL) {
-        n_sub = (u32)std::min<u64>((known + f->sub_rows - 1) / f->sub_rows, 64);
-      } else if (f->sub_auto && f->p.track_wm) {
-        const i64 tmin = ((const i64*)(f->h_verdict + 4))[0], tmax = ((const i64*)(f->h_verdict + 4))[1];
-        if (tmax > tmin) {
-          const u64 panes = (u64)(tmax - tmin) / (u64)f->p.pane_us + (((u64)(tmax - tmin) % (u64)f->p.pane_us) ? 1 : 0);
-          n_sub = (u32)std::min<u64>(panes, 8);
-          n_sub = (u32)std::min<u64>(n_sub, std::max<u64>(known >> 20, 1));  // keep sub-ranges >= 2^20 rows
-        }
-      }
-      if (n_sub < 1) n_sub = 1;
-      for (u32 i = 0; i < n_sub; ++i) {
-        const u64 n_hi = (known * (i + 1ULL)) / n_sub, n_lo = (known * (u64)i) / n_sub;
-        EventPair* ep = next_timer(f);
-        if (ep) {
-          ep->rows = (ctx->world > 1) ? 0 : (n_hi - n_lo);
-          CU(ctx, cudaEventRecord(ep->a, f->s_compute));
-        }
-        int grid = (int)std::min<u64>((n_hi - n_lo + tile - 1) / tile + 1, (u64)f->fold_grid);
-        f->fold_kernel<<<grid, BW_FOLD_THREADS, 0, f->s_compute>>>(bv, f->t, f->p, batch_no, i, n_sub);
-        CU(ctx, cudaGetLastError());
-        if (ep) CU(ctx, cudaEventRecord(ep->b, f->s_compute));
-        f->st.kernel_launches++;
-        f->st.fold_launches++;
-        if (f->pt.on && ep) {
-          f->pt.ev[3][0].push_back(ep->a);
-          f->pt.ev[3][1].push_back(ep->b);
-        }
-        if (i + 1 < n_sub) {
-          k_close_dirty<<<f->close_grid, 256, 0, f->s_compute>>>(f->t, f->p, f->e, ord);
-          k_reset_dirty<<<1, 1, 0, f->s_compute>>>(f->t);
-          f->st.kernel_launches += 2;
-        }
-      }
+      bw_status st = direct_fold(f, bv, known, batch_no, ord, f->p.track_wm ? tmin : 0, f->p.track_wm ? tmax : 0);
+      if (st != BW_OK) return st;
     } else {
       u64 total = rows;
       if (ctx->world > 1) {
@@ -1050,20 +1276,20 @@ static bw_status run_batch(bw_fold* f, const u64* d_keys, const void* d_vals, co
         total = 0;
         for (int r = 0; r < ctx->world; ++r) total += hc[r];
       }
-      bw_status st = slow_path(f, bv, total, ord);
+      bw_status st = slow_path(f, bv, total, ord, batch_no);
       if (st != BW_OK) return st;
       f->st.slow_batches++;
     }
-    f->pt.mark(4, 0, f->s_compute);
-    k_close_dirty<<<f->close_grid, 256, 0, f->s_compute>>>(f->t, f->p, f->e, ord);
-    k_reset_dirty<<<1, 1, 0, f->s_compute>>>(f->t);
-    CU(ctx, cudaGetLastError());
-    f->st.kernel_launches += 2;
-    f->pt.mark(4, 1, f->s_compute);
+    bw_status st = close_stage(f, ord, batch_no, nullptr);
+    if (st != BW_OK) return st;
   }
   if (ctx->world > 1) {
     CU(ctx, cudaEventRecord(f->ev_fold_done, f->s_compute));
     f->fold_recorded = true;
+  }
+  if (stage) {
+    CU(ctx, cudaEventRecord(stage->consumed, f->s_compute));
+    stage->used = true;
   }
   return BW_OK;
 }
@@ -1098,10 +1324,8 @@ bw_status bw_ingest_commit(bw_fold* f, const bw_batch* batch, uint64_t rows, uin
   CU(ctx, cudaEventRecord(f->ev_in, f->s_copy));
   f->pre_wait = f->ev_in;
   CU(ctx, cudaEventRecord(f->ev_src_ready, f->s_copy));
-  bw_status st = run_batch(f, sg.d_keys, sg.d_vals, sg.d_ts, rows, epoch);
+  bw_status st = run_batch(f, sg.d_keys, sg.d_vals, sg.d_ts, rows, epoch, &sg);
   if (st != BW_OK) return st;
-  CU(ctx, cudaEventRecord(sg.consumed, f->s_compute));
-  sg.used = true;
   // the pinned slot may be refilled once its H2D is done
   CU(ctx, cudaEventSynchronize(f->ev_h2d));
   sl.acquired = false;
@@ -1124,7 +1348,7 @@ bw_status bw_ingest_device(bw_fold* f, const uint64_t* d_keys, const void* d_val
   // multi-GPU: the caller's columns must already be complete (see bwgpu.h); no ordering with the fold's
   // stream is taken, so that this activation's exchange can overlap the previous activation's fold
   CU(ctx, cudaEventRecord(f->ev_src_ready, f->s_x));
-  return run_batch(f, d_keys, d_vals, d_ts_us, rows, epoch);
+  return run_batch(f, d_keys, d_vals, d_ts_us, rows, epoch, nullptr);
 }
 
 // ---------------------------------------------------------------------------
@@ -1134,10 +1358,9 @@ struct MaxI64 {
   __host__ __device__ __forceinline__ i64 operator()(const i64& a, const i64& b) const { return a > b ? a : b; }
 };
 
-static bw_status slow_path(bw_fold* f, const BatchView& bv, u64 total, u64 epoch_ord) {
+static bw_status slow_path(bw_fold* f, const BatchView& bv, u64 total, u64 epoch_ord, u32 batch_no) {
   bw_ctx* ctx = f->ctx;
   cudaStream_t s = f->s_compute;
-  const u32 batch_no = f->batch_no - 1;
   if (total == 0) return BW_OK;
   if (total > f->slow_cap) {
     void* old[] = {f->d_kflat, f->d_ksorted, f->d_tsflat, f->d_tssorted, f->d_prefmax, f->d_idx, f->d_idxsorted, f->d_late};
@@ -1287,7 +1510,9 @@ static bw_status collect(bw_fold* f, bw_emit* out) {
   const bool ordered = f->spec.emit_order == BW_ORDER_REFERENCE;
   const int grid = ctx->sm_count * 4;
   const u64 n_ord = f->have_pending ? (f->last_epoch - f->min_epoch + 1) : 1;
-  const bool sliding = f->p.panes_per_window > 1 || f->p.panes_per_offset > 1;
+  // the window-id pass orders a key's rows where the sequence column ties: sliding windows emitted from one
+  // pane, and folds whose sequence is just the closing activation (FoldParams::seq_by_id)
+  const bool sliding = f->p.panes_per_window > 1 || f->p.panes_per_offset > 1 || f->p.seq_by_id;
   auto ship = [&](u64 n, const u64* src, u64* dst, bool use_perm) -> bw_status {
     if (use_perm) {
       k_gather_u64<<<grid, 256, 0, s>>>(src, f->d_perm, f->d_gather, n);
@@ -1349,6 +1574,8 @@ bw_status bw_advance(bw_fold* f, uint64_t closed_epoch, int64_t system_now_us, b
   (void)system_now_us;
   if (!f || !out) return BW_ERR_SPEC;
   CU(f->ctx, cudaSetDevice(f->ctx->device));
+  bw_status st = stream_resolve(f);
+  if (st != BW_OK) return st;
   return collect(f, out);
 }
 
@@ -1357,9 +1584,13 @@ bw_status bw_eof(bw_fold* f, bw_emit* out) {
   bw_ctx* ctx = f->ctx;
   CU(ctx, cudaSetDevice(ctx->device));
   if (f->eof_done) FAIL(f, BW_ERR_STATE, "eof called twice");
+  {
+    bw_status st = stream_resolve(f);
+    if (st != BW_OK) return st;
+  }
   const u64 ord = f->last_epoch;
   if (!f->have_pending) { f->min_epoch = f->last_epoch; f->have_pending = true; }
-  k_close_all<<<f->close_grid, 256, 0, f->s_compute>>>(f->t, f->p, f->e, ord);
+  k_close_all<<<f->close_grid, 256, 0, f->s_compute>>>(f->t, f->p, f->e, ord, f->batch_no);
   CU(ctx, cudaGetLastError());
   f->st.kernel_launches++;
   f->eof_done = true;
@@ -1388,6 +1619,10 @@ bw_status bw_snapshot_take(bw_fold* f, bw_snapshot* out) {
   bw_ctx* ctx = f->ctx;
   CU(ctx, cudaSetDevice(ctx->device));
   if (f->eof_done) FAIL(f, BW_ERR_STATE, "snapshot after eof");
+  {
+    bw_status st = stream_resolve(f);
+    if (st != BW_OK) return st;
+  }
   cudaStream_t s = f->s_compute;
   if (f->s_x) CU(ctx, cudaStreamSynchronize(f->s_x));
   if (!f->d_snap_ctr) CU(ctx, dmalloc(&f->d_snap_ctr, 2));
@@ -1446,7 +1681,7 @@ bw_status bw_snapshot_load(bw_fold* f, const bw_snapshot* in) {
     k_snap_load<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(f->t, f->p, dc, n, (u32)in->batch_no, ctx->world, ctx->rank);
     CU(ctx, cudaGetLastError());
     // re-rank every restored key (newest pane into the hot slot); nothing is closable in a state dumped after an advance
-    k_close_dirty<<<f->close_grid, 256, 0, s>>>(f->t, f->p, f->e, in->last_epoch);
+    k_close_dirty<<<f->close_grid, 256, 0, s>>>(f->t, f->p, f->e, in->last_epoch, (u32)in->batch_no);
     k_reset_dirty<<<1, 1, 0, s>>>(f->t);
     f->st.kernel_launches += 3;
     CU(ctx, cudaStreamSynchronize(s));
@@ -1472,9 +1707,14 @@ static void drain_timers(bw_fold* f) {
   for (size_t i = 0; i < f->timers_used; ++i) {
     float ms = 0;
     if (cudaEventElapsedTime(&ms, f->timers[i].a, f->timers[i].b) == cudaSuccess) {
-      f->st.last_fold_ms = ms;
-      f->st.sum_fold_ms += ms;
-      f->st.fold_rows += f->timers[i].rows;
+      if (f->timers[i].kind == 1) {
+        f->st.sum_scatter_ms += ms;
+        f->st.scatter_launches++;
+      } else {
+        f->st.last_fold_ms = ms;
+        f->st.sum_fold_ms += ms;
+        f->st.fold_rows += f->timers[i].rows;
+      }
     }
   }
   f->timers_used = 0;
@@ -1483,6 +1723,10 @@ static void drain_timers(bw_fold* f) {
 bw_status bw_fold_stats(bw_fold* f, bw_stats* out) {
   if (!f || !out) return BW_ERR_SPEC;
   CU(f->ctx, cudaSetDevice(f->ctx->device));
+  {
+    bw_status st = stream_resolve(f);
+    if (st != BW_OK) return st;
+  }
   CU(f->ctx, cudaStreamSynchronize(f->s_compute));
   drain_timers(f);
   *out = f->st;
@@ -1490,8 +1734,14 @@ bw_status bw_fold_stats(bw_fold* f, bw_stats* out) {
 }
 bw_status bw_fold_reset_timers(bw_fold* f) {
   if (!f) return BW_ERR_SPEC;
+  {
+    bw_status st = stream_resolve(f);
+    if (st != BW_OK) return st;
+  }
   CU(f->ctx, cudaStreamSynchronize(f->s_compute));
   drain_timers(f);
+  f->st.sum_scatter_ms = 0;
+  f->st.scatter_launches = 0;
   f->st.sum_fold_ms = 0;
   f->st.last_fold_ms = 0;
   f->st.fold_rows = 0;
@@ -1502,6 +1752,10 @@ bw_status bw_fold_reset_timers(bw_fold* f) {
 bw_status bw_fold_sync(bw_fold* f) {
   if (!f) return BW_ERR_SPEC;
   CU(f->ctx, cudaSetDevice(f->ctx->device));
+  {
+    bw_status st = stream_resolve(f);
+    if (st != BW_OK) return st;
+  }
   CU(f->ctx, cudaStreamSynchronize(f->s_copy));
   CU(f->ctx, cudaStreamSynchronize(f->s_pre));
   CU(f->ctx, cudaStreamSynchronize(f->s_x));
@@ -1517,6 +1771,10 @@ bw_status bw_fold_time_begin(bw_fold* f) {
     CU(ctx, cudaEventCreate(&f->ev_t1));
   }
   // everything submitted so far (copies, prepass) must be done before the clock starts
+  {
+    bw_status st = stream_resolve(f);
+    if (st != BW_OK) return st;
+  }
   CU(ctx, cudaStreamSynchronize(f->s_copy));
   CU(ctx, cudaStreamSynchronize(f->s_pre));
   CU(ctx, cudaStreamSynchronize(f->s_x));
@@ -1527,6 +1785,10 @@ bw_status bw_fold_time_begin(bw_fold* f) {
 bw_status bw_fold_time_end(bw_fold* f, float* ms) {
   if (!f || !ms || !f->ev_t0) return BW_ERR_SPEC;
   bw_ctx* ctx = f->ctx;
+  {
+    bw_status st = stream_resolve(f);
+    if (st != BW_OK) return st;
+  }
   CU(ctx, cudaStreamSynchronize(f->s_copy));
   CU(ctx, cudaStreamSynchronize(f->s_pre));
   CU(ctx, cudaStreamSynchronize(f->s_x));

@@ -178,7 +178,10 @@ typedef struct bw_stats {
   float sum_fold_ms;        /* sum over fold kernels since bw_fold_create / reset */
   uint64_t fold_launches;
   uint64_t fold_rows;
-  uint64_t combined_folds;  /* fold launches that took the bucket + shared-memory combining path */
+  uint64_t combined_folds;  /* activations folded by the streaming path: bucket scatter + shared-memory segment fold */
+  float sum_scatter_ms;     /* CUDA-event time of the scatter + verdict stage of those activations */
+  float reserved0;
+  uint64_t scatter_launches;
 } bw_stats;
 
 /* ---- context ---------------------------------------------------------- */

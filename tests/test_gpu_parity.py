@@ -23,16 +23,12 @@ def ctx():
     c.close()
 
 
-@pytest.fixture(scope="module", params=["direct", "combine"], autouse=True)
+@pytest.fixture(scope="module", params=["stream", "direct"], autouse=True)
 def fold_mode(request):
-    """Every parity test runs twice: with the direct fold kernel and with the bucket + shared-memory combining
-    fold forced on for every clean activation (BW_SEG is read when a fold is created)."""
-    old = {k: os.environ.get(k) for k in ("BW_SEG", "BW_SEG_MIN_ROWS")}
-    if request.param == "combine":
-        os.environ["BW_SEG"] = "1"
-        os.environ["BW_SEG_MIN_ROWS"] = "0"
-    else:
-        os.environ["BW_SEG"] = "0"
+    """Every parity test runs twice: with the streaming path (fused verdict + bucket scatter, shared-memory segment
+    fold: the default) and with the direct hash-table kernel alone (BW_STREAM is read when a fold is created)."""
+    old = {k: os.environ.get(k) for k in ("BW_STREAM",)}
+    os.environ["BW_STREAM"] = "1" if request.param == "stream" else "0"
     yield request.param
     for k, v in old.items():
         if v is None:
@@ -156,7 +152,7 @@ def test_against_c_oracle_medium(ctx, fold_mode, red, length, offset, wait, jitt
     st = fold.stats()
     if jitter > (wait if wait is not None else 10**9):
         assert st.slow_batches > 0
-    if fold_mode == "combine" and wait is not None:
+    if fold_mode == "stream" and wait is not None:  # every clean activation took the streaming path
         assert st.combined_folds == st.fold_launches and st.fold_launches + st.slow_batches == len(batches)
     if fold_mode == "direct":
         assert st.combined_folds == 0
@@ -324,7 +320,7 @@ def test_c1_properties_and_sampled_parity(ctx, fold_mode):
     assert (per_window[:nfull] == L).all() and per_window.sum() == nb * B
     st = fold.stats()
     assert st.slow_batches == 0 and st.fold_launches >= nb
-    assert st.combined_folds == (nb if fold_mode == "combine" else 0)
+    assert st.combined_folds == (nb if fold_mode == "stream" else 0)
     ctx.dev_free(dk)
     ctx.dev_free(dv)
     fold.close()
