@@ -154,6 +154,7 @@ struct Table {
   u32* dirty;      // list of slot indices with possibly closable panes
   u64 cap;         // number of slots (a multiple of the segment size); slot `cap` is the BW_EMPTY_KEY alias slot
   u32 pool_cap;
+  u32 seg_shift;   // log2 of the segment size
   u32 seg_mask;    // segment size - 1 (power of two): linear probing wraps inside the segment of the home slot,
                    // so a block that owns a segment owns every key that hashes into it (bw_stream.cuh)
   // device counters
@@ -265,6 +266,80 @@ __device__ __forceinline__ void bw_red_max_u64(u64* p, u64 v) {
 }
 __device__ __forceinline__ void bw_red_min_u64(u64* p, u64 v) {
   asm volatile("red.global.relaxed.gpu.min.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// ---------------------------------------------------------------------------
+// Shared memory by 32-bit shared-window address.  Pointers into `extern __shared__` that travel
+// through structs or runtime-sized layouts lose their address space and compile to GENERIC loads
+// and atomics (LD.E / ATOM.E: measured 2x the instructions and none of the ATOMS throughput);
+// these keep every access an LDS / STS / ATOMS.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ u32 bw_smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ u64 bw_lds_u64(u32 a) {
+  u64 v;
+  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ u32 bw_lds_u32(u32 a) {
+  u32 v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void bw_lds_2u64(u32 a, u64& x, u64& y) {
+  asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(x), "=l"(y) : "r"(a) : "memory");
+}
+__device__ __forceinline__ void bw_lds_2u32(u32 a, u32& x, u32& y) {
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(x), "=r"(y) : "r"(a) : "memory");
+}
+__device__ __forceinline__ void bw_sts_u64(u32 a, u64 v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
+__device__ __forceinline__ void bw_sts_u32(u32 a, u32 v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ u64 bw_atoms_cas_u64(u32 a, u64 cmp, u64 val) {
+  u64 old;
+  asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(a), "l"(cmp), "l"(val) : "memory");
+  return old;
+}
+__device__ __forceinline__ u32 bw_atoms_add_u32(u32 a, u32 v) {
+  u32 old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ void bw_reds_add_u32(u32 a, u32 v) { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void bw_reds_or_u32(u32 a, u32 v) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void bw_reds_max_s32(u32 a, int v) { asm volatile("red.shared.max.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void bw_reds_min_u32(u32 a, u32 v) { asm volatile("red.shared.min.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void bw_reds_add_f64(u32 a, double v) { asm volatile("red.shared.add.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ void bw_reds_min_s64(u32 a, i64 v) { asm volatile("red.shared.min.s64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
+__device__ __forceinline__ void bw_reds_max_s64(u32 a, i64 v) { asm volatile("red.shared.max.s64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
+__device__ __forceinline__ void bw_reds_min_u64(u32 a, u64 v) { asm volatile("red.shared.min.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
+__device__ __forceinline__ void bw_reds_max_u64(u32 a, u64 v) { asm volatile("red.shared.max.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
+
+// mbarrier + 1-D bulk async copy (TMA, `cp.async.bulk`): global -> shared, completion counted in
+// bytes on an mbarrier.  SASS: UBLKCP / SYNCS.
+__device__ __forceinline__ void bw_mbar_init(u32 bar, u32 count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bw_mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void bw_mbar_expect_tx(u32 bar, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool bw_mbar_try_wait(u32 bar, u32 parity) {
+  u32 ok;
+  asm volatile(
+      "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void bw_mbar_wait(u32 bar, u32 parity) {
+  while (!bw_mbar_try_wait(bar, parity)) {
+  }
+}
+// size: multiple of 16 bytes; src / dst 16-byte aligned; streaming data: evict-first in L2
+__device__ __forceinline__ void bw_bulk_g2s(u32 dst, const void* src, u32 bytes, u32 bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar), "l"(bw_evict_first_policy())
+               : "memory");
 }
 
 __device__ __forceinline__ void bw_apply(int op, u64* acc, u64 operand) {

@@ -32,12 +32,13 @@
 #include "bw_common.cuh"
 #include "bw_fold.cuh"
 
-#define BW_SEG_SHIFT 11
-#define BW_SEG_SLOTS (1u << BW_SEG_SHIFT)  // slots per segment == per bucket
+#define BW_SEG_SHIFT_DEFAULT 11            // 2048 slots per segment == per bucket (env BW_SEG_SHIFT: 10..12)
 #define BW_STREAM_MAX_NB 8192              // buckets per table (beyond: the direct kernel)
 
-#define BW_SC_THREADS 256
+#define BW_SC_THREADS 512
 #define BW_SC_WARPS (BW_SC_THREADS / 32)
+#define BW_SC_TILE 2048                    // rows per scatter tile == rows per TMA stage
+#define BW_SC_RPT (BW_SC_TILE / BW_SC_THREADS)
 #define BW_SF_THREADS 512
 #define BW_SF_UNROLL 4
 
@@ -140,7 +141,9 @@ struct ScatterArgs {
   i64 *tile_min, *tile_max;
   u32* tile_bad;
   u64 cap;           // table capacity (slots)
+  u32 seg_shift;
   u32 batch_no;
+  u32 nstage;        // TMA stages in shared memory (2 or 3)
 };
 
 __device__ __forceinline__ void bw_spill_push(SpillRec* list, u32* n, u32 cap, u32* flags, u32 lost_flag, Counters* ctr, u64 key,
@@ -160,38 +163,34 @@ __device__ __forceinline__ void bw_spill_push(SpillRec* list, u32* n, u32 cap, u
   list[i] = r;
 }
 
-// value bits of one row as stored in the input column (f32 widened to its 32 raw bits in the low word)
-template <int VB_IN>
-__device__ __forceinline__ void bw_ld_val_pair(const void* vals, u64 row, bool both, u64& a, u64& b) {
-  a = 0;
-  b = 0;
-  if (VB_IN == 8) {
-    const u64* p = (const u64*)vals + row;
-    if (both) bw_ld_stream_2u64(p, a, b);
-    else a = bw_ld_stream_u64(p);
-  } else if (VB_IN == 4) {
-    const u32* p = (const u32*)vals + row;
-    u32 x = 0, y = 0;
-    if (both) bw_ld_stream_2u32(p, x, y);
-    else x = bw_ld_stream_u32(p);
-    a = x;
-    b = y;
-  }
+// shared-memory bytes of one TMA stage: the tile's key column, value column, ts column
+__host__ __device__ __forceinline__ u32 bw_scatter_stage_bytes(int tsm, int vb_in) {
+  return (u32)BW_SC_TILE * (8u + (u32)vb_in + (tsm == 0 ? 8u : 0u));
+}
+__host__ __device__ __forceinline__ size_t bw_scatter_smem(int tsm, int vb_in, u32 nstage, u32 nb) {
+  return 128 + (size_t)nstage * bw_scatter_stage_bytes(tsm, vb_in) + 3 * sizeof(u32) * (size_t)nb;
 }
 
 // TSM: 0 = ts column, 1 = ts from the (integer) value, 2 = none (the *_final folds).
 // VB_IN: bytes per entry of the value column read here (0: not read).  VB_OUT: value bytes stored beside
-// the records (0 for counts).  RPT rows per thread per tile (even).
-template <int TSM, int VB_IN, int VB_OUT, int RPT>
+// the records (0 for counts).
+//
+// Producer / consumer over shared memory: one thread keeps `nstage` tiles of the input columns in flight
+// with bulk async copies (TMA, completion on an mbarrier per stage); the block ranks and scatters the
+// tile that has landed.  The DRAM reads therefore never wait for the block's barriers.
+template <int TSM, int VB_IN, int VB_OUT>
 __global__ void __launch_bounds__(BW_SC_THREADS) k_scatter(ScatterArgs A, FoldParams p) {
-  extern __shared__ __align__(16) u32 sc_sm[];
-  u32* cnt = sc_sm;
-  u32* gbase = sc_sm + A.nb;
-  constexpr int NPAIR = RPT / 2;
-  constexpr int NCHUNK = NPAIR * BW_SC_WARPS;  // 64-row chunks per tile, in arrival order
+  extern __shared__ __align__(128) unsigned char sc_raw[];
+  constexpr u32 T = BW_SC_TILE;
+  constexpr int RPT = BW_SC_RPT, NPAIR = RPT / 2;
+  constexpr int NCHUNK = T / 64;  // 64-row chunks per tile, in arrival order
+  constexpr u32 COLB_K = T * 8, COLB_V = T * VB_IN;
+  constexpr u32 STAGE = COLB_K + COLB_V + (TSM == 0 ? T * 8 : 0);
   __shared__ i64 c_min[NCHUNK], c_max[NCHUNK];
   __shared__ u32 c_bad[NCHUNK];
-  constexpr u32 T = BW_SC_THREADS * RPT;
+  const u32 sbase = bw_smem_addr(sc_raw);
+  const u32 bars = sbase, stage0 = sbase + 128;
+  const u32 cnt = stage0 + A.nstage * STAGE, gb = cnt + A.nb * 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const u64 ntiles = (A.n + T - 1) / T;
   // base of the relative timestamps: event time of row 0
@@ -200,134 +199,209 @@ __global__ void __launch_bounds__(BW_SC_THREADS) k_scatter(ScatterArgs A, FoldPa
   else if (TSM == 1) ts0 = p.align_us + (i64)((const u64*)A.vals)[0];
   u32* flags = &A.out.sv->flags;
   u32* n_spill = &A.out.sv->n_spill;
-  for (u64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    for (u32 d = threadIdx.x; d < A.nb; d += BW_SC_THREADS) cnt[d] = 0u;
-    __syncthreads();
-    u64 key[RPT], val[VB_OUT ? RPT : 1];
-    u32 meta[RPT];  // bucket << 16 | rank inside (tile, bucket); 0xFFFFFFFF: not scattered
-    int rel[RPT];
+  auto issue = [&](u64 tile, u32 stage) {  // one thread
     const u64 tbase = tile * (u64)T;
+    const u32 rows = (u32)((A.n - tbase < (u64)T) ? A.n - tbase : (u64)T);
+    const u32 tr = rows & ~3u;  // whole 16-byte units of every column; the (< 4) rows left are read directly
+    const u32 bar = bars + 8 * stage, sk = stage0 + stage * STAGE;
+    bw_mbar_expect_tx(bar, tr * (8u + (u32)VB_IN + (TSM == 0 ? 8u : 0u)));
+    if (tr) {
+      bw_bulk_g2s(sk, A.keys + tbase, tr * 8, bar);
+      if (VB_IN) bw_bulk_g2s(sk + COLB_K, (const unsigned char*)A.vals + tbase * VB_IN, tr * VB_IN, bar);
+      if (TSM == 0) bw_bulk_g2s(sk + COLB_K + COLB_V, A.ts + tbase, tr * 8, bar);
+    }
+  };
+  if (threadIdx.x == 0) {
+    for (u32 s = 0; s < A.nstage; ++s) bw_mbar_init(bars + 8 * s, 1);
+    bw_mbar_fence_init();
+  }
+  for (u32 d = threadIdx.x; d < A.nb; d += BW_SC_THREADS) bw_sts_u32(cnt + 4 * d, 0u);
+  __syncthreads();
+  if (threadIdx.x == 0)
+    for (u32 s = 0; s < A.nstage; ++s) {
+      const u64 tile = blockIdx.x + (u64)s * gridDim.x;
+      if (tile < ntiles) issue(tile, s);
+    }
+  // Software pipeline over this block's tiles: iteration `it` ranks tile `it` (phase A), reserves its runs
+  // (phase B: the global atomics' round trip is not waited for) and writes out the records of tile `it - 1`
+  // (phase C), whose bases were reserved one iteration earlier.  Two block barriers per tile.
+  const u32 my_tiles = (ntiles > blockIdx.x) ? (u32)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
+  u32 meta_p[RPT], meta_c[RPT];  // bucket << 16 | rank inside (tile, bucket); 0xFFFFFFFF: not scattered
+  int rel_p[RPT], rel_c[RPT];
 #pragma unroll
-    for (int j = 0; j < NPAIR; ++j) {
-      const u64 row = tbase + 2ull * ((u64)j * BW_SC_THREADS + threadIdx.x);
-      const bool va = row < A.n, vb = row + 1 < A.n;
-      u64 ka = 0, kb = 0, xa = 0, xb = 0;
-      i64 ta = p.align_us, tb = p.align_us;
-      if (va) {
-        if (vb) bw_ld_stream_2u64(A.keys + row, ka, kb);
-        else ka = bw_ld_stream_u64(A.keys + row);
-        if (VB_IN) bw_ld_val_pair<VB_IN>(A.vals, row, vb, xa, xb);
-        if (TSM == 0) {
-          u64 a, b = 0;
-          if (vb) bw_ld_stream_2u64((const u64*)A.ts + row, a, b);
-          else a = bw_ld_stream_u64((const u64*)A.ts + row);
-          ta = (i64)a;
-          tb = (i64)b;
-        } else if (TSM == 1) {
+  for (int i = 0; i < RPT; ++i) {
+    meta_p[i] = 0xFFFFFFFFu;
+    rel_p[i] = 0;
+  }
+  for (u32 it = 0; it <= my_tiles; ++it) {
+    const bool have = it < my_tiles;
+    const u64 tile = blockIdx.x + (u64)it * gridDim.x;
+    const u32 stage = it % A.nstage;
+    const u32 sk = stage0 + stage * STAGE, sv = sk + COLB_K, st = sv + COLB_V;
+    const u64 tbase = tile * (u64)T;
+    const u32 rows = have ? (u32)((A.n - tbase < (u64)T) ? A.n - tbase : (u64)T) : 0u;
+    const u32 tr = rows & ~3u;
+    if (have) {
+      bw_mbar_wait(bars + 8 * stage, (it / A.nstage) & 1u);
+      // ---- phase A: bucket and rank of every row, lateness triple of every 64-row chunk ----
+#pragma unroll
+      for (int j = 0; j < NPAIR; ++j) {
+        const u32 r0 = 2u * ((u32)j * BW_SC_THREADS + threadIdx.x);  // row inside the tile
+        const bool va = r0 < rows, vb = r0 + 1 < rows;
+        u64 ka = 0, kb = 0, xa = 0, xb = 0;
+        i64 ta = p.align_us, tb = p.align_us;
+        if (r0 + 1 < tr) {
+          bw_lds_2u64(sk + r0 * 8, ka, kb);
+          if (VB_IN == 8) bw_lds_2u64(sv + r0 * 8, xa, xb);
+          if (VB_IN == 4) {
+            u32 x, y;
+            bw_lds_2u32(sv + r0 * 4, x, y);
+            xa = x;
+            xb = y;
+          }
+          if (TSM == 0) {
+            u64 a, b;
+            bw_lds_2u64(st + r0 * 8, a, b);
+            ta = (i64)a;
+            tb = (i64)b;
+          }
+        } else if (va) {  // the last (< 4) rows of the input
+          ka = A.keys[tbase + r0];
+          if (vb) kb = A.keys[tbase + r0 + 1];
+          if (VB_IN == 8) {
+            xa = ((const u64*)A.vals)[tbase + r0];
+            if (vb) xb = ((const u64*)A.vals)[tbase + r0 + 1];
+          }
+          if (VB_IN == 4) {
+            xa = ((const u32*)A.vals)[tbase + r0];
+            if (vb) xb = ((const u32*)A.vals)[tbase + r0 + 1];
+          }
+          if (TSM == 0) {
+            ta = A.ts[tbase + r0];
+            if (vb) tb = A.ts[tbase + r0 + 1];
+          }
+        }
+        if (TSM == 1) {
           ta = p.align_us + (i64)xa;
           tb = p.align_us + (i64)xb;
         }
-      }
-      key[2 * j] = ka;
-      key[2 * j + 1] = kb;
-      if (VB_OUT) {
-        val[VB_OUT ? 2 * j : 0] = xa;
-        val[VB_OUT ? 2 * j + 1 : 0] = xb;
-      }
-      // lateness triple of this warp's 64 consecutive rows
-      if (TSM != 2) {
-        const i64 nxt = __shfl_down_sync(0xffffffffu, ta, 1);
-        const bool ordered = va && vb && ta <= tb && (lane == 31 || tb <= nxt);
-        Trip ct;
-        if (__all_sync(0xffffffffu, ordered)) {
-          ct.mn = __shfl_sync(0xffffffffu, ta, 0);
-          ct.mx = __shfl_sync(0xffffffffu, tb, 31);
-          ct.bad = 0u;
-        } else {
-          ct = bw_trip_warp(bw_trip_cat(bw_trip_of(ta, va), bw_trip_of(tb, vb), p.wait_us), p.wait_us);
-          ct.mn = __shfl_sync(0xffffffffu, ct.mn, 31);
-          ct.mx = __shfl_sync(0xffffffffu, ct.mx, 31);
-          ct.bad = __shfl_sync(0xffffffffu, ct.bad, 31);
-        }
-        if (lane == 0) {
-          const int c = j * BW_SC_WARPS + warp;
-          c_min[c] = ct.mn;
-          c_max[c] = ct.mx;
-          c_bad[c] = ct.bad;
-        }
-      }
-      // bucket + rank
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const bool v = h ? vb : va;
-        const u64 k = h ? kb : ka;
-        const i64 t = h ? tb : ta;
-        u32 m = 0xFFFFFFFFu;
-        int r = 0;
-        if (v) {
-          const i64 d = t - ts0;
-          r = (int)d;
-          if (d != (i64)r || r == INT32_MIN || r == INT32_MAX) atomicOr(flags, BW_SV_RANGE);
-          if (k == BW_EMPTY_KEY) {
-            // the alias slot lives outside every segment: general path
-            const u64 x = h ? xb : xa;
-            u64 operand;
-            bw_operand(p, x, operand);
-            bw_spill_push(A.out.spill, n_spill, A.spill_cap, flags, BW_SV_LOST, nullptr, k, t, (p.op == BW_OP_ADD_ONE) ? 1ULL : operand,
-                          ((u64)A.batch_no << 32) | (row + h), 1ULL);
+        if (TSM != 2) {
+          const i64 nxt = __shfl_down_sync(0xffffffffu, ta, 1);
+          const bool ordered = va && vb && ta <= tb && (lane == 31 || tb <= nxt);
+          Trip ct;
+          if (__all_sync(0xffffffffu, ordered)) {
+            ct.mn = __shfl_sync(0xffffffffu, ta, 0);
+            ct.mx = __shfl_sync(0xffffffffu, tb, 31);
+            ct.bad = 0u;
           } else {
-            const u32 b = (u32)(bw_slot_of_hash(bw_mix64(k), A.cap) >> BW_SEG_SHIFT);
-            m = (b << 16) | atomicAdd(&cnt[b], 1u);
+            ct = bw_trip_warp(bw_trip_cat(bw_trip_of(ta, va), bw_trip_of(tb, vb), p.wait_us), p.wait_us);
+            ct.mn = __shfl_sync(0xffffffffu, ct.mn, 31);
+            ct.mx = __shfl_sync(0xffffffffu, ct.mx, 31);
+            ct.bad = __shfl_sync(0xffffffffu, ct.bad, 31);
+          }
+          if (lane == 0) {
+            const int c = j * BW_SC_WARPS + warp;
+            c_min[c] = ct.mn;
+            c_max[c] = ct.mx;
+            c_bad[c] = ct.bad;
           }
         }
-        meta[2 * j + h] = m;
-        rel[2 * j + h] = r;
-      }
-    }
-    __syncthreads();
-    // one reservation per (tile, bucket)
-    for (u32 d = threadIdx.x; d < A.nb; d += BW_SC_THREADS) {
-      const u32 c = cnt[d];
-      if (c) gbase[d] = atomicAdd(&A.out.cursor[d], c);
-    }
-    if (TSM != 2 && warp == 0) {
-      // triple of the tile: chunks in arrival order, NCHUNK / 32 per lane, then across the warp
-      constexpr int E = (NCHUNK + 31) / 32;
-      Trip tt = bw_trip_id();
 #pragma unroll
-      for (int e = 0; e < E; ++e) {
-        const int c = lane * E + e;
-        if (c < NCHUNK) tt = bw_trip_cat(tt, Trip{c_min[c], c_max[c], c_bad[c]}, p.wait_us);
-      }
-      tt = bw_trip_warp(tt, p.wait_us);
-      if (lane == 31) {
-        A.tile_min[tile] = tt.mn;
-        A.tile_max[tile] = tt.mx;
-        A.tile_bad[tile] = tt.bad;
+        for (int h = 0; h < 2; ++h) {
+          const bool v = h ? vb : va;
+          const u64 k = h ? kb : ka;
+          const i64 t = h ? tb : ta;
+          u32 m = 0xFFFFFFFFu;
+          int r = 0;
+          if (v) {
+            const i64 d = t - ts0;
+            r = (int)d;
+            if (d != (i64)r || r == INT32_MIN || r == INT32_MAX) atomicOr(flags, BW_SV_RANGE);
+            if (k == BW_EMPTY_KEY) {
+              // the alias slot lives outside every segment: general path
+              u64 operand;
+              bw_operand(p, h ? xb : xa, operand);
+              bw_spill_push(A.out.spill, n_spill, A.spill_cap, flags, BW_SV_LOST, nullptr, k, t, (p.op == BW_OP_ADD_ONE) ? 1ULL : operand,
+                            ((u64)A.batch_no << 32) | (tbase + r0 + h), 1ULL);
+            } else {
+              const u32 b = (u32)(bw_slot_of_hash(bw_mix64(k), A.cap) >> A.seg_shift);
+              m = (b << 16) | bw_atoms_add_u32(cnt + 4 * b, 1u);
+            }
+          }
+          meta_c[2 * j + h] = m;
+          rel_c[2 * j + h] = r;
+        }
       }
     }
     __syncthreads();
+    const u32 gb_c = gb + (it & 1u) * A.nb * 4, gb_p = gb + ((it & 1u) ^ 1u) * A.nb * 4;
+    if (have) {
+      // ---- phase B: one global reservation per (tile, bucket); triple of the tile ----
+      for (u32 d = threadIdx.x; d < A.nb; d += BW_SC_THREADS) {
+        const u32 c = bw_lds_u32(cnt + 4 * d);
+        if (c) {
+          bw_sts_u32(gb_c + 4 * d, atomicAdd(&A.out.cursor[d], c));
+          bw_sts_u32(cnt + 4 * d, 0u);
+        }
+      }
+      if (TSM != 2 && warp == 0) {
+        constexpr int E = (NCHUNK + 31) / 32;
+        Trip tt = bw_trip_id();
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const int c = lane * E + e;
+          if (c < NCHUNK && (u32)c * 64u < rows) tt = bw_trip_cat(tt, Trip{c_min[c], c_max[c], c_bad[c]}, p.wait_us);
+        }
+        tt = bw_trip_warp(tt, p.wait_us);
+        if (lane == 31) {
+          A.tile_min[tile] = tt.mn;
+          A.tile_max[tile] = tt.mx;
+          A.tile_bad[tile] = tt.bad;
+        }
+      }
+    }
+    if (it > 0) {
+      // ---- phase C: records of the previous tile out (its columns are read again from its stage) ----
+      const u32 pstage = (it - 1) % A.nstage;
+      const u32 psk = stage0 + pstage * STAGE, psv = psk + COLB_K;
+      const u64 ptbase = (blockIdx.x + (u64)(it - 1) * gridDim.x) * (u64)T;
+      const u32 prows = (u32)((A.n - ptbase < (u64)T) ? A.n - ptbase : (u64)T);
+      const u32 ptr = prows & ~3u;
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        const u32 m = meta_p[i];
+        if (m == 0xFFFFFFFFu) continue;
+        const u32 b = m >> 16;
+        const u32 pos = bw_lds_u32(gb_p + 4 * b) + (m & 0xFFFFu);
+        const u32 r = 2u * ((u32)(i >> 1) * BW_SC_THREADS + threadIdx.x) + (u32)(i & 1);
+        const u64 key = (r < ptr) ? bw_lds_u64(psk + r * 8) : A.keys[ptbase + r];
+        u64 x = 0;
+        if (VB_OUT == 8) x = (r < ptr) ? bw_lds_u64(psv + r * 8) : ((const u64*)A.vals)[ptbase + r];
+        if (VB_OUT == 4) x = (r < ptr) ? (u64)bw_lds_u32(psv + r * 4) : (u64)((const u32*)A.vals)[ptbase + r];
+        if (pos < A.region_cap) {
+          const size_t at = (size_t)b * A.region_cap + pos;
+          A.out.rec[at] = make_uint4((u32)key, (u32)(key >> 32), (u32)rel_p[i], (u32)(ptbase + r));
+          if (VB_OUT == 8) ((u64*)A.out.val)[at] = x;
+          else if (VB_OUT == 4) ((u32*)A.out.val)[at] = (u32)x;
+        } else {
+          // the bucket's region is full (skewed keys): general path for this row
+          u64 operand = 1ULL;
+          if (VB_OUT) bw_operand(p, x, operand);
+          bw_spill_push(A.out.spill, n_spill, A.spill_cap, flags, BW_SV_LOST, nullptr, key, ts0 + (i64)rel_p[i],
+                        (p.op == BW_OP_ADD_ONE) ? 1ULL : operand, ((u64)A.batch_no << 32) | (ptbase + r), 1ULL);
+        }
+      }
+    }
+    __syncthreads();  // the previous tile's stage is free; this tile's bases are published
+    if (it > 0 && threadIdx.x == 0) {
+      const u64 next = blockIdx.x + (u64)(it - 1 + A.nstage) * gridDim.x;
+      if (next < ntiles) issue(next, (it - 1) % A.nstage);
+    }
 #pragma unroll
     for (int i = 0; i < RPT; ++i) {
-      const u32 m = meta[i];
-      if (m == 0xFFFFFFFFu) continue;
-      const u32 b = m >> 16;
-      const u32 pos = gbase[b] + (m & 0xFFFFu);
-      const u64 row = tbase + 2ull * ((u64)(i >> 1) * BW_SC_THREADS + threadIdx.x) + (i & 1);
-      if (pos < A.region_cap) {
-        const size_t at = (size_t)b * A.region_cap + pos;
-        A.out.rec[at] = make_uint4((u32)key[i], (u32)(key[i] >> 32), (u32)rel[i], (u32)row);
-        if (VB_OUT == 8) ((u64*)A.out.val)[at] = val[VB_OUT ? i : 0];
-        else if (VB_OUT == 4) ((u32*)A.out.val)[at] = (u32)val[VB_OUT ? i : 0];
-      } else {
-        // the bucket's region is full (skewed keys): general path for this row
-        u64 operand = 1ULL;
-        if (VB_OUT) bw_operand(p, val[VB_OUT ? i : 0], operand);
-        bw_spill_push(A.out.spill, n_spill, A.spill_cap, flags, BW_SV_LOST, nullptr, key[i], ts0 + (i64)rel[i],
-                      (p.op == BW_OP_ADD_ONE) ? 1ULL : operand, ((u64)A.batch_no << 32) | row, 1ULL);
-      }
+      meta_p[i] = have ? meta_c[i] : 0xFFFFFFFFu;
+      rel_p[i] = rel_c[i];
     }
-    // cnt / gbase are rewritten two barriers from here: no barrier needed at the end of the tile
   }
 }
 
@@ -382,6 +456,7 @@ struct SegArgs {
   StreamSide in;
   u32 nb, region_cap, spill_cap;
   int val_bytes;
+  u32 seg_shift;
   i64 ts0;      // base of the records' relative timestamps
   i64 q_lo;     // pane of the activation's earliest timestamp
   u32 npass;    // the activation spans panes [q_lo, q_lo + 2 * npass): folded two panes at a time, closing in
@@ -390,51 +465,48 @@ struct SegArgs {
   u64 epoch;
 };
 
-// shared-memory accumulators of one segment: two local panes per slot
-template <typename DT>
-struct SegAcc {
-  u64* key;    // [S] key of the slot (BW_EMPTY_KEY: free)
-  DT* d[2];    // [S] delta of local pane 0 / 1
-  int* mts;    // [S] newest relative timestamp, INT32_MIN: untouched
-  u32* sq[2];  // [S] first arrival index per local pane (SEQ)
-  u32* cn[2];  // [S] value counts (CNT)
-  u32* tm;     // [S / 16] touched bits (2 per slot) for ops whose delta can equal the identity
-};
-
+// One accumulator op on a shared-memory delta (32-bit shared-window address)
 template <int OP>
 struct SegOp {
   static constexpr bool narrow = (OP == BW_OP_ADD_ONE);  // < 2^32 rows per activation: 32-bit deltas
-  typedef typename std::conditional<narrow, u32, u64>::type DT;
-  __device__ __forceinline__ static void apply(DT* a, u64 operand) {
+  static constexpr u32 DTB = narrow ? 4u : 8u;
+  __device__ __forceinline__ static void apply(u32 a, u64 operand) {
     if (OP == BW_OP_ADD_ONE) {
-      atomicAdd((u32*)a, 1u);
+      bw_reds_add_u32(a, 1u);
     } else if (OP == BW_OP_ADD_U64) {
       // exact 64-bit sum from two native 32-bit atomics: each add carries its own overflow up
       const u32 lo = (u32)operand, hi = (u32)(operand >> 32);
-      const u32 old = atomicAdd((u32*)a, lo);
+      const u32 old = bw_atoms_add_u32(a, lo);
       const u32 carry = ((u32)(old + lo) < old) ? 1u : 0u;
-      if (hi | carry) atomicAdd((u32*)a + 1, hi + carry);
+      if (hi | carry) bw_reds_add_u32(a + 4, hi + carry);
     } else if (OP == BW_OP_ADD_F64) {
-      atomicAdd((double*)a, __longlong_as_double((i64)operand));
+      bw_reds_add_f64(a, __longlong_as_double((i64)operand));
     } else if (OP == BW_OP_MIN_S64) {
-      atomicMin((long long*)a, (long long)operand);
+      bw_reds_min_s64(a, (i64)operand);
     } else if (OP == BW_OP_MIN_U64) {
-      atomicMin((unsigned long long*)a, (unsigned long long)operand);
+      bw_reds_min_u64(a, operand);
     } else if (OP == BW_OP_MAX_S64) {
-      atomicMax((long long*)a, (long long)operand);
+      bw_reds_max_s64(a, (i64)operand);
     } else {
-      atomicMax((unsigned long long*)a, (unsigned long long)operand);
+      bw_reds_max_u64(a, operand);
     }
+  }
+  __device__ __forceinline__ static u64 load(u32 a) { return narrow ? (u64)bw_lds_u32(a) : bw_lds_u64(a); }
+  __device__ __forceinline__ static void store(u32 a, u64 v) {
+    if (narrow) bw_sts_u32(a, (u32)v);
+    else bw_sts_u64(a, v);
   }
 };
 
-__host__ __device__ __forceinline__ size_t bw_segfold_smem(int op, bool seq, bool cnt) {
-  const size_t S = BW_SEG_SLOTS;
-  size_t b = S * 8 + S * 4;                          // keys, newest timestamp
-  b += 2 * S * (op == BW_OP_ADD_ONE ? 4 : 8);        // deltas
-  if (op != BW_OP_ADD_ONE) b += S / 16 * 4;          // touched bits
-  if (seq) b += 2 * S * 4;
-  if (cnt) b += 2 * S * 4;
+// shared-memory layout of one segment of S slots:
+//   keys u64[S] | delta pane 0, pane 1 (u32 or u64)[S] | newest relative ts i32[S] | touched bits u32[S/16]
+//   | first arrival index u32[S] x 2 (SEQ) | value counts u32[S] x 2 (CNT)
+__host__ __device__ __forceinline__ size_t bw_segfold_smem(u32 S, int op, bool seq, bool cnt) {
+  size_t b = (size_t)S * 8 + (size_t)S * 4;
+  b += 2 * (size_t)S * (op == BW_OP_ADD_ONE ? 4 : 8);
+  if (op != BW_OP_ADD_ONE) b += (size_t)S / 16 * 4;
+  if (seq) b += 2 * (size_t)S * 4;
+  if (cnt) b += 2 * (size_t)S * 4;
   return b;
 }
 
@@ -444,7 +516,7 @@ struct MPane {
   u64 acc, cnt, seq;
 };
 
-// The fold kernel proper.  C = FoldCfg<op, wm, cnt> (compile-time), SEQ: keep first-open indices
+// The fold kernel proper.  C = FoldCfg<op, -1, cnt> (compile-time op), SEQ: keep first-open indices
 // (folds whose emission order is not simply ascending window id).
 template <class C, bool SEQ>
 __global__ void __launch_bounds__(BW_SF_THREADS)
@@ -453,321 +525,318 @@ k_segfold(SegArgs A, Table t, FoldParams p, EmitBufs e) {
   constexpr bool CNT = C::kCnt != 0;
   const bool WM = p.track_wm != 0;
   typedef SegOp<OP> SO;
-  typedef typename SO::DT DT;
-  constexpr u32 S = BW_SEG_SLOTS;
+  constexpr u32 DTB = SO::DTB;
   extern __shared__ __align__(16) unsigned char sf_raw[];
   __shared__ DirtySink sink;
   __shared__ u32 sink_buf[512];
-  SegAcc<DT> sa;
-  {
-    unsigned char* q = sf_raw;
-    sa.key = (u64*)q;
-    q += S * 8;
-    sa.d[0] = (DT*)q;
-    q += S * sizeof(DT);
-    sa.d[1] = (DT*)q;
-    q += S * sizeof(DT);
-    sa.mts = (int*)q;
-    q += S * 4;
-    sa.tm = (u32*)q;
-    if (!SO::narrow) q += S / 16 * 4;
-    sa.sq[0] = (u32*)q;
-    if (SEQ) q += S * 4;
-    sa.sq[1] = (u32*)q;
-    if (SEQ) q += S * 4;
-    sa.cn[0] = (u32*)q;
-    if (CNT) q += S * 4;
-    sa.cn[1] = (u32*)q;
-  }
+  const u32 S = 1u << A.seg_shift, smask = S - 1;
+  const u32 a_key = bw_smem_addr(sf_raw);
+  const u32 a_d0 = a_key + S * 8, a_d1 = a_d0 + S * DTB;
+  const u32 a_mts = a_d1 + S * DTB;
+  const u32 a_tm = a_mts + S * 4;
+  const u32 a_sq0 = a_tm + (SO::narrow ? 0u : S / 16 * 4), a_sq1 = a_sq0 + (SEQ ? S * 4 : 0u);
+  const u32 a_cn0 = a_sq1 + (SEQ ? S * 4 : 0u), a_cn1 = a_cn0 + (CNT ? S * 4 : 0u);
   if (threadIdx.x == 0) {
     sink.n_dirty = 0;
     sink.n_new_keys = 0;
     sink.cap = 512;
     sink.buf = sink_buf;
   }
-  const DT ident = (OP <= BW_OP_ADD_F64) ? (DT)0 : (DT)p.acc_identity;
+  const u64 ident = (OP <= BW_OP_ADD_F64) ? 0ULL : p.acc_identity;
   const bool tumbling = p.panes_per_offset == 1 && p.panes_per_window == 1;
   for (u32 b = blockIdx.x; b < A.nb; b += gridDim.x) {
-    const u64 slot_base = (u64)b << BW_SEG_SHIFT;
+    const u64 slot_base = (u64)b << A.seg_shift;
     const u32 n = min(A.in.cursor[b], A.region_cap);
     __syncthreads();  // the previous segment's merge is done with shared memory
     if (n == 0) continue;  // uniform
-    for (u32 i = threadIdx.x; i < S; i += BW_SF_THREADS) sa.key[i] = t.hot[slot_base + i].key;
-    for (u32 pass = 0; pass < A.npass; ++pass) {
-    // relative start of the two local panes of this pass, and of the next pass
-    const i64 pb0 = p.align_us + (A.q_lo + 2 * (i64)pass) * p.pane_us - A.ts0, pb1 = pb0 + p.pane_us, pb2 = pb1 + p.pane_us;
-    const i64 q_pass = A.q_lo + 2 * (i64)pass;
-    __syncthreads();
-    for (u32 i = threadIdx.x; i < S; i += BW_SF_THREADS) {
-      sa.d[0][i] = ident;
-      sa.d[1][i] = ident;
-      sa.mts[i] = INT32_MIN;
-      if (!SO::narrow && i < S / 16) sa.tm[i] = 0u;
-      if (SEQ) {
-        sa.sq[0][i] = 0xFFFFFFFFu;
-        sa.sq[1][i] = 0xFFFFFFFFu;
-      }
-      if (CNT) {
-        sa.cn[0][i] = 0u;
-        sa.cn[1][i] = 0u;
-      }
-    }
-    __syncthreads();
-    // ---- events of the bucket ----
+    for (u32 i = threadIdx.x; i < S; i += BW_SF_THREADS) bw_sts_u64(a_key + 8 * i, t.hot[slot_base + i].key);
     const uint4* rec = A.in.rec + (size_t)b * A.region_cap;
-    for (u32 base = 0; base < n; base += BW_SF_THREADS * BW_SF_UNROLL) {
-      uint4 r[BW_SF_UNROLL];
-      u64 v[BW_SF_UNROLL];
-#pragma unroll
-      for (int u = 0; u < BW_SF_UNROLL; ++u) {
-        const u32 i = base + (u32)u * BW_SF_THREADS + threadIdx.x;
-        r[u] = make_uint4(0, 0, 0, 0);
-        v[u] = 0;
-        if (i < n) {
-          r[u] = bw_ld_stream_rec(rec + i);
-          if (OP != BW_OP_ADD_ONE) {
-            const size_t at = (size_t)b * A.region_cap + i;
-            v[u] = (A.val_bytes == 8) ? bw_ld_stream_u64((const u64*)A.in.val + at) : (u64)bw_ld_stream_u32((const u32*)A.in.val + at);
-          }
+    for (u32 pass = 0; pass < A.npass; ++pass) {
+      // relative start of the two local panes of this pass, and of the next pass
+      const i64 q_pass = A.q_lo + 2 * (i64)pass;
+      const i64 pb0 = p.align_us + q_pass * p.pane_us - A.ts0, pb1 = pb0 + p.pane_us, pb2 = pb1 + p.pane_us;
+      // the same bounds clamped into the records' 32-bit range: the per-event tests are 32-bit compares
+      const int lo32 = (A.npass > 1 && pb0 > (i64)INT32_MIN) ? (pb0 > (i64)INT32_MAX ? INT32_MAX : (int)pb0) : INT32_MIN;
+      const int mid32 = pb1 > (i64)INT32_MAX ? INT32_MAX : (pb1 < (i64)INT32_MIN ? INT32_MIN : (int)pb1);
+      const int hi32 = (A.npass > 1 && pb2 < (i64)INT32_MAX) ? (pb2 < (i64)INT32_MIN ? INT32_MIN : (int)pb2) : INT32_MAX;
+      __syncthreads();
+      for (u32 i = threadIdx.x; i < S; i += BW_SF_THREADS) {
+        SO::store(a_d0 + DTB * i, ident);
+        SO::store(a_d1 + DTB * i, ident);
+        bw_sts_u32(a_mts + 4 * i, (u32)INT32_MIN);
+        if (!SO::narrow && i < S / 16) bw_sts_u32(a_tm + 4 * i, 0u);
+        if (SEQ) {
+          bw_sts_u32(a_sq0 + 4 * i, 0xFFFFFFFFu);
+          bw_sts_u32(a_sq1 + 4 * i, 0xFFFFFFFFu);
+        }
+        if (CNT) {
+          bw_sts_u32(a_cn0 + 4 * i, 0u);
+          bw_sts_u32(a_cn1 + 4 * i, 0u);
         }
       }
+      __syncthreads();
+      // ---- events of the bucket ----
+      for (u32 base = 0; base < n; base += BW_SF_THREADS * BW_SF_UNROLL) {
+        uint4 r[BW_SF_UNROLL];
+        u64 v[BW_SF_UNROLL];
 #pragma unroll
-      for (int u = 0; u < BW_SF_UNROLL; ++u) {
-        const u32 i = base + (u32)u * BW_SF_THREADS + threadIdx.x;
-        if (i >= n) continue;
-        const u64 key = (u64)r[u].x | ((u64)r[u].y << 32);
-        const int rel = (int)r[u].z;
-        if (A.npass > 1 && ((i64)rel < pb0 || (i64)rel >= pb2)) continue;  // another pass's rows
-        u32 ls = (u32)bw_slot_of_hash(bw_mix64(key), t.cap) & (S - 1);
-        // find or claim the key's slot: linear probing inside the segment, in shared memory
-        bool found = false;
-        for (u32 probe = 0; probe < S; ++probe) {
-          const u64 k = ((volatile u64*)sa.key)[ls];
-          if (k == key) {
-            found = true;
-            break;
-          }
-          if (k == BW_EMPTY_KEY) {
-            const u64 old = atomicCAS((unsigned long long*)&sa.key[ls], (unsigned long long)BW_EMPTY_KEY, (unsigned long long)key);
-            if (old == BW_EMPTY_KEY || old == key) {
-              found = true;
-              break;
+        for (int u = 0; u < BW_SF_UNROLL; ++u) {
+          const u32 i = base + (u32)u * BW_SF_THREADS + threadIdx.x;
+          r[u] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0);  // no record: the empty key
+          v[u] = 0;
+          if (i < n) {
+            r[u] = bw_ld_stream_rec(rec + i);
+            if (OP != BW_OP_ADD_ONE) {
+              const size_t at = (size_t)b * A.region_cap + i;
+              v[u] = (A.val_bytes == 8) ? bw_ld_stream_u64((const u64*)A.in.val + at) : (u64)bw_ld_stream_u32((const u32*)A.in.val + at);
             }
           }
-          ls = (ls + 1) & (S - 1);
         }
-        if (!found) {
-          bw_raise(t.ctr, 3u);  // segment full: capacity_hint too small
-          continue;
-        }
-        const int j = ((i64)rel >= pb1) ? 1 : 0;
-        u64 operand = 0;
-        if (OP != BW_OP_ADD_ONE) bw_operand(p, v[u], operand);
-        SO::apply(&sa.d[j][ls], operand);
-        if (!SO::narrow) atomicOr(&sa.tm[ls >> 4], 1u << (2 * (ls & 15) + j));
-        atomicMax(&sa.mts[ls], rel);
-        if (SEQ) atomicMin(&sa.sq[j][ls], r[u].w);
-        if (CNT) atomicAdd(&sa.cn[j][ls], 1u);
-      }
-    }
-    __syncthreads();
-    // ---- merge: one thread per touched slot; the block owns the segment ----
-    for (u32 ls = threadIdx.x; ls < S; ls += BW_SF_THREADS) {
-      const int m = sa.mts[ls];
-      if (m == INT32_MIN) continue;
-      const u64 s = slot_base + ls;
-      const u64 key = sa.key[ls];
-      HotSlot h = t.hot[s];
-      if (h.key == BW_EMPTY_KEY) {
-        atomicAdd(&sink.n_new_keys, 1u);
-        h.key = key;
-      }
-      bool touched[2];
-      if (SO::narrow) {
-        touched[0] = sa.d[0][ls] != 0;
-        touched[1] = sa.d[1][ls] != 0;
-      } else {
-        const u32 bits = sa.tm[ls >> 4] >> (2 * (ls & 15));
-        touched[0] = bits & 1u;
-        touched[1] = bits & 2u;
-      }
-      const i64 ts_new = A.ts0 + (i64)m;  // newest event of the key in this activation
-      if (WM && ts_new > h.max_ts) h.max_ts = ts_new;
-      const i64 tag_in = h.wt0;
-      const bool had_p1 = (tag_in & BW_TAG_HAS_P1) != 0;
-      const u64 seq_hi = (u64)A.batch_no << 32;
-      bool done = false;
-      if (tumbling && !(tag_in & (BW_TAG_HAS_LIST | BW_TAG_DIRTY))) {
-        // Every pane of the key is at hand: close what the new watermark allows and re-rank,
-        // exactly what K4 (bw_close_key_simple) would do for it after the activation.  (A key
-        // already on the dirty list stays K4's: its entry there must meet the DIRTY bit again.)
-        MPane P[4];
-        int np = 0;
-        AuxSlot ax;
-        const bool need_aux = (SEQ || CNT) && tag_in != BW_EMPTY_WIDTAG;
-        if (need_aux) ax = t.aux[s];
-        if (tag_in != BW_EMPTY_WIDTAG) {
-          P[np++] = MPane{bw_widtag_q(tag_in), h.acc0, CNT ? ax.cnt0 : 0ULL, SEQ ? ax.seq0 : 0ULL};
-          if (had_p1) {
-            const P1Slot ps = t.p1[s];
-            P[np++] = MPane{bw_widtag_q1(tag_in), ps.acc1, CNT ? ax.cnt1 : 0ULL, ps.seq1};
+#pragma unroll
+        for (int u = 0; u < BW_SF_UNROLL; ++u) {
+          const u64 key = (u64)r[u].x | ((u64)r[u].y << 32);
+          const int rel = (int)r[u].z;
+          const bool valid = key != BW_EMPTY_KEY && rel >= lo32 && rel < hi32;  // a record, and of this pass
+          u32 ls = (u32)bw_slot_of_hash(bw_mix64(key), t.cap) & smask;
+          // Find or claim the key's slot: linear probing inside the segment, in shared memory.  The loop is
+          // warp-uniform (every lane stays until the last one has its slot) so that the accumulator updates
+          // below issue once per warp: left to diverge, each exit iteration ran them again for its few lanes
+          // (profiles/r02_segfold_divergence.md: 6.5 active lanes per instruction).
+          bool searching = valid, found = false;
+          u32 tries = 0;
+          while (__any_sync(0xffffffffu, searching)) {
+            if (searching) {
+              const u64 k = bw_lds_u64(a_key + 8 * ls);
+              bool hit = k == key;
+              if (!hit && k == BW_EMPTY_KEY) {
+                const u64 old = bw_atoms_cas_u64(a_key + 8 * ls, BW_EMPTY_KEY, key);
+                hit = old == BW_EMPTY_KEY || old == key;
+              }
+              if (hit) {
+                found = true;
+                searching = false;
+              } else {
+                ls = (ls + 1) & smask;
+                if (++tries >= S) searching = false;
+              }
+            }
+          }
+          if (valid && !found) bw_raise(t.ctr, 3u);  // segment full: capacity_hint too small
+          if (found) {
+            const u32 j = (rel >= mid32) ? 1u : 0u;
+            u64 operand = 0;
+            if (OP != BW_OP_ADD_ONE) bw_operand(p, v[u], operand);
+            SO::apply((j ? a_d1 : a_d0) + DTB * ls, operand);
+            if (!SO::narrow) bw_reds_or_u32(a_tm + 4 * (ls >> 4), 1u << (2 * (ls & 15) + j));
+            bw_reds_max_s32(a_mts + 4 * ls, rel);
+            if (SEQ) bw_reds_min_u32((j ? a_sq1 : a_sq0) + 4 * ls, r[u].w);
+            if (CNT) bw_reds_add_u32((j ? a_cn1 : a_cn0) + 4 * ls, 1u);
           }
         }
+      }
+      __syncthreads();
+      // ---- merge: one thread per touched slot; the block owns the segment ----
+      for (u32 ls = threadIdx.x; ls < S; ls += BW_SF_THREADS) {
+        const int m = (int)bw_lds_u32(a_mts + 4 * ls);
+        if (m == INT32_MIN) continue;
+        const u64 s = slot_base + ls;
+        const u64 key = bw_lds_u64(a_key + 8 * ls);
+        HotSlot h = t.hot[s];
+        if (h.key == BW_EMPTY_KEY) {
+          atomicAdd(&sink.n_new_keys, 1u);
+          h.key = key;
+        }
+        const u64 dv[2] = {SO::load(a_d0 + DTB * ls), SO::load(a_d1 + DTB * ls)};
+        bool touched[2];
+        if (SO::narrow) {
+          touched[0] = dv[0] != 0;
+          touched[1] = dv[1] != 0;
+        } else {
+          const u32 bits = bw_lds_u32(a_tm + 4 * (ls >> 4)) >> (2 * (ls & 15));
+          touched[0] = bits & 1u;
+          touched[1] = bits & 2u;
+        }
+        u64 dcn[2] = {0, 0}, dsq[2] = {0, 0};
+        if (CNT) {
+          dcn[0] = bw_lds_u32(a_cn0 + 4 * ls);
+          dcn[1] = bw_lds_u32(a_cn1 + 4 * ls);
+        }
+        const u64 seq_hi = (u64)A.batch_no << 32;
+        if (SEQ) {
+          dsq[0] = seq_hi | bw_lds_u32(a_sq0 + 4 * ls);
+          dsq[1] = seq_hi | bw_lds_u32(a_sq1 + 4 * ls);
+        }
+        const i64 ts_new = A.ts0 + (i64)m;  // newest event of the key in this pass
+        if (WM && ts_new > h.max_ts) h.max_ts = ts_new;
+        const i64 tag_in = h.wt0;
+        const bool had_p1 = (tag_in & BW_TAG_HAS_P1) != 0;
+        bool done = false;
+        if (tumbling && !(tag_in & (BW_TAG_HAS_LIST | BW_TAG_DIRTY))) {
+          // Every pane of the key is at hand: close what the new watermark allows and re-rank,
+          // exactly what K4 (bw_close_key_simple) would do for it after the activation.  (A key
+          // already on the dirty list stays K4's: its entry there must meet the DIRTY bit again.)
+          MPane P[4];
+          int np = 0;
+          AuxSlot ax;
+          const bool need_aux = (SEQ || CNT) && tag_in != BW_EMPTY_WIDTAG;
+          if (need_aux) ax = t.aux[s];
+          if (tag_in != BW_EMPTY_WIDTAG) {
+            P[np++] = MPane{bw_widtag_q(tag_in), h.acc0, CNT ? ax.cnt0 : 0ULL, SEQ ? ax.seq0 : 0ULL};
+            if (had_p1) {
+              const P1Slot ps = t.p1[s];
+              P[np++] = MPane{bw_widtag_q1(tag_in), ps.acc1, CNT ? ax.cnt1 : 0ULL, ps.seq1};
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            if (!touched[j]) continue;
+            const i64 q = q_pass + j;
+            int at = -1;
+            for (int i = 0; i < np; ++i)
+              if (P[i].q == q) at = i;
+            if (at < 0) {
+              P[np++] = MPane{q, bw_combine(OP, p.acc_identity, dv[j]), dcn[j], dsq[j]};
+            } else {
+              P[at].acc = bw_combine(OP, P[at].acc, dv[j]);
+              P[at].cnt += dcn[j];
+              if (dsq[j] < P[at].seq) P[at].seq = dsq[j];
+            }
+          }
+          i64 wm = INT64_MIN;
+          if (WM) {
+            wm = bw_sub_sat(h.max_ts, p.wait_us);
+            if (wm < BW_UTC_MIN_US_DEV) wm = BW_UTC_MIN_US_DEV;
+          }
+          // survivors: newest and second newest
+          int i0 = -1, i1 = -1, alive = 0;
+          bool range_ok = true;
+          for (int i = 0; i < np; ++i) {
+            if (P[i].q <= -BW_WID_LIMIT || P[i].q >= BW_WID_LIMIT) range_ok = false;
+            if (WM && wm >= bw_pane_release(P[i].q, p)) continue;
+            ++alive;
+            if (i0 < 0 || P[i].q > P[i0].q) {
+              i1 = i0;
+              i0 = i;
+            } else if (i1 < 0 || P[i].q > P[i1].q) {
+              i1 = i;
+            }
+          }
+          if (!range_ok) {
+            bw_raise(t.ctr, 6u);
+            continue;
+          }
+          if (alive <= 1 || (alive == 2 && P[i1].q == P[i0].q - 1)) {
+            for (int i = 0; i < np; ++i)
+              if (WM && wm >= bw_pane_release(P[i].q, p))
+                bw_emit_closed(e, t.ctr, key, P[i].q, bw_finish_acc(p, P[i].acc), P[i].cnt, p.seq_by_id ? (u64)A.batch_no : P[i].seq,
+                               A.epoch);
+            const bool both = alive == 2;
+            if (alive == 0) {
+              // no panes left: the reference discards the whole logic, watermark included (windowing.py:1110-1113)
+              h.max_ts = INT64_MIN;
+              h.wt0 = BW_EMPTY_WIDTAG;
+              h.acc0 = p.acc_identity;
+              if (SEQ || CNT) {
+                AuxSlot z = need_aux ? ax : t.aux[s];
+                z.seq0 = ~0ULL;
+                z.cnt0 = 0;
+                z.cnt1 = 0;
+                t.aux[s] = z;
+              }
+            } else {
+              h.wt0 = bw_pack_widtag(P[i0].q, both ? 1u : 0u, BW_TAG_STALE, both, both);
+              h.acc0 = P[i0].acc;
+              if (SEQ || CNT) {
+                AuxSlot z = need_aux ? ax : t.aux[s];
+                z.seq0 = P[i0].seq;
+                z.cnt0 = P[i0].cnt;
+                z.cnt1 = both ? P[i1].cnt : 0;
+                t.aux[s] = z;
+              }
+            }
+            if (both) {
+              P1Slot ps;
+              ps.acc1 = P[i1].acc;
+              ps.seq1 = SEQ ? P[i1].seq : 0ULL;  // present (any value but ~0)
+              t.p1[s] = ps;
+            } else if (had_p1) {
+              P1Slot ps;
+              ps.acc1 = p.acc_identity;
+              ps.seq1 = ~0ULL;
+              t.p1[s] = ps;
+            }
+            t.hot[s] = h;
+            done = true;
+          }
+        }
+        if (done) continue;
+        // General shape (sliding windows, an overflow list, or more survivors than the two direct
+        // panes hold): apply the deltas where the direct kernel would have, leave the closing to K4.
+        i64 tag0 = tag_in;
+        bool created = false;
+        AuxSlot ax = t.aux[s];
+        bool aux_dirty = false;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           if (!touched[j]) continue;
           const i64 q = q_pass + j;
-          const u64 d = (u64)sa.d[j][ls];
-          const u64 dc = CNT ? (u64)sa.cn[j][ls] : 0ULL;
-          const u64 ds = SEQ ? (seq_hi | sa.sq[j][ls]) : 0ULL;
-          int at = -1;
-          for (int i = 0; i < np; ++i)
-            if (P[i].q == q) at = i;
-          if (at < 0) {
-            P[np++] = MPane{q, bw_combine(OP, p.acc_identity, d), dc, ds};
-          } else {
-            P[at].acc = bw_combine(OP, P[at].acc, d);
-            P[at].cnt += dc;
-            if (ds < P[at].seq) P[at].seq = ds;
+          if (q <= -BW_WID_LIMIT || q >= BW_WID_LIMIT) {
+            bw_raise(t.ctr, 6u);
+            continue;
           }
-        }
-        i64 wm = INT64_MIN;
-        if (WM) {
-          wm = bw_sub_sat(h.max_ts, p.wait_us);
-          if (wm < BW_UTC_MIN_US_DEV) wm = BW_UTC_MIN_US_DEV;
-        }
-        // survivors: newest and second newest
-        int i0 = -1, i1 = -1, alive = 0;
-        bool range_ok = true;
-        for (int i = 0; i < np; ++i) {
-          if (P[i].q <= -BW_WID_LIMIT || P[i].q >= BW_WID_LIMIT) range_ok = false;
-          if (WM && wm >= bw_pane_release(P[i].q, p)) continue;
-          ++alive;
-          if (i0 < 0 || P[i].q > P[i0].q) {
-            i1 = i0;
-            i0 = i;
-          } else if (i1 < 0 || P[i].q > P[i1].q) {
-            i1 = i;
-          }
-        }
-        if (!range_ok) {
-          bw_raise(t.ctr, 6u);
-          continue;
-        }
-        if (alive <= 1 || (alive == 2 && P[i1].q == P[i0].q - 1)) {
-          for (int i = 0; i < np; ++i)
-            if (WM && wm >= bw_pane_release(P[i].q, p))
-              bw_emit_closed(e, t.ctr, key, P[i].q, bw_finish_acc(p, P[i].acc), P[i].cnt, p.seq_by_id ? (u64)A.batch_no : P[i].seq,
-                             A.epoch);
-          const bool both = alive == 2;
-          if (alive == 0) {
-            // no panes left: the reference discards the whole logic, watermark included (windowing.py:1110-1113)
-            h.max_ts = INT64_MIN;
-            h.wt0 = BW_EMPTY_WIDTAG;
+          const u64 d = dv[j], dc = dcn[j], ds = SEQ ? dsq[j] : seq_hi;
+          if (tag0 == BW_EMPTY_WIDTAG) {
+            const i64 a = p.panes_per_offset, bb = p.panes_per_window;
+            const i64 d0 = (a == 1) ? (bb - 1) : (q - a * bw_floordiv(q - bb + a, a));
+            tag0 = bw_pack_widtag(q, d0 > (i64)BW_TAG_DELTA_MAX ? BW_TAG_DELTA_MAX : (u32)d0, A.batch_no & 63u);
             h.acc0 = p.acc_identity;
-            if (SEQ || CNT) {
-              AuxSlot z = need_aux ? ax : t.aux[s];
-              z.seq0 = ~0ULL;
-              z.cnt0 = 0;
-              z.cnt1 = 0;
-              t.aux[s] = z;
-            }
-          } else {
-            h.wt0 = bw_pack_widtag(P[i0].q, both ? 1u : 0u, BW_TAG_STALE, both, both);
-            h.acc0 = P[i0].acc;
-            if (SEQ || CNT) {
-              AuxSlot z = need_aux ? ax : t.aux[s];
-              z.seq0 = P[i0].seq;
-              z.cnt0 = P[i0].cnt;
-              z.cnt1 = both ? P[i1].cnt : 0;
-              t.aux[s] = z;
-            }
+            ax.seq0 = ~0ULL;
+            created = true;
           }
-          if (both) {
-            P1Slot ps;
-            ps.acc1 = P[i1].acc;
-            ps.seq1 = SEQ ? P[i1].seq : 0ULL;  // present (any value but ~0)
+          if (bw_widtag_q(tag0) == q) {
+            h.acc0 = bw_combine(OP, h.acc0, d);
+            ax.cnt0 += dc;
+            if (((u32)tag0 & 0x7Fu) == (A.batch_no & 63u) && ds < ax.seq0) ax.seq0 = ds;
+            aux_dirty = true;
+          } else if (bw_widtag_q1(tag0) == q) {
+            P1Slot ps = t.p1[s];
+            ps.acc1 = bw_combine(OP, ps.acc1, d);
+            if (!(tag0 & BW_TAG_P1_PREV) && ds < ps.seq1) ps.seq1 = ds;
             t.p1[s] = ps;
-          } else if (had_p1) {
-            P1Slot ps;
-            ps.acc1 = p.acc_identity;
-            ps.seq1 = ~0ULL;
-            t.p1[s] = ps;
-          }
-          t.hot[s] = h;
-          done = true;
-        }
-      }
-      if (done) continue;
-      // General shape (sliding windows, an overflow list, or more survivors than the two direct
-      // panes hold): apply the deltas where the direct kernel would have, leave the closing to K4.
-      i64 tag0 = tag_in;
-      bool created = false;
-      AuxSlot ax = t.aux[s];
-      bool aux_dirty = false;
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        if (!touched[j]) continue;
-        const i64 q = q_pass + j;
-        if (q <= -BW_WID_LIMIT || q >= BW_WID_LIMIT) {
-          bw_raise(t.ctr, 6u);
-          continue;
-        }
-        const u64 d = (u64)sa.d[j][ls];
-        const u64 dc = CNT ? (u64)sa.cn[j][ls] : 0ULL;
-        const u64 ds = seq_hi | (SEQ ? sa.sq[j][ls] : 0u);
-        if (tag0 == BW_EMPTY_WIDTAG) {
-          const i64 a = p.panes_per_offset, bb = p.panes_per_window;
-          const i64 d0 = (a == 1) ? (bb - 1) : (q - a * bw_floordiv(q - bb + a, a));
-          tag0 = bw_pack_widtag(q, d0 > (i64)BW_TAG_DELTA_MAX ? BW_TAG_DELTA_MAX : (u32)d0, A.batch_no & 63u);
-          h.acc0 = p.acc_identity;
-          ax.seq0 = ~0ULL;
-          created = true;
-        }
-        if (bw_widtag_q(tag0) == q) {
-          h.acc0 = bw_combine(OP, h.acc0, d);
-          ax.cnt0 += dc;
-          if (((u32)tag0 & 0x7Fu) == (A.batch_no & 63u) && ds < ax.seq0) ax.seq0 = ds;
-          aux_dirty = true;
-        } else if (bw_widtag_q1(tag0) == q) {
-          P1Slot ps = t.p1[s];
-          ps.acc1 = bw_combine(OP, ps.acc1, d);
-          if (!(tag0 & BW_TAG_P1_PREV) && ds < ps.seq1) ps.seq1 = ds;
-          t.p1[s] = ps;
-          tag0 |= BW_TAG_HAS_P1;
-          ax.cnt1 += dc;
-          aux_dirty = true;
-        } else {
-          // a further pane: the overflow list, through the general path
-          const i64 ts_j = (j == 0 && ts_new >= A.ts0 + pb1) ? A.ts0 + pb1 - 1 : ts_new;
-          bw_spill_push(A.in.spill, &A.in.sv->n_spill, A.spill_cap, nullptr, 0u, t.ctr, key, ts_j, d, ds, dc);
-        }
-      }
-      // watermark / closability: what bw_after_fold decides per event, once per key
-      {
-        i64 rem;
-        const i64 qn = bw_pane_of_r(ts_new, p, rem);
-        bool mark = created;
-        if (WM && !mark) {
-          const u32 delta = bw_widtag_delta(tag0);
-          const i64 qc = qn - p.close_back - ((rem < p.wait_rem) ? 1 : 0);
-          mark = (delta == BW_TAG_DELTA_MAX) || (qc >= bw_widtag_q(tag0) - (i64)delta);
-        }
-        if (mark && !(tag0 & BW_TAG_DIRTY)) {
-          tag0 |= BW_TAG_DIRTY;
-          const u32 i = atomicAdd(&sink.n_dirty, 1u);
-          if (i < sink.cap) {
-            sink.buf[i] = (u32)s;
+            tag0 |= BW_TAG_HAS_P1;
+            ax.cnt1 += dc;
+            aux_dirty = true;
           } else {
-            const u32 g = atomicAdd(&t.ctr->dirty_count, 1u);
-            t.dirty[g] = (u32)s;
+            // a further pane: the overflow list, through the general path
+            const i64 ts_j = (j == 0 && ts_new >= A.ts0 + pb1) ? A.ts0 + pb1 - 1 : ts_new;
+            bw_spill_push(A.in.spill, &A.in.sv->n_spill, A.spill_cap, nullptr, 0u, t.ctr, key, ts_j, d, ds, dc);
           }
         }
+        // watermark / closability: what bw_after_fold decides per event, once per key
+        {
+          i64 rem;
+          const i64 qn = bw_pane_of_r(ts_new, p, rem);
+          bool mark = created;
+          if (WM && !mark) {
+            const u32 delta = bw_widtag_delta(tag0);
+            const i64 qc = qn - p.close_back - ((rem < p.wait_rem) ? 1 : 0);
+            mark = (delta == BW_TAG_DELTA_MAX) || (qc >= bw_widtag_q(tag0) - (i64)delta);
+          }
+          if (mark && !(tag0 & BW_TAG_DIRTY)) {
+            tag0 |= BW_TAG_DIRTY;
+            const u32 i = atomicAdd(&sink.n_dirty, 1u);
+            if (i < sink.cap) {
+              sink.buf[i] = (u32)s;
+            } else {
+              const u32 g = atomicAdd(&t.ctr->dirty_count, 1u);
+              t.dirty[g] = (u32)s;
+            }
+          }
+        }
+        h.wt0 = tag0;
+        if (aux_dirty && (SEQ || CNT || created)) t.aux[s] = ax;
+        t.hot[s] = h;
       }
-      h.wt0 = tag0;
-      if (aux_dirty && (SEQ || CNT || created)) t.aux[s] = ax;
-      t.hot[s] = h;
-    }
     }  // pass
     if (threadIdx.x == 0) A.in.cursor[b] = 0u;  // ready for the next scatter into this side
     __syncthreads();

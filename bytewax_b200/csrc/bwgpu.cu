@@ -199,7 +199,7 @@ struct bw_fold {
   scatter_kernel_t scatter_kernel = nullptr;
   segfold_kernel_t segfold_kernel = nullptr;
   size_t segfold_smem = 0, scatter_smem = 0;
-  int scatter_rpt = 16;
+  int scatter_nstage = 3;
   cudaEvent_t ev_sv[2] = {nullptr, nullptr};
   StreamVerdict* h_sv = nullptr;  // pinned mirror of the two sides' verdicts
   Deferred dq{};            // the activation whose fold has not been launched yet
@@ -439,22 +439,21 @@ static segfold_kernel_t pick_segfold_kernel(const FoldParams& p) {
   }
 }
 // k_scatter instantiations: timestamp source x value bytes read / stored
-static scatter_kernel_t pick_scatter_kernel(int tsm, int vb_in, int vb_out, int* rpt) {
-  *rpt = vb_out ? 8 : 16;
-  if (tsm == 1) return vb_out ? (scatter_kernel_t)k_scatter<1, 8, 8, 8> : (scatter_kernel_t)k_scatter<1, 8, 0, 16>;
+static scatter_kernel_t pick_scatter_kernel(int tsm, int vb_in, int vb_out) {
+  if (tsm == 1) return vb_out ? (scatter_kernel_t)k_scatter<1, 8, 8> : (scatter_kernel_t)k_scatter<1, 8, 0>;
   if (tsm == 0) {
-    if (!vb_out) return (scatter_kernel_t)k_scatter<0, 0, 0, 16>;
-    return vb_in == 4 ? (scatter_kernel_t)k_scatter<0, 4, 4, 8> : (scatter_kernel_t)k_scatter<0, 8, 8, 8>;
+    if (!vb_out) return (scatter_kernel_t)k_scatter<0, 0, 0>;
+    return vb_in == 4 ? (scatter_kernel_t)k_scatter<0, 4, 4> : (scatter_kernel_t)k_scatter<0, 8, 8>;
   }
-  if (!vb_out) return (scatter_kernel_t)k_scatter<2, 0, 0, 16>;
-  return vb_in == 4 ? (scatter_kernel_t)k_scatter<2, 4, 4, 8> : (scatter_kernel_t)k_scatter<2, 8, 8, 8>;
+  if (!vb_out) return (scatter_kernel_t)k_scatter<2, 0, 0>;
+  return vb_in == 4 ? (scatter_kernel_t)k_scatter<2, 4, 4> : (scatter_kernel_t)k_scatter<2, 8, 8>;
 }
 
 static bw_status stream_alloc(bw_fold* f) {
   bw_ctx* ctx = f->ctx;
   StreamBufs& sb = f->sb;
   const u64 rows = f->spec.max_batch_rows;
-  const u64 nb = f->t.cap >> BW_SEG_SHIFT;
+  const u64 nb = f->t.cap >> f->t.seg_shift;
   if (const char* e = getenv("BW_STREAM")) f->stream_mode = atoi(e) ? 1 : 0;
   if (!f->stream_mode || ctx->world != 1 || nb > BW_STREAM_MAX_NB || rows >= (1ULL << 32)) return BW_OK;
   // wait == forever with event time: nothing closes before EOF, every key grows an overflow list of panes --
@@ -484,21 +483,24 @@ static bw_status stream_alloc(bw_fold* f) {
   CU(ctx, cudaHostAlloc((void**)&f->h_sv, 2 * sizeof(StreamVerdict), cudaHostAllocDefault));
   const int tsm = f->p.ts_from_value ? f->p.ts_from_value : 0;
   const int vb_in = (tsm == 1) ? 8 : (sb.val_bytes ? f->val_bytes : 0);
-  f->scatter_kernel = pick_scatter_kernel(tsm, vb_in, sb.val_bytes, &f->scatter_rpt);
-  const u64 T = (u64)BW_SC_THREADS * f->scatter_rpt;
+  f->scatter_kernel = pick_scatter_kernel(tsm, vb_in, sb.val_bytes);
+  const u64 T = BW_SC_TILE;
   sb.tiles_cap = (u32)((rows + T - 1) / T + 1);
   CU(ctx, dmalloc(&sb.tile_min, sb.tiles_cap));
   CU(ctx, dmalloc(&sb.tile_max, sb.tiles_cap));
   CU(ctx, dmalloc(&sb.tile_bad, sb.tiles_cap));
-  f->scatter_smem = 2 * sizeof(u32) * sb.nb;
+  // TMA stages of the input tile: three when two blocks of that size still share an SM
+  f->scatter_nstage = (bw_scatter_smem(tsm, vb_in, 3, sb.nb) <= 110 * 1024) ? 3 : 2;
+  if (const char* e = getenv("BW_SC_STAGES")) f->scatter_nstage = std::max(2, std::min(4, atoi(e)));
+  f->scatter_smem = bw_scatter_smem(tsm, vb_in, f->scatter_nstage, sb.nb);
   // the attribute belongs to the kernel, not to this fold: folds with other table sizes share it
-  CU(ctx, cudaFuncSetAttribute((const void*)f->scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sizeof(u32) * BW_STREAM_MAX_NB)));
+  CU(ctx, cudaFuncSetAttribute((const void*)f->scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
   int occ = 0;
   CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)f->scatter_kernel, BW_SC_THREADS, f->scatter_smem));
   f->scatter_grid = ctx->sm_count * std::max(occ, 1);
   f->segfold_kernel = pick_segfold_kernel(f->p);
-  f->segfold_smem = bw_segfold_smem(f->p.op, !f->p.seq_by_id, f->p.need_count != 0);
-  CU(ctx, cudaFuncSetAttribute((const void*)f->segfold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->segfold_smem));
+  f->segfold_smem = bw_segfold_smem(1u << f->t.seg_shift, f->p.op, !f->p.seq_by_id, f->p.need_count != 0);
+  CU(ctx, cudaFuncSetAttribute((const void*)f->segfold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
   CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)f->segfold_kernel, BW_SF_THREADS, f->segfold_smem));
   f->segfold_grid = ctx->sm_count * std::max(occ, 1);
   f->stream_ok = true;
@@ -515,11 +517,15 @@ static bw_status fold_alloc(bw_fold* f) {
     int v = atoi(e);
     if (v >= 10 && v <= 90) load_pct = v;
   }
-  u64 cap = std::max<u64>(BW_SEG_SLOTS, (std::max<u64>(s.capacity_hint, 1) * 100 + load_pct - 1) / load_pct);
-  cap = (cap + BW_SEG_SLOTS - 1) & ~(u64)(BW_SEG_SLOTS - 1);
+  u32 seg_shift = BW_SEG_SHIFT_DEFAULT;
+  if (const char* e = getenv("BW_SEG_SHIFT")) seg_shift = (u32)std::max(10, std::min(12, atoi(e)));
+  const u64 seg_slots = 1ULL << seg_shift;
+  u64 cap = std::max<u64>(seg_slots, (std::max<u64>(s.capacity_hint, 1) * 100 + load_pct - 1) / load_pct);
+  cap = (cap + seg_slots - 1) & ~(seg_slots - 1);
   if (cap > (1ULL << 31)) FAIL(f, BW_ERR_SPEC, "capacity_hint too large");
   f->t.cap = cap;
-  f->t.seg_mask = BW_SEG_SLOTS - 1;
+  f->t.seg_shift = seg_shift;
+  f->t.seg_mask = (u32)seg_slots - 1;
   {
     // overflow pane nodes: panes a key can hold beyond its two direct slots
     const i64 per_window = f->p.panes_per_window;
@@ -1074,8 +1080,10 @@ static bw_status stream_front(bw_fold* f, const u64* d_keys, const void* d_vals,
   A.tile_max = sb.tile_max;
   A.tile_bad = sb.tile_bad;
   A.cap = f->t.cap;
+  A.seg_shift = f->t.seg_shift;
+  A.nstage = (u32)f->scatter_nstage;
   A.batch_no = batch_no;
-  const u64 T = (u64)BW_SC_THREADS * f->scatter_rpt;
+  const u64 T = BW_SC_TILE;
   const u64 ntiles = (rows + T - 1) / T;
   const int grid = (int)std::min<u64>(ntiles, (u64)f->scatter_grid);
   EventPair* ep = next_timer(f);
@@ -1128,6 +1136,7 @@ static bw_status stream_resolve(bw_fold* f) {
     A.region_cap = sb.region_cap;
     A.spill_cap = sb.spill_cap;
     A.val_bytes = sb.val_bytes;
+    A.seg_shift = f->t.seg_shift;
     A.ts0 = sv.ts0;
     A.q_lo = q_lo;
     A.npass = (u32)((q_hi - q_lo) / 2 + 1);
@@ -1138,6 +1147,21 @@ static bw_status stream_resolve(bw_fold* f) {
       ep->rows = d.rows;
       ep->kind = 0;
       CU(ctx, cudaEventRecord(ep->a, s));
+    }
+    if (getenv("BW_DEBUG_CURSOR")) {
+      std::vector<u32> hc(sb.nb);
+      cudaMemcpy(hc.data(), sb.side[d.side].cursor, sizeof(u32) * sb.nb, cudaMemcpyDeviceToHost);
+      u64 sum = 0;
+      u32 mn = ~0u, mx = 0, nz = 0;
+      for (u32 c : hc) {
+        sum += c;
+        mn = std::min(mn, c);
+        mx = std::max(mx, c);
+        nz += c != 0;
+      }
+      fprintf(stderr, "[bwgpu] batch %u: nb %u region_cap %u rows %llu cursor sum %llu min %u max %u nonzero %u spill %u flags %u span [%lld, %lld] ts0 %lld\n",
+              d.batch_no, sb.nb, sb.region_cap, (unsigned long long)d.rows, (unsigned long long)sum, mn, mx, nz, sv.n_spill, sv.flags,
+              (long long)sv.tmin, (long long)sv.tmax, (long long)sv.ts0);
     }
     const u32 n_pre = std::min<u32>(sv.n_spill, sb.spill_cap);  // rows the scatter set aside: fold them first
     if (n_pre) {
