@@ -23,6 +23,23 @@ __host__ __device__ __forceinline__ u64 bw_mix64(u64 z) {
 __host__ __device__ __forceinline__ u64 bw_splitmix64(u64 x) {
   return bw_mix64(x + 0x9E3779B97F4A7C15ULL);
 }
+// Table placement hash: two multiplies and a fold (~10 instructions against mix64's ~30; the fold stage is
+// instruction-issue bound).  Independent of the routing hash, so a rank's slice of the key space still
+// spreads over its whole table.
+__host__ __device__ __forceinline__ u64 bw_khash(u64 k) {
+  k *= 0x9E3779B97F4A7C15ULL;
+  k ^= k >> 32;
+  k *= 0xD6E8FEB86659FD93ULL;
+  return k;
+}
+// home slot of a table hash: high 32 bits scaled into [0, cap) (cap <= 2^31)
+__host__ __device__ __forceinline__ u64 bw_slot_of_khash(u64 h, u64 cap) {
+#ifdef __CUDA_ARCH__
+  return (u64)__umulhi((u32)(h >> 32), (u32)cap);
+#else
+  return ((h >> 32) * (u64)(u32)cap) >> 32;
+#endif
+}
 // owning rank: high 32 bits scaled into [0, world)
 __host__ __device__ __forceinline__ u32 bw_route_hash(u64 h, u32 world) {
   return (u32)(((h >> 32) * (u64)world) >> 32);
@@ -280,6 +297,12 @@ __device__ __forceinline__ u64 bw_lds_u64(u32 a) {
   asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory");
   return v;
 }
+// for polling a location another warp writes: ptxas may hoist a plain ld.shared out of a spin loop
+__device__ __forceinline__ u64 bw_lds_u64_volatile(u32 a) {
+  u64 v;
+  asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory");
+  return v;
+}
 __device__ __forceinline__ u32 bw_lds_u32(u32 a) {
   u32 v;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
@@ -332,8 +355,9 @@ __device__ __forceinline__ bool bw_mbar_try_wait(u32 bar, u32 parity) {
   return ok != 0;
 }
 __device__ __forceinline__ void bw_mbar_wait(u32 bar, u32 parity) {
-  while (!bw_mbar_try_wait(bar, parity)) {
-  }
+  // a bulk copy that never lands is a bug: trap (an error the host sees) rather than hang the device
+  for (u32 spin = 0; !bw_mbar_try_wait(bar, parity); ++spin)
+    if (spin > (1u << 26)) __trap();
 }
 // size: multiple of 16 bytes; src / dst 16-byte aligned; streaming data: evict-first in L2
 __device__ __forceinline__ void bw_bulk_g2s(u32 dst, const void* src, u32 bytes, u32 bar) {

@@ -92,7 +92,7 @@ __device__ __forceinline__ i64 bw_ld_i64_coherent(const i64* p) {
 }
 
 __device__ __forceinline__ u64 bw_home_slot(const Table& t, u64 key) {
-  return (key == BW_EMPTY_KEY) ? t.cap : bw_slot_of_hash(bw_mix64(key), t.cap);
+  return (key == BW_EMPTY_KEY) ? t.cap : bw_slot_of_khash(bw_khash(key), t.cap);
 }
 // Linear probing wraps inside the segment of the home slot (Table::seg_mask): slot number `i`
 // positions after `s` in probe order.

@@ -35,10 +35,10 @@
 #define BW_SEG_SHIFT_DEFAULT 11            // 2048 slots per segment == per bucket (env BW_SEG_SHIFT: 10..12)
 #define BW_STREAM_MAX_NB 8192              // buckets per table (beyond: the direct kernel)
 
-#define BW_SC_THREADS 512
+#define BW_SC_THREADS 1024
 #define BW_SC_WARPS (BW_SC_THREADS / 32)
-#define BW_SC_TILE 2048                    // rows per scatter tile == rows per TMA stage
-#define BW_SC_RPT (BW_SC_TILE / BW_SC_THREADS)
+#define BW_SC_TILE 2048                    // rows per scatter tile == rows per TMA stage: one 64-row chunk per warp
+
 #define BW_SF_THREADS 512
 #define BW_SF_UNROLL 4
 
@@ -62,15 +62,16 @@ struct StreamVerdict {
 #define BW_SV_LOST 2u    // the spill list overflowed during the scatter: rows were dropped from the buckets
 
 struct StreamSide {    // one of two alternating sets (scatter of b+1 is queued before the fold of b)
-  uint4* rec;          // [nb * region_cap]
-  void* val;           // [nb * region_cap] values (only folds that need them)
-  u32* cursor;         // [nb] rows per bucket; zero between activations
+  uint4* rec;          // [nb][nlanes][lane_cap] {key lo, key hi, ts - ts0, w}: w = arrival index (folds that need first-open
+                       // order), else the key's home slot inside its segment | 7-bit fingerprint << 16 (bw_rec_tag)
+  void* val;           // same shape: values (only folds that need them)
+  u32* cnt;            // [nb][nlanes] rows each scatter block put in its lane of each bucket (written whole by every scatter)
   SpillRec* spill;
   StreamVerdict* sv;   // device
 };
 struct StreamBufs {
   StreamSide side[2];
-  u32 nb, region_cap, spill_cap;
+  u32 nb, nlanes, lane_cap, spill_cap;  // every scatter block owns one lane of lane_cap rows in every bucket's region
   int val_bytes;       // value bytes stored beside the records: 0 (counts), 4 or 8
   i64 *tile_min, *tile_max;
   u32* tile_bad;
@@ -131,19 +132,28 @@ __device__ __forceinline__ uint4 bw_ld_stream_rec(const uint4* p) {
   return v;
 }
 
+// What a record carries for the segment fold when it does not need the arrival index: the home slot inside the
+// segment and a fingerprint (bit 7 set: a zero byte is a free slot) for the byte-parallel probe.
+__device__ __forceinline__ u32 bw_fp_of(u64 h) { return ((u32)(h >> 8) & 0x7Fu) | 0x80u; }
+__device__ __forceinline__ u32 bw_rec_tag(u64 h, u64 slot, u32 seg_mask) { return ((u32)slot & seg_mask) | (bw_fp_of(h) << 16); }
+
 struct ScatterArgs {
   const u64* keys;
   const void* vals;  // may be NULL (counts with a ts column)
   const i64* ts;     // NULL unless the fold has a ts column
   u64 n;
   StreamSide out;
-  u32 nb, region_cap, spill_cap;
+  u32 nb, nlanes, lane_cap, spill_cap;
   i64 *tile_min, *tile_max;
   u32* tile_bad;
   u64 cap;           // table capacity (slots)
   u32 seg_shift;
   u32 batch_no;
   u32 nstage;        // TMA stages in shared memory (2 or 3)
+  u32 rec_idx;       // 1: records carry the arrival index; 0: the slot / fingerprint tag
+  u32 dbg;           // diagnostics only (env BW_SC_DBG): 1 skip the record stores, 2 skip the position atomics, 4 skip the verdict
+  u32 stg_cap;       // records per bucket assembled in shared memory before they are written out (0: every record straight out)
+  u32 stg_every;     // ... every this many tiles
 };
 
 __device__ __forceinline__ void bw_spill_push(SpillRec* list, u32* n, u32 cap, u32* flags, u32 lost_flag, Counters* ctr, u64 key,
@@ -167,30 +177,42 @@ __device__ __forceinline__ void bw_spill_push(SpillRec* list, u32* n, u32 cap, u
 __host__ __device__ __forceinline__ u32 bw_scatter_stage_bytes(int tsm, int vb_in) {
   return (u32)BW_SC_TILE * (8u + (u32)vb_in + (tsm == 0 ? 8u : 0u));
 }
-__host__ __device__ __forceinline__ size_t bw_scatter_smem(int tsm, int vb_in, u32 nstage, u32 nb) {
-  return 128 + (size_t)nstage * bw_scatter_stage_bytes(tsm, vb_in) + 3 * sizeof(u32) * (size_t)nb;
+// barriers + stage-done counters | stages | per bucket: rows this block has put there (u32), rows of those already
+// written out (u32), and stg_cap records being assembled
+__host__ __device__ __forceinline__ size_t bw_scatter_smem(int tsm, int vb_in, u32 nstage, u32 nb, u32 stg_cap) {
+  return 128 + (size_t)nstage * bw_scatter_stage_bytes(tsm, vb_in) + (((size_t)nb * 8 + 15) & ~(size_t)15) + (size_t)nb * stg_cap * 16;
 }
 
 // TSM: 0 = ts column, 1 = ts from the (integer) value, 2 = none (the *_final folds).
 // VB_IN: bytes per entry of the value column read here (0: not read).  VB_OUT: value bytes stored beside
 // the records (0 for counts).
 //
-// Producer / consumer over shared memory: one thread keeps `nstage` tiles of the input columns in flight
-// with bulk async copies (TMA, completion on an mbarrier per stage); the block ranks and scatters the
-// tile that has landed.  The DRAM reads therefore never wait for the block's barriers.
+// No block barrier in the tile loop.  One thread keeps `nstage` tiles of the input columns in flight with
+// bulk async copies (TMA, completion counted on an mbarrier per stage); every WARP then handles its own 64
+// rows of the tile that has landed, start to finish: lateness triple of the chunk, and for each row the
+// bucket of its key, a position, and the 16-byte record store.  Every block owns a LANE of lane_cap rows in
+// every bucket's region, so a position is just a shared-memory counter: no global atomic, nobody to wait for,
+// nothing to pad (the fold reads each lane's row count).  A lane that fills up (skewed keys) overflows into
+// the spill list.  The last warp to finish with a stage refills it.
+//
+// Writing every 16-byte record straight to its lane costs the LSU one wavefront per ROW (32 lanes, 32 lines:
+// measured 0.21 ms of a 0.34 ms kernel).  So the records of a bucket are first assembled in shared memory,
+// stg_cap per bucket, and every stg_every tiles the block writes what it has assembled: eight lanes per bucket,
+// one 128-byte line per wavefront.  A bucket that outruns its staging rows writes those straight out.
 template <int TSM, int VB_IN, int VB_OUT>
-__global__ void __launch_bounds__(BW_SC_THREADS) k_scatter(ScatterArgs A, FoldParams p) {
+__global__ void __launch_bounds__(BW_SC_THREADS, 1) k_scatter(ScatterArgs A, FoldParams p) {
   extern __shared__ __align__(128) unsigned char sc_raw[];
   constexpr u32 T = BW_SC_TILE;
-  constexpr int RPT = BW_SC_RPT, NPAIR = RPT / 2;
-  constexpr int NCHUNK = T / 64;  // 64-row chunks per tile, in arrival order
   constexpr u32 COLB_K = T * 8, COLB_V = T * VB_IN;
   constexpr u32 STAGE = COLB_K + COLB_V + (TSM == 0 ? T * 8 : 0);
-  __shared__ i64 c_min[NCHUNK], c_max[NCHUNK];
-  __shared__ u32 c_bad[NCHUNK];
+  // lateness triples of the tiles in flight: [2 * nstage tiles][one per warp], combined by the tile's last warp
+  __shared__ i64 c_min[8][BW_SC_WARPS], c_max[8][BW_SC_WARPS];
+  __shared__ u32 c_bad[8][BW_SC_WARPS], c_done[8];
   const u32 sbase = bw_smem_addr(sc_raw);
-  const u32 bars = sbase, stage0 = sbase + 128;
-  const u32 cnt = stage0 + A.nstage * STAGE, gb = cnt + A.nb * 4;
+  const u32 bars = sbase, done = sbase + 64, stage0 = sbase + 128;
+  const u32 lcur = stage0 + A.nstage * STAGE;  // u32[nb]: rows this block has put in each bucket
+  const u32 fbase = lcur + A.nb * 4;           // u32[nb]: ... of which already written to the lane
+  const u32 stg = fbase + (((A.nb * 8 + 15) & ~15u) - A.nb * 4);  // uint4[nb][stg_cap]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const u64 ntiles = (A.n + T - 1) / T;
   // base of the relative timestamps: event time of row 0
@@ -199,6 +221,7 @@ __global__ void __launch_bounds__(BW_SC_THREADS) k_scatter(ScatterArgs A, FoldPa
   else if (TSM == 1) ts0 = p.align_us + (i64)((const u64*)A.vals)[0];
   u32* flags = &A.out.sv->flags;
   u32* n_spill = &A.out.sv->n_spill;
+  const u32 seg_mask = (1u << A.seg_shift) - 1u;
   auto issue = [&](u64 tile, u32 stage) {  // one thread
     const u64 tbase = tile * (u64)T;
     const u32 rows = (u32)((A.n - tbase < (u64)T) ? A.n - tbase : (u64)T);
@@ -212,196 +235,187 @@ __global__ void __launch_bounds__(BW_SC_THREADS) k_scatter(ScatterArgs A, FoldPa
     }
   };
   if (threadIdx.x == 0) {
-    for (u32 s = 0; s < A.nstage; ++s) bw_mbar_init(bars + 8 * s, 1);
+    for (u32 s = 0; s < A.nstage; ++s) {
+      bw_mbar_init(bars + 8 * s, 1);
+      bw_sts_u32(done + 4 * s, 0u);
+    }
+    for (int s = 0; s < 8; ++s) c_done[s] = 0u;
     bw_mbar_fence_init();
   }
-  for (u32 d = threadIdx.x; d < A.nb; d += BW_SC_THREADS) bw_sts_u32(cnt + 4 * d, 0u);
+  for (u32 d = threadIdx.x; d < A.nb; d += BW_SC_THREADS) {
+    bw_sts_u32(lcur + 4 * d, 0u);
+    bw_sts_u32(fbase + 4 * d, 0u);
+  }
+  const u32 my_tiles = (ntiles > blockIdx.x) ? (u32)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
   __syncthreads();
   if (threadIdx.x == 0)
     for (u32 s = 0; s < A.nstage; ++s) {
       const u64 tile = blockIdx.x + (u64)s * gridDim.x;
       if (tile < ntiles) issue(tile, s);
     }
-  // Software pipeline over this block's tiles: iteration `it` ranks tile `it` (phase A), reserves its runs
-  // (phase B: the global atomics' round trip is not waited for) and writes out the records of tile `it - 1`
-  // (phase C), whose bases were reserved one iteration earlier.  Two block barriers per tile.
-  const u32 my_tiles = (ntiles > blockIdx.x) ? (u32)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
-  u32 meta_p[RPT], meta_c[RPT];  // bucket << 16 | rank inside (tile, bucket); 0xFFFFFFFF: not scattered
-  int rel_p[RPT], rel_c[RPT];
-#pragma unroll
-  for (int i = 0; i < RPT; ++i) {
-    meta_p[i] = 0xFFFFFFFFu;
-    rel_p[i] = 0;
-  }
-  for (u32 it = 0; it <= my_tiles; ++it) {
-    const bool have = it < my_tiles;
-    const u64 tile = blockIdx.x + (u64)it * gridDim.x;
+  u32 it = 0;
+  for (u64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
     const u32 stage = it % A.nstage;
     const u32 sk = stage0 + stage * STAGE, sv = sk + COLB_K, st = sv + COLB_V;
     const u64 tbase = tile * (u64)T;
-    const u32 rows = have ? (u32)((A.n - tbase < (u64)T) ? A.n - tbase : (u64)T) : 0u;
+    const u32 rows = (u32)((A.n - tbase < (u64)T) ? A.n - tbase : (u64)T);
     const u32 tr = rows & ~3u;
-    if (have) {
-      bw_mbar_wait(bars + 8 * stage, (it / A.nstage) & 1u);
-      // ---- phase A: bucket and rank of every row, lateness triple of every 64-row chunk ----
-#pragma unroll
-      for (int j = 0; j < NPAIR; ++j) {
-        const u32 r0 = 2u * ((u32)j * BW_SC_THREADS + threadIdx.x);  // row inside the tile
-        const bool va = r0 < rows, vb = r0 + 1 < rows;
-        u64 ka = 0, kb = 0, xa = 0, xb = 0;
-        i64 ta = p.align_us, tb = p.align_us;
-        if (r0 + 1 < tr) {
-          bw_lds_2u64(sk + r0 * 8, ka, kb);
-          if (VB_IN == 8) bw_lds_2u64(sv + r0 * 8, xa, xb);
-          if (VB_IN == 4) {
-            u32 x, y;
-            bw_lds_2u32(sv + r0 * 4, x, y);
-            xa = x;
-            xb = y;
-          }
-          if (TSM == 0) {
-            u64 a, b;
-            bw_lds_2u64(st + r0 * 8, a, b);
-            ta = (i64)a;
-            tb = (i64)b;
-          }
-        } else if (va) {  // the last (< 4) rows of the input
-          ka = A.keys[tbase + r0];
-          if (vb) kb = A.keys[tbase + r0 + 1];
-          if (VB_IN == 8) {
-            xa = ((const u64*)A.vals)[tbase + r0];
-            if (vb) xb = ((const u64*)A.vals)[tbase + r0 + 1];
-          }
-          if (VB_IN == 4) {
-            xa = ((const u32*)A.vals)[tbase + r0];
-            if (vb) xb = ((const u32*)A.vals)[tbase + r0 + 1];
-          }
-          if (TSM == 0) {
-            ta = A.ts[tbase + r0];
-            if (vb) tb = A.ts[tbase + r0 + 1];
-          }
-        }
-        if (TSM == 1) {
-          ta = p.align_us + (i64)xa;
-          tb = p.align_us + (i64)xb;
-        }
-        if (TSM != 2) {
-          const i64 nxt = __shfl_down_sync(0xffffffffu, ta, 1);
-          const bool ordered = va && vb && ta <= tb && (lane == 31 || tb <= nxt);
-          Trip ct;
-          if (__all_sync(0xffffffffu, ordered)) {
-            ct.mn = __shfl_sync(0xffffffffu, ta, 0);
-            ct.mx = __shfl_sync(0xffffffffu, tb, 31);
-            ct.bad = 0u;
-          } else {
-            ct = bw_trip_warp(bw_trip_cat(bw_trip_of(ta, va), bw_trip_of(tb, vb), p.wait_us), p.wait_us);
-            ct.mn = __shfl_sync(0xffffffffu, ct.mn, 31);
-            ct.mx = __shfl_sync(0xffffffffu, ct.mx, 31);
-            ct.bad = __shfl_sync(0xffffffffu, ct.bad, 31);
-          }
-          if (lane == 0) {
-            const int c = j * BW_SC_WARPS + warp;
-            c_min[c] = ct.mn;
-            c_max[c] = ct.mx;
-            c_bad[c] = ct.bad;
-          }
-        }
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const bool v = h ? vb : va;
-          const u64 k = h ? kb : ka;
-          const i64 t = h ? tb : ta;
-          u32 m = 0xFFFFFFFFu;
-          int r = 0;
-          if (v) {
-            const i64 d = t - ts0;
-            r = (int)d;
-            if (d != (i64)r || r == INT32_MIN || r == INT32_MAX) atomicOr(flags, BW_SV_RANGE);
-            if (k == BW_EMPTY_KEY) {
-              // the alias slot lives outside every segment: general path
-              u64 operand;
-              bw_operand(p, h ? xb : xa, operand);
-              bw_spill_push(A.out.spill, n_spill, A.spill_cap, flags, BW_SV_LOST, nullptr, k, t, (p.op == BW_OP_ADD_ONE) ? 1ULL : operand,
-                            ((u64)A.batch_no << 32) | (tbase + r0 + h), 1ULL);
-            } else {
-              const u32 b = (u32)(bw_slot_of_hash(bw_mix64(k), A.cap) >> A.seg_shift);
-              m = (b << 16) | bw_atoms_add_u32(cnt + 4 * b, 1u);
-            }
-          }
-          meta_c[2 * j + h] = m;
-          rel_c[2 * j + h] = r;
-        }
+    bw_mbar_wait(bars + 8 * stage, (it / A.nstage) & 1u);
+    const u32 r0 = 2u * threadIdx.x;  // this thread's two rows of the tile
+    const bool va = r0 < rows, vb = r0 + 1 < rows;
+    u64 ka = 0, kb = 0, xa = 0, xb = 0;
+    i64 ta = p.align_us, tb = p.align_us;
+    if (r0 + 1 < tr) {
+      bw_lds_2u64(sk + r0 * 8, ka, kb);
+      if (VB_IN == 8) bw_lds_2u64(sv + r0 * 8, xa, xb);
+      if (VB_IN == 4) {
+        u32 x, y;
+        bw_lds_2u32(sv + r0 * 4, x, y);
+        xa = x;
+        xb = y;
+      }
+      if (TSM == 0) {
+        u64 a, b;
+        bw_lds_2u64(st + r0 * 8, a, b);
+        ta = (i64)a;
+        tb = (i64)b;
+      }
+    } else if (va) {  // the last (< 4) rows of the input
+      ka = A.keys[tbase + r0];
+      if (vb) kb = A.keys[tbase + r0 + 1];
+      if (VB_IN == 8) {
+        xa = ((const u64*)A.vals)[tbase + r0];
+        if (vb) xb = ((const u64*)A.vals)[tbase + r0 + 1];
+      }
+      if (VB_IN == 4) {
+        xa = ((const u32*)A.vals)[tbase + r0];
+        if (vb) xb = ((const u32*)A.vals)[tbase + r0 + 1];
+      }
+      if (TSM == 0) {
+        ta = A.ts[tbase + r0];
+        if (vb) tb = A.ts[tbase + r0 + 1];
       }
     }
-    __syncthreads();
-    const u32 gb_c = gb + (it & 1u) * A.nb * 4, gb_p = gb + ((it & 1u) ^ 1u) * A.nb * 4;
-    if (have) {
-      // ---- phase B: one global reservation per (tile, bucket); triple of the tile ----
-      for (u32 d = threadIdx.x; d < A.nb; d += BW_SC_THREADS) {
-        const u32 c = bw_lds_u32(cnt + 4 * d);
-        if (c) {
-          bw_sts_u32(gb_c + 4 * d, atomicAdd(&A.out.cursor[d], c));
-          bw_sts_u32(cnt + 4 * d, 0u);
+    if (TSM == 1) {
+      ta = p.align_us + (i64)xa;
+      tb = p.align_us + (i64)xb;
+    }
+    // the columns are in registers: this warp is done with the stage; the last warp to say so refills it
+    __syncwarp();
+    if (lane == 0) {
+      // (no fence: the loads above and this atomic go down the same shared-memory pipe in order; a fence here
+      // would also wait for the thread's record stores of the previous tile to be acknowledged)
+      if (bw_atoms_add_u32(done + 4 * stage, 1u) == BW_SC_WARPS - 1) {
+        bw_sts_u32(done + 4 * stage, 0u);
+        const u64 next = tile + (u64)A.nstage * gridDim.x;
+        if (next < ntiles) issue(next, stage);
+      }
+    }
+    // lateness triple of this warp's 64 consecutive rows; the last warp of the tile concatenates the tile's
+    if (TSM != 2 && !(A.dbg & 4u)) {
+      Trip ct = bw_trip_id();
+      if ((u32)warp * 64u < rows) {
+        const i64 nxt = __shfl_down_sync(0xffffffffu, ta, 1);
+        const bool ordered = va && vb && ta <= tb && (lane == 31 || tb <= nxt);
+        if (__all_sync(0xffffffffu, ordered)) {
+          ct.mn = __shfl_sync(0xffffffffu, ta, 0);
+          ct.mx = __shfl_sync(0xffffffffu, tb, 31);
+          ct.bad = 0u;
+        } else {
+          ct = bw_trip_warp(bw_trip_cat(bw_trip_of(ta, va), bw_trip_of(tb, vb), p.wait_us), p.wait_us);
+          ct.mn = __shfl_sync(0xffffffffu, ct.mn, 31);
+          ct.mx = __shfl_sync(0xffffffffu, ct.mx, 31);
+          ct.bad = __shfl_sync(0xffffffffu, ct.bad, 31);
         }
       }
-      if (TSM != 2 && warp == 0) {
-        constexpr int E = (NCHUNK + 31) / 32;
-        Trip tt = bw_trip_id();
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-          const int c = lane * E + e;
-          if (c < NCHUNK && (u32)c * 64u < rows) tt = bw_trip_cat(tt, Trip{c_min[c], c_max[c], c_bad[c]}, p.wait_us);
-        }
-        tt = bw_trip_warp(tt, p.wait_us);
+      const u32 ring = it % (2u * A.nstage);  // a warp is never nstage tiles ahead of another: 2 * nstage slots never collide
+      u32 last = 0;
+      if (lane == 0) {
+        ((volatile i64*)c_min[ring])[warp] = ct.mn;
+        ((volatile i64*)c_max[ring])[warp] = ct.mx;
+        ((volatile u32*)c_bad[ring])[warp] = ct.bad;
+        last = atomicAdd(&c_done[ring], 1u) == BW_SC_WARPS - 1 ? 1u : 0u;  // same pipe, in order, after the three stores
+      }
+      last = __shfl_sync(0xffffffffu, last, 0);
+      if (last) {
+        Trip tt = bw_trip_warp(Trip{((volatile i64*)c_min[ring])[lane], ((volatile i64*)c_max[ring])[lane], ((volatile u32*)c_bad[ring])[lane]},
+                               p.wait_us);
         if (lane == 31) {
           A.tile_min[tile] = tt.mn;
           A.tile_max[tile] = tt.mx;
           A.tile_bad[tile] = tt.bad;
+          c_done[ring] = 0u;
         }
       }
     }
-    if (it > 0) {
-      // ---- phase C: records of the previous tile out (its columns are read again from its stage) ----
-      const u32 pstage = (it - 1) % A.nstage;
-      const u32 psk = stage0 + pstage * STAGE, psv = psk + COLB_K;
-      const u64 ptbase = (blockIdx.x + (u64)(it - 1) * gridDim.x) * (u64)T;
-      const u32 prows = (u32)((A.n - ptbase < (u64)T) ? A.n - ptbase : (u64)T);
-      const u32 ptr = prows & ~3u;
+    // bucket of each row and its position in this block's lane there; record out
 #pragma unroll
-      for (int i = 0; i < RPT; ++i) {
-        const u32 m = meta_p[i];
-        if (m == 0xFFFFFFFFu) continue;
-        const u32 b = m >> 16;
-        const u32 pos = bw_lds_u32(gb_p + 4 * b) + (m & 0xFFFFu);
-        const u32 r = 2u * ((u32)(i >> 1) * BW_SC_THREADS + threadIdx.x) + (u32)(i & 1);
-        const u64 key = (r < ptr) ? bw_lds_u64(psk + r * 8) : A.keys[ptbase + r];
-        u64 x = 0;
-        if (VB_OUT == 8) x = (r < ptr) ? bw_lds_u64(psv + r * 8) : ((const u64*)A.vals)[ptbase + r];
-        if (VB_OUT == 4) x = (r < ptr) ? (u64)bw_lds_u32(psv + r * 4) : (u64)((const u32*)A.vals)[ptbase + r];
-        if (pos < A.region_cap) {
-          const size_t at = (size_t)b * A.region_cap + pos;
-          A.out.rec[at] = make_uint4((u32)key, (u32)(key >> 32), (u32)rel_p[i], (u32)(ptbase + r));
+    for (int h = 0; h < 2; ++h) {
+      const bool v = h ? vb : va;
+      if (!v) continue;
+      const u64 k = h ? kb : ka;
+      const u64 x = h ? xb : xa;
+      const i64 t = h ? tb : ta;
+      const u64 row = tbase + r0 + h;
+      const i64 d = t - ts0;
+      const int rel = (int)d;
+      if (d != (i64)rel || rel == INT32_MIN || rel == INT32_MAX) atomicOr(flags, BW_SV_RANGE);
+      bool stored = false;
+      if (k != BW_EMPTY_KEY) {  // (the alias slot lives outside every segment: general path)
+        const u64 hh = bw_khash(k);
+        const u64 slot = bw_slot_of_khash(hh, A.cap);
+        const u32 b = (u32)(slot >> A.seg_shift);
+        const u32 pos = (A.dbg & 2u) ? (u32)(row & 7u) : bw_atoms_add_u32(lcur + 4 * b, 1u);
+        const uint4 rec4 = make_uint4((u32)k, (u32)(k >> 32), (u32)rel, A.rec_idx ? (u32)row : bw_rec_tag(hh, slot, seg_mask));
+        const u32 soff = pos - bw_lds_u32(fbase + 4 * b);  // rows of the bucket since the last write-out
+        if (A.dbg & 1u) stored = true;
+        else if (VB_OUT == 0 && soff < A.stg_cap && pos < A.lane_cap) {
+          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(stg + 16 * (b * A.stg_cap + soff)), "r"(rec4.x), "r"(rec4.y), "r"(rec4.z),
+                       "r"(rec4.w)
+                       : "memory");
+          stored = true;
+        } else if (pos < A.lane_cap) {
+          const size_t at = ((size_t)b * A.nlanes + blockIdx.x) * A.lane_cap + pos;
+          A.out.rec[at] = rec4;
           if (VB_OUT == 8) ((u64*)A.out.val)[at] = x;
           else if (VB_OUT == 4) ((u32*)A.out.val)[at] = (u32)x;
-        } else {
-          // the bucket's region is full (skewed keys): general path for this row
-          u64 operand = 1ULL;
-          if (VB_OUT) bw_operand(p, x, operand);
-          bw_spill_push(A.out.spill, n_spill, A.spill_cap, flags, BW_SV_LOST, nullptr, key, ts0 + (i64)rel_p[i],
-                        (p.op == BW_OP_ADD_ONE) ? 1ULL : operand, ((u64)A.batch_no << 32) | (ptbase + r), 1ULL);
+          stored = true;
         }
       }
+      if (!stored) {
+        u64 operand = 1ULL;
+        if (VB_IN) bw_operand(p, x, operand);
+        bw_spill_push(A.out.spill, n_spill, A.spill_cap, flags, BW_SV_LOST, nullptr, k, t, (p.op == BW_OP_ADD_ONE) ? 1ULL : operand,
+                      ((u64)A.batch_no << 32) | row, 1ULL);
+      }
     }
-    __syncthreads();  // the previous tile's stage is free; this tile's bases are published
-    if (it > 0 && threadIdx.x == 0) {
-      const u64 next = blockIdx.x + (u64)(it - 1 + A.nstage) * gridDim.x;
-      if (next < ntiles) issue(next, (it - 1) % A.nstage);
+    // every stg_every tiles (and after the last): write out what the buckets have assembled
+    if (VB_OUT == 0 && A.stg_cap && ((it + 1) % A.stg_every == 0 || it + 1 == my_tiles)) {
+      __syncthreads();
+      for (u32 bb = (u32)warp * 4; bb < A.nb; bb += BW_SC_WARPS * 4) {  // uniform trip count per warp: four buckets at a time
+        const u32 b = bb + ((u32)lane >> 3);
+        u32 c = 0;
+        if (b < A.nb) {
+          const u32 fb = bw_lds_u32(fbase + 4 * b);
+          c = bw_lds_u32(lcur + 4 * b);
+          const u32 nrec = min(c - fb, A.stg_cap);
+          for (u32 r = (u32)lane & 7u; r < nrec && fb + r < A.lane_cap; r += 8) {
+            uint4 v;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(stg + 16 * (b * A.stg_cap + r)) : "memory");
+            A.out.rec[((size_t)b * A.nlanes + blockIdx.x) * A.lane_cap + fb + r] = v;
+          }
+        }
+        __syncwarp();
+        if (b < A.nb && ((u32)lane & 7u) == 0) bw_sts_u32(fbase + 4 * b, c);
+      }
+      __syncthreads();
     }
-#pragma unroll
-    for (int i = 0; i < RPT; ++i) {
-      meta_p[i] = have ? meta_c[i] : 0xFFFFFFFFu;
-      rel_p[i] = rel_c[i];
-    }
+  }
+  // rows in each of this block's lanes
+  __syncthreads();
+  for (u32 b = threadIdx.x; b < A.nb; b += BW_SC_THREADS) {
+    const u32 c = bw_lds_u32(lcur + 4 * b);
+    A.out.cnt[(size_t)b * A.nlanes + blockIdx.x] = c < A.lane_cap ? c : A.lane_cap;
   }
 }
 
@@ -454,7 +468,8 @@ __global__ void k_verdict_none(FoldParams p, Counters* ctr, StreamVerdict* sv) {
 // ---------------------------------------------------------------------------
 struct SegArgs {
   StreamSide in;
-  u32 nb, region_cap, spill_cap;
+  u32 nb, nlanes, lane_cap, spill_cap;
+  u32 nlanes_used;  // blocks of the scatter that filled this side
   int val_bytes;
   u32 seg_shift;
   i64 ts0;      // base of the records' relative timestamps
@@ -499,10 +514,10 @@ struct SegOp {
 };
 
 // shared-memory layout of one segment of S slots:
-//   keys u64[S] | delta pane 0, pane 1 (u32 or u64)[S] | newest relative ts i32[S] | touched bits u32[S/16]
+//   keys u64[S] | fingerprints u8[S] | delta pane 0, pane 1 (u32 or u64)[S] | newest relative ts i32[S] | touched bits u32[S/16]
 //   | first arrival index u32[S] x 2 (SEQ) | value counts u32[S] x 2 (CNT)
 __host__ __device__ __forceinline__ size_t bw_segfold_smem(u32 S, int op, bool seq, bool cnt) {
-  size_t b = (size_t)S * 8 + (size_t)S * 4;
+  size_t b = (size_t)S * 8 + (size_t)S + (size_t)S * 4;
   b += 2 * (size_t)S * (op == BW_OP_ADD_ONE ? 4 : 8);
   if (op != BW_OP_ADD_ONE) b += (size_t)S / 16 * 4;
   if (seq) b += 2 * (size_t)S * 4;
@@ -531,7 +546,8 @@ k_segfold(SegArgs A, Table t, FoldParams p, EmitBufs e) {
   __shared__ u32 sink_buf[512];
   const u32 S = 1u << A.seg_shift, smask = S - 1;
   const u32 a_key = bw_smem_addr(sf_raw);
-  const u32 a_d0 = a_key + S * 8, a_d1 = a_d0 + S * DTB;
+  const u32 a_fp = a_key + S * 8;  // one byte per slot: 0 == free, else 0x80 | 7 hash bits of the key in the slot
+  const u32 a_d0 = a_fp + S, a_d1 = a_d0 + S * DTB;
   const u32 a_mts = a_d1 + S * DTB;
   const u32 a_tm = a_mts + S * 4;
   const u32 a_sq0 = a_tm + (SO::narrow ? 0u : S / 16 * 4), a_sq1 = a_sq0 + (SEQ ? S * 4 : 0u);
@@ -546,11 +562,18 @@ k_segfold(SegArgs A, Table t, FoldParams p, EmitBufs e) {
   const bool tumbling = p.panes_per_offset == 1 && p.panes_per_window == 1;
   for (u32 b = blockIdx.x; b < A.nb; b += gridDim.x) {
     const u64 slot_base = (u64)b << A.seg_shift;
-    const u32 n = min(A.in.cursor[b], A.region_cap);
     __syncthreads();  // the previous segment's merge is done with shared memory
-    if (n == 0) continue;  // uniform
-    for (u32 i = threadIdx.x; i < S; i += BW_SF_THREADS) bw_sts_u64(a_key + 8 * i, t.hot[slot_base + i].key);
-    const uint4* rec = A.in.rec + (size_t)b * A.region_cap;
+    for (u32 i = threadIdx.x; i < S / 4; i += BW_SF_THREADS) {  // four slots per thread: one 32-bit word of fingerprints
+      u32 w = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const u64 key = t.hot[slot_base + 4 * i + k].key;
+        bw_sts_u64(a_key + 8 * (4 * i + k), key);
+        if (key != BW_EMPTY_KEY) w |= bw_fp_of(bw_khash(key)) << (8 * k);
+      }
+      bw_sts_u32(a_fp + 4 * i, w);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (u32 pass = 0; pass < A.npass; ++pass) {
       // relative start of the two local panes of this pass, and of the next pass
       const i64 q_pass = A.q_lo + 2 * (i64)pass;
@@ -575,19 +598,23 @@ k_segfold(SegArgs A, Table t, FoldParams p, EmitBufs e) {
         }
       }
       __syncthreads();
-      // ---- events of the bucket ----
-      for (u32 base = 0; base < n; base += BW_SF_THREADS * BW_SF_UNROLL) {
+      // ---- events of the bucket: its lanes (one per scatter block) are dealt to the warps round-robin ----
+      for (u32 ln = (u32)warp; ln < A.nlanes_used; ln += BW_SF_THREADS / 32) {
+      const size_t lane_base = ((size_t)b * A.nlanes + ln) * A.lane_cap;
+      const u32 n = min(A.in.cnt[(size_t)b * A.nlanes + ln], A.lane_cap);
+      const uint4* rec = A.in.rec + lane_base;
+      for (u32 base = 0; base < n; base += 32 * BW_SF_UNROLL) {
         uint4 r[BW_SF_UNROLL];
         u64 v[BW_SF_UNROLL];
 #pragma unroll
         for (int u = 0; u < BW_SF_UNROLL; ++u) {
-          const u32 i = base + (u32)u * BW_SF_THREADS + threadIdx.x;
+          const u32 i = base + (u32)u * 32 + (u32)lane;
           r[u] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0);  // no record: the empty key
           v[u] = 0;
           if (i < n) {
             r[u] = bw_ld_stream_rec(rec + i);
             if (OP != BW_OP_ADD_ONE) {
-              const size_t at = (size_t)b * A.region_cap + i;
+              const size_t at = lane_base + i;
               v[u] = (A.val_bytes == 8) ? bw_ld_stream_u64((const u64*)A.in.val + at) : (u64)bw_ld_stream_u32((const u32*)A.in.val + at);
             }
           }
@@ -597,27 +624,70 @@ k_segfold(SegArgs A, Table t, FoldParams p, EmitBufs e) {
           const u64 key = (u64)r[u].x | ((u64)r[u].y << 32);
           const int rel = (int)r[u].z;
           const bool valid = key != BW_EMPTY_KEY && rel >= lo32 && rel < hi32;  // a record, and of this pass
-          u32 ls = (u32)bw_slot_of_hash(bw_mix64(key), t.cap) & smask;
-          // Find or claim the key's slot: linear probing inside the segment, in shared memory.  The loop is
-          // warp-uniform (every lane stays until the last one has its slot) so that the accumulator updates
-          // below issue once per warp: left to diverge, each exit iteration ran them again for its few lanes
-          // (profiles/r02_segfold_divergence.md: 6.5 active lanes per instruction).
+          u32 ls, fp;
+          if (SEQ) {  // the 4th word is the arrival index: hash here
+            const u64 hh = bw_khash(key);
+            ls = (u32)bw_slot_of_khash(hh, t.cap) & smask;
+            fp = bw_fp_of(hh);
+          } else {
+            ls = r[u].w & smask;
+            fp = (r[u].w >> 16) & 0xFFu;
+          }
+          // Find or claim the key's slot.  Linear probing from the home slot, wrapping inside the segment, is the
+          // table's placement rule (bw_find_slot); here it is walked 16 slots at a time: one LDS.128 brings the
+          // fingerprint bytes of an aligned window, byte-parallel compares give the candidate and the free
+          // positions, and only a candidate's 8-byte key is read.  The loop is warp-uniform (every lane stays until
+          // the last one has its slot) so that the accumulator updates below issue once per warp.
+          const u32 fp4 = fp * 0x01010101u;
+          u32 wb = ls & ~15u;                 // window base
+          u32 ahead = 0xFFFFu << (ls & 15u);  // positions of the window at or after the home slot
           bool searching = valid, found = false;
           u32 tries = 0;
           while (__any_sync(0xffffffffu, searching)) {
             if (searching) {
-              const u64 k = bw_lds_u64(a_key + 8 * ls);
-              bool hit = k == key;
-              if (!hit && k == BW_EMPTY_KEY) {
-                const u64 old = bw_atoms_cas_u64(a_key + 8 * ls, BW_EMPTY_KEY, key);
-                hit = old == BW_EMPTY_KEY || old == key;
+              u32 w0, w1, w2, w3;
+              asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(a_fp + wb) : "memory");
+              // free positions: bytes with bit 7 clear; matches: zero bytes of (word ^ fingerprint x 4), exact
+              auto zmask = [](u32 x) { return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu); };  // 0x80 per zero byte
+              auto pack4 = [](u32 m80) { return (m80 * 0x00204081u) >> 28; };                                // -> 4 bits
+              const u32 freem = (pack4(~w0 & 0x80808080u) | (pack4(~w1 & 0x80808080u) << 4) | (pack4(~w2 & 0x80808080u) << 8) |
+                                 (pack4(~w3 & 0x80808080u) << 12)) & ahead;
+              u32 cand = (pack4(zmask(w0 ^ fp4)) | (pack4(zmask(w1 ^ fp4)) << 4) | (pack4(zmask(w2 ^ fp4)) << 8) |
+                          (pack4(zmask(w3 ^ fp4)) << 12)) & ahead;
+              // the key, if present, sits before the first free position of its probe sequence
+              if (freem) cand &= (freem & (0u - freem)) - 1u;
+              bool hit = false;
+              while (cand) {
+                const u32 pos = __ffs(cand) - 1;
+                cand &= cand - 1;
+                if (bw_lds_u64(a_key + 8 * (wb + pos)) == key) {
+                  ls = wb + pos;
+                  hit = true;
+                  break;
+                }
+              }
+              if (!hit && freem) {
+                const u32 pos = __ffs(freem) - 1;
+                const u64 old = bw_atoms_cas_u64(a_key + 8 * (wb + pos), BW_EMPTY_KEY, key);
+                if (old == BW_EMPTY_KEY) {
+                  asm volatile("st.shared.u8 [%0], %1;" ::"r"(a_fp + wb + pos), "r"(fp) : "memory");
+                  ls = wb + pos;
+                  hit = true;
+                } else if (old == key) {
+                  ls = wb + pos;
+                  hit = true;
+                }
+                // else: another key won the slot (its fingerprint may not be visible yet): look at the window again
+              } else if (!hit) {
+                wb = (wb + 16) & smask;
+                ahead = 0xFFFFu;
+                tries += 16;
               }
               if (hit) {
                 found = true;
                 searching = false;
-              } else {
-                ls = (ls + 1) & smask;
-                if (++tries >= S) searching = false;
+              } else if (tries > S + 16) {
+                searching = false;
               }
             }
           }
@@ -634,6 +704,7 @@ k_segfold(SegArgs A, Table t, FoldParams p, EmitBufs e) {
           }
         }
       }
+      }  // lane
       __syncthreads();
       // ---- merge: one thread per touched slot; the block owns the segment ----
       for (u32 ls = threadIdx.x; ls < S; ls += BW_SF_THREADS) {
@@ -669,6 +740,25 @@ k_segfold(SegArgs A, Table t, FoldParams p, EmitBufs e) {
         const i64 ts_new = A.ts0 + (i64)m;  // newest event of the key in this pass
         if (WM && ts_new > h.max_ts) h.max_ts = ts_new;
         const i64 tag_in = h.wt0;
+        if (tumbling && !SEQ && !CNT && touched[0] != touched[1] && tag_in != BW_EMPTY_WIDTAG &&
+            !(tag_in & (BW_TAG_HAS_P1 | BW_TAG_HAS_LIST | BW_TAG_DIRTY))) {
+          // The steady state of an in-order stream: the key's only pane took more values and stays open.
+          const int j = touched[1] ? 1 : 0;
+          const i64 q = q_pass + j;
+          if (bw_widtag_q(tag_in) == q) {
+            bool open = true;
+            if (WM) {
+              i64 wm = bw_sub_sat(h.max_ts, p.wait_us);
+              if (wm < BW_UTC_MIN_US_DEV) wm = BW_UTC_MIN_US_DEV;
+              open = wm < p.align_us + (q + 1) * p.length_us;
+            }
+            if (open) {
+              h.acc0 = bw_combine(OP, h.acc0, dv[j]);
+              t.hot[s] = h;
+              continue;
+            }
+          }
+        }
         const bool had_p1 = (tag_in & BW_TAG_HAS_P1) != 0;
         bool done = false;
         if (tumbling && !(tag_in & (BW_TAG_HAS_LIST | BW_TAG_DIRTY))) {
@@ -838,7 +928,6 @@ k_segfold(SegArgs A, Table t, FoldParams p, EmitBufs e) {
         t.hot[s] = h;
       }
     }  // pass
-    if (threadIdx.x == 0) A.in.cursor[b] = 0u;  // ready for the next scatter into this side
     __syncthreads();
     if (sink.n_dirty > sink.cap / 2) bw_sinks_flush(&sink, t);  // uniform: read after the barrier
   }

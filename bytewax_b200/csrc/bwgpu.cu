@@ -137,6 +137,7 @@ struct Deferred {
   const i64* d_ts = nullptr;
   u64 rows = 0, ord = 0;
   u32 batch_no = 0;
+  u32 lanes = 0;           // blocks of this activation's scatter
   Stage* stage = nullptr;  // device staging buffer to release once the fold has read it
 };
 
@@ -200,6 +201,7 @@ struct bw_fold {
   segfold_kernel_t segfold_kernel = nullptr;
   size_t segfold_smem = 0, scatter_smem = 0;
   int scatter_nstage = 3;
+  u32 last_scatter_grid = 0, scatter_stg_cap = 0, scatter_stg_every = 1;
   cudaEvent_t ev_sv[2] = {nullptr, nullptr};
   StreamVerdict* h_sv = nullptr;  // pinned mirror of the two sides' verdicts
   Deferred dq{};            // the activation whose fold has not been launched yet
@@ -460,21 +462,25 @@ static bw_status stream_alloc(bw_fold* f) {
   // the shape the direct kernel's general path is for
   if (!f->p.track_wm && f->p.ts_from_value != 2) return BW_OK;
   sb.nb = (u32)nb;
-  // one region per bucket: mean + 6 sigma + slack of a uniform split, where the variance of a bucket's row count is that of
-  // its rows (Poisson) plus that of its number of distinct keys (a fuller bucket overflows into the spill list)
-  const double mean = (double)rows / (double)nb;
+  // Every scatter block owns a lane in every bucket's region.  A lane holds the block's share of the bucket's rows: mean
+  // + 6 sigma, where the variance is that of the rows (Poisson) plus that of the bucket's number of distinct keys (a fuller
+  // lane overflows into the spill list).
+  sb.nlanes = (u32)ctx->sm_count;
+  const u64 max_tiles = (rows + BW_SC_TILE - 1) / BW_SC_TILE;
+  const double block_rows = (double)((max_tiles + sb.nlanes - 1) / sb.nlanes) * BW_SC_TILE;
+  const double mean = block_rows / (double)nb;
   const double keys_per_bucket = std::max(1.0, (double)std::max<u64>(f->spec.capacity_hint, 1) / (double)nb);
   const double sigma = std::sqrt(mean + mean * mean / keys_per_bucket);
-  sb.region_cap = (u32)std::min<double>((double)rows, mean + 6.0 * sigma + 64.0);
-  sb.region_cap = (sb.region_cap + 7u) & ~7u;
+  sb.lane_cap = (u32)std::min<double>(block_rows, mean + 6.0 * sigma + 24.0);
+  sb.lane_cap = (sb.lane_cap + 7u) & ~7u;
   sb.spill_cap = (u32)std::min<u64>(std::max<u64>(rows / 4, 8192), 1u << 24);
   sb.val_bytes = (f->p.op == BW_OP_ADD_ONE && !f->p.need_count) ? 0 : f->val_bytes;
-  const size_t region_rows = (size_t)sb.nb * sb.region_cap;
+  const size_t region_rows = (size_t)sb.nb * sb.nlanes * sb.lane_cap;
   for (int i = 0; i < 2; ++i) {
     CU(ctx, dmalloc(&sb.side[i].rec, region_rows));
     if (sb.val_bytes) CU(ctx, cudaMalloc(&sb.side[i].val, region_rows * (size_t)sb.val_bytes));
-    CU(ctx, dmalloc(&sb.side[i].cursor, sb.nb));
-    CU(ctx, cudaMemsetAsync(sb.side[i].cursor, 0, sizeof(u32) * sb.nb, f->s_compute));
+    CU(ctx, dmalloc(&sb.side[i].cnt, (size_t)sb.nb * sb.nlanes));
+    CU(ctx, cudaMemsetAsync(sb.side[i].cnt, 0, sizeof(u32) * sb.nb * sb.nlanes, f->s_compute));
     CU(ctx, dmalloc(&sb.side[i].spill, sb.spill_cap));
     CU(ctx, dmalloc(&sb.side[i].sv, 1));
     CU(ctx, cudaMemsetAsync(sb.side[i].sv, 0, sizeof(StreamVerdict), f->s_compute));
@@ -484,15 +490,29 @@ static bw_status stream_alloc(bw_fold* f) {
   const int tsm = f->p.ts_from_value ? f->p.ts_from_value : 0;
   const int vb_in = (tsm == 1) ? 8 : (sb.val_bytes ? f->val_bytes : 0);
   f->scatter_kernel = pick_scatter_kernel(tsm, vb_in, sb.val_bytes);
-  const u64 T = BW_SC_TILE;
-  sb.tiles_cap = (u32)((rows + T - 1) / T + 1);
+  sb.tiles_cap = (u32)((rows + BW_SC_TILE - 1) / BW_SC_TILE + 1);  // one lateness triple per scatter tile
   CU(ctx, dmalloc(&sb.tile_min, sb.tiles_cap));
   CU(ctx, dmalloc(&sb.tile_max, sb.tiles_cap));
   CU(ctx, dmalloc(&sb.tile_bad, sb.tiles_cap));
-  // TMA stages of the input tile: three when two blocks of that size still share an SM
-  f->scatter_nstage = (bw_scatter_smem(tsm, vb_in, 3, sb.nb) <= 110 * 1024) ? 3 : 2;
+  // Shared memory of the scatter: up to 8 records per bucket assembled before they are written out (counts only: the
+  // value column is not staged), then as many TMA stages of the input tile (2..4) as still fit.
+  const size_t smem_budget = 208 * 1024;
+  f->scatter_stg_cap = 0;
+  if (sb.val_bytes == 0)
+    for (u32 c = 8; c >= 4; c -= 2)
+      if (bw_scatter_smem(tsm, vb_in, 2, sb.nb, c) <= smem_budget) {
+        f->scatter_stg_cap = c;
+        break;
+      }
+  if (const char* e = getenv("BW_SC_STG")) f->scatter_stg_cap = (u32)std::max(0, std::min(16, atoi(e)));
+  // write out when an average bucket has assembled ~3/4 of its staging rows
+  f->scatter_stg_every = (u32)std::max<double>(1.0, std::floor(0.75 * f->scatter_stg_cap * (double)sb.nb / BW_SC_TILE));
+  if (const char* e = getenv("BW_SC_EVERY")) f->scatter_stg_every = (u32)std::max(1, atoi(e));
+  f->scatter_nstage = 4;
+  while (f->scatter_nstage > 2 && bw_scatter_smem(tsm, vb_in, f->scatter_nstage, sb.nb, f->scatter_stg_cap) > smem_budget) --f->scatter_nstage;
   if (const char* e = getenv("BW_SC_STAGES")) f->scatter_nstage = std::max(2, std::min(4, atoi(e)));
-  f->scatter_smem = bw_scatter_smem(tsm, vb_in, f->scatter_nstage, sb.nb);
+  if (bw_scatter_smem(tsm, vb_in, f->scatter_nstage, sb.nb, f->scatter_stg_cap) > 216 * 1024) return BW_OK;  // too many segments
+  f->scatter_smem = bw_scatter_smem(tsm, vb_in, f->scatter_nstage, sb.nb, f->scatter_stg_cap);
   // the attribute belongs to the kernel, not to this fold: folds with other table sizes share it
   CU(ctx, cudaFuncSetAttribute((const void*)f->scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
   int occ = 0;
@@ -799,7 +819,7 @@ void bw_fold_destroy(bw_fold* f) {
   for (void* p : dev)
     if (p) cudaFree(p);
   for (int i = 0; i < 2; ++i) {
-    void* sp[] = {f->sb.side[i].rec, f->sb.side[i].val, f->sb.side[i].cursor, f->sb.side[i].spill, f->sb.side[i].sv};
+    void* sp[] = {f->sb.side[i].rec, f->sb.side[i].val, f->sb.side[i].cnt, f->sb.side[i].spill, f->sb.side[i].sv};
     for (void* q : sp)
       if (q) cudaFree(q);
     if (f->ev_sv[i]) cudaEventDestroy(f->ev_sv[i]);
@@ -1074,7 +1094,8 @@ static bw_status stream_front(bw_fold* f, const u64* d_keys, const void* d_vals,
   A.n = rows;
   A.out = sb.side[side];
   A.nb = sb.nb;
-  A.region_cap = sb.region_cap;
+  A.nlanes = sb.nlanes;
+  A.lane_cap = sb.lane_cap;
   A.spill_cap = sb.spill_cap;
   A.tile_min = sb.tile_min;
   A.tile_max = sb.tile_max;
@@ -1082,10 +1103,15 @@ static bw_status stream_front(bw_fold* f, const u64* d_keys, const void* d_vals,
   A.cap = f->t.cap;
   A.seg_shift = f->t.seg_shift;
   A.nstage = (u32)f->scatter_nstage;
+  A.rec_idx = f->p.seq_by_id ? 0u : 1u;
+  if (const char* e = getenv("BW_SC_DBG")) A.dbg = (u32)atoi(e);
+  A.stg_cap = f->scatter_stg_cap;
+  A.stg_every = f->scatter_stg_every;
   A.batch_no = batch_no;
   const u64 T = BW_SC_TILE;
   const u64 ntiles = (rows + T - 1) / T;
-  const int grid = (int)std::min<u64>(ntiles, (u64)f->scatter_grid);
+  const int grid = (int)std::min<u64>(ntiles, (u64)std::min<u32>((u32)f->scatter_grid, sb.nlanes));
+  f->last_scatter_grid = (u32)grid;
   EventPair* ep = next_timer(f);
   if (ep) {
     ep->rows = rows;
@@ -1133,7 +1159,9 @@ static bw_status stream_resolve(bw_fold* f) {
     memset(&A, 0, sizeof A);
     A.in = sb.side[d.side];
     A.nb = sb.nb;
-    A.region_cap = sb.region_cap;
+    A.nlanes = sb.nlanes;
+    A.lane_cap = sb.lane_cap;
+    A.nlanes_used = d.lanes;
     A.spill_cap = sb.spill_cap;
     A.val_bytes = sb.val_bytes;
     A.seg_shift = f->t.seg_shift;
@@ -1149,19 +1177,18 @@ static bw_status stream_resolve(bw_fold* f) {
       CU(ctx, cudaEventRecord(ep->a, s));
     }
     if (getenv("BW_DEBUG_CURSOR")) {
-      std::vector<u32> hc(sb.nb);
-      cudaMemcpy(hc.data(), sb.side[d.side].cursor, sizeof(u32) * sb.nb, cudaMemcpyDeviceToHost);
+      std::vector<u32> hc((size_t)sb.nb * sb.nlanes);
+      cudaMemcpy(hc.data(), sb.side[d.side].cnt, sizeof(u32) * hc.size(), cudaMemcpyDeviceToHost);
       u64 sum = 0;
-      u32 mn = ~0u, mx = 0, nz = 0;
-      for (u32 c : hc) {
-        sum += c;
-        mn = std::min(mn, c);
-        mx = std::max(mx, c);
-        nz += c != 0;
-      }
-      fprintf(stderr, "[bwgpu] batch %u: nb %u region_cap %u rows %llu cursor sum %llu min %u max %u nonzero %u spill %u flags %u span [%lld, %lld] ts0 %lld\n",
-              d.batch_no, sb.nb, sb.region_cap, (unsigned long long)d.rows, (unsigned long long)sum, mn, mx, nz, sv.n_spill, sv.flags,
-              (long long)sv.tmin, (long long)sv.tmax, (long long)sv.ts0);
+      u32 mx = 0;
+      for (u32 bb = 0; bb < sb.nb; ++bb)
+        for (u32 l = 0; l < d.lanes; ++l) {
+          sum += hc[(size_t)bb * sb.nlanes + l];
+          mx = std::max(mx, hc[(size_t)bb * sb.nlanes + l]);
+        }
+      fprintf(stderr, "[bwgpu] batch %u: nb %u lanes %u lane_cap %u rows %llu in lanes %llu max %u spill %u flags %u span [%lld, %lld]\n", d.batch_no,
+              sb.nb, d.lanes, sb.lane_cap, (unsigned long long)d.rows, (unsigned long long)sum, mx, sv.n_spill, sv.flags, (long long)sv.tmin,
+              (long long)sv.tmax);
     }
     const u32 n_pre = std::min<u32>(sv.n_spill, sb.spill_cap);  // rows the scatter set aside: fold them first
     if (n_pre) {
@@ -1183,8 +1210,7 @@ static bw_status stream_resolve(bw_fold* f) {
     st = close_stage(f, d.ord, d.batch_no, sb.side[d.side].sv);
     f->pt.mark(7, 1, s);
   } else {
-    // drop the scatter output of this activation
-    CU(ctx, cudaMemsetAsync(sb.side[d.side].cursor, 0, sizeof(u32) * sb.nb, s));
+    // (the scatter output of this activation is simply not read)
     BatchView bv;
     memset(&bv, 0, sizeof bv);
     bv.nseg = 1;
@@ -1236,6 +1262,7 @@ static bw_status run_batch(bw_fold* f, const u64* d_keys, const void* d_vals, co
     d.rows = rows;
     d.ord = ord;
     d.batch_no = batch_no;
+    d.lanes = f->last_scatter_grid;
     d.stage = stage;
     return BW_OK;
   }
