@@ -327,6 +327,99 @@ def test_c1_properties_and_sampled_parity(ctx, fold_mode):
     orc.close()
 
 
+@pytest.mark.parametrize("total_rows", [1 << 20, 10_000_000])
+def test_c1_exact_rows_per_activation(ctx, fold_mode, total_rows):
+    """Config C1 with its 10^6 distinct keys: eight activations, windows scaled so that four close
+    before EOF; every activation's rows -- (key, window id, count) AND their order, i.e. the per-key emission
+    sequence -- must equal the C oracle's, bit for bit."""
+    from bytewax_b200 import gpu
+
+    A = 1_640_995_200_000_000
+    n_keys, nb = 1_000_000, 8
+    B = total_rows // nb
+    L = (total_rows // 4 // 1000) * 1000  # window length in us: the stream spans total_rows us -> ~4 windows
+    fold = gpu.WindowFold(ctx, "count", L, None, A, 0, val_dtype="u64", ts_from_value=True, capacity_hint=n_keys,
+                          max_batch_rows=B, max_emit_rows=1 << 23)
+    dk, dv = ctx.dev_alloc(B * 8), ctx.dev_alloc(B * 8)
+    orc = coracle.COracle("count", L, align_us=A)
+    got = []
+    for b in range(nb):
+        fold.gen_c1(dk, dv, b * B, B, n_keys)
+        fold.ingest_device(dk, dv, None, B)
+        got.append(fold.advance())
+        k2, t2, _ = coracle.gen_c1(b * B, B, n_keys, A)
+        orc.on_batch(k2, t2)
+    got.append(fold.eof())
+    orc.on_eof()
+    ck, cw, ca, _, cact = orc.closed()
+    n_closed_before_eof = 0
+    for b in range(nb + 1):
+        sel = cact == b
+        em = got[b]
+        assert np.array_equal(em.closed_key, ck[sel]), (b, len(em.closed_key), int(sel.sum()))
+        assert np.array_equal(em.closed_window_id, cw[sel]), b
+        assert np.array_equal(em.closed_acc.astype(np.int64), ca[sel]), b
+        if b < nb:
+            n_closed_before_eof += len(em.closed_key)
+    assert n_closed_before_eof > total_rows // 8  # not vacuous: windows closed (per key, by that key's later events) before EOF
+    assert sum(int(e.closed_acc.sum()) for e in got) == nb * B
+    st = fold.stats()
+    assert st.slow_batches == 0
+    assert st.combined_folds == (nb if fold_mode == "stream" else 0)
+    ctx.dev_free(dk)
+    ctx.dev_free(dv)
+    fold.close()
+    orc.close()
+
+
+def test_c3_shape_sliding_f32_sum(ctx, fold_mode):
+    """Config C3's shape: sliding 60 s / 10 s event-time windows, f32 values summed, 10^6 keys, N = 10^6
+    rows spread over C3's 1000 s of event time; rows within 1e-6 relative of the oracle (f64 left-to-right sums), and
+    the sum over all windows == 6 x the sum of the values (every event lies in six windows)."""
+    from bytewax_b200 import gpu
+
+    S = 1_000_000
+    A = 1_640_995_200_000_000
+    n, n_keys, nb = 1_000_000, 1_000_000, 8
+    i = np.arange(n, dtype=np.uint64)
+
+    def sm64(x):  # splitmix64, vectorised (== oracle.pyoracle.splitmix64)
+        x = x + np.uint64(0x9E3779B97F4A7C15)
+        z = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+    with np.errstate(over="ignore"):
+        keys = sm64(np.uint64(0xC3) ^ i) % np.uint64(n_keys)
+        vals = ((sm64(np.uint64(0xF3) ^ i) >> np.uint64(40)).astype(np.float64) / float(1 << 24)).astype(np.float32)
+    assert int(keys[5]) == po.splitmix64(0xC3 ^ 5) % n_keys
+    ts = (A + np.arange(n, dtype=np.int64) * 1000).astype(np.int64)
+    fold = gpu.WindowFold(ctx, "sum", 60 * S, 10 * S, A, 0, val_dtype="f32", capacity_hint=n_keys, max_batch_rows=n // nb,
+                          max_emit_rows=1 << 23)
+    orc = coracle.COracle("sum", 60 * S, 10 * S, A, 0, False, is_float=True)
+    got = []
+    for b in range(nb):
+        sl = slice(b * (n // nb), (b + 1) * (n // nb))
+        fold.ingest(keys[sl], vals[sl], ts[sl])
+        orc.on_batch(keys[sl], ts[sl], vals[sl].astype(np.float64))
+        got.append(fold.advance())
+    got.append(fold.eof())
+    orc.on_eof()
+    ck, cw, ca, _, cact = orc.closed()
+    gk = np.concatenate([e.closed_key for e in got])
+    gw = np.concatenate([e.closed_window_id for e in got])
+    ga = np.concatenate([e.closed_acc for e in got])
+    assert np.array_equal(gk, ck) and np.array_equal(gw, cw)
+    np.testing.assert_allclose(ga, ca, rtol=REL_TOL)
+    assert abs(float(ga.sum()) - 6.0 * float(vals.astype(np.float64).sum())) <= REL_TOL * 6.0 * float(vals.sum())
+    st = fold.stats()
+    assert st.slow_batches == 0
+    if fold_mode == "stream":
+        assert st.combined_folds == nb
+    fold.close()
+    orc.close()
+
+
 @pytest.mark.parametrize("red,length,offset,wait", [("count", 10, None, 2), ("sum", 10, 5, 3), ("max", 7, None, 0)])
 def test_snapshot_restore_resumes_identically(ctx, red, length, offset, wait):
     """bw_snapshot_take after three activations, bw_snapshot_load into a fresh fold of a different capacity, then the
