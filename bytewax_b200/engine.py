@@ -90,6 +90,11 @@ def _get_gpu_ctx():
     return _gpu_ctx
 
 
+class _GpuPlanUnfit(Exception):
+    """The first batch of a step whose reducer LOOKED numeric (operator.add, max, min ...) holds values the CUDA fold
+    cannot carry (strings, tuples, datetimes, ints beyond int64): the engine runs that step on the host logic instead."""
+
+
 class _GpuWindowStep:
     """One worker's ``stateful_batch`` of a numeric windowed fold, on ``libbwgpu``."""
 
@@ -115,11 +120,14 @@ class _GpuWindowStep:
         self.key_ids: Dict[str, int] = {}
         self.id_keys: Dict[int, str] = {}
         self.resort = False
+        self.last_epoch = 0
         self.originals: Dict[int, Any] = {}
 
     def _key_id(self, k: str) -> int:
-        if k.isdigit() and (k == "0" or k[0] != "0") and len(k) < 20:
-            return int(k)  # canonical decimal text: the id is the number itself
+        # canonical ASCII decimal text below 2^63: the id is the number itself (str.isdigit alone also accepts other
+        # scripts' digits and superscripts); every other key is interned from 2^63 up, so the two ranges never meet
+        if k.isascii() and k.isdigit() and (k == "0" or k[0] != "0") and len(k) < 20 and int(k) < (1 << 63):
+            return int(k)
         i = self.key_ids.get(k)
         if i is None:
             i = self.key_ids[k] = (1 << 63) + len(self.key_ids)
@@ -138,6 +146,8 @@ class _GpuWindowStep:
             raise TypeError(f"step {self.step_id!r}: mixing KeyedColumns and per-item values in one batch")
         if cols:
             k = np.concatenate([c[1].keys for c in cols]).astype(np.uint64)
+            if k.size and int(k.max()) >= (1 << 63):
+                raise TypeError(f"step {self.step_id!r}: KeyedColumns keys must be below 2^63 (ids from 2^63 up are interned string keys)")
             t = np.concatenate([c[1].ts_us for c in cols]).astype(np.int64)
             v = None if cols[0][1].vals is None else np.concatenate([c[1].vals for c in cols])
         else:
@@ -156,8 +166,10 @@ class _GpuWindowStep:
                     orig.append(value)
                 else:
                     num = plan.value_of(value)
-                    if isinstance(num, bool) or not isinstance(num, (int, float)):
-                        raise TypeError(f"step {self.step_id!r}: the CUDA fold needs numeric values; got a {type(num)!r}")
+                    if isinstance(num, bool) or not isinstance(num, (int, float)) or (isinstance(num, int) and not -(1 << 63) <= num < (1 << 63)):
+                        if self.fold is None:  # nothing folded yet: this step runs on the host logic instead
+                            raise _GpuPlanUnfit(f"value {num!r} of type {type(num)!r}")
+                        raise TypeError(f"step {self.step_id!r}: the CUDA fold needs numeric values in the int64 / float64 range; got {num!r}")
                     vals.append(num)
             k, t = np.array(keys, dtype=np.uint64), np.array(ts, dtype=np.int64)
             v = np.array(vals) if vals else np.zeros(0, dtype=np.int64)
@@ -166,7 +178,8 @@ class _GpuWindowStep:
             self.fold = self._mk("f64" if self.float_vals else "i64")
         if v is not None and v.dtype.kind == "f" and not self.float_vals:
             raise TypeError(f"step {self.step_id!r}: value type changed from integer to float mid-stream")
-        self.fold.ingest(k, v, t, epoch)
+        self.fold.ingest(k, v, t, max(epoch, self.last_epoch))  # (the engine's frontier already keeps epochs in order)
+        self.last_epoch = max(epoch, self.last_epoch)
         return self._rows(self.fold.advance(), orig)
 
     def on_eof(self) -> list:
@@ -227,6 +240,7 @@ class _GpuFinalStep(_GpuWindowStep):
         self.key_ids: Dict[str, int] = {}
         self.id_keys: Dict[int, str] = {}
         self.resort = False
+        self.last_epoch = 0
 
     def on_epoch(self, epoch: int, items: list) -> list:
         np = self.np
@@ -238,8 +252,10 @@ class _GpuFinalStep(_GpuWindowStep):
                 raise TypeError(f"step {self.step_id!r} requires `(key, value)` 2-tuple as upstream for routing; got a {type(item)!r} instead") from ex
             if not isinstance(key, str):
                 raise TypeError(f"step {self.step_id!r} requires `str` keys in `(key, value)` from upstream; got a {type(key)!r} instead")
-            if isinstance(value, bool) or not isinstance(value, (int, float)):
-                raise TypeError(f"step {self.step_id!r}: the CUDA fold needs numeric values; got a {type(value)!r}")
+            if isinstance(value, bool) or not isinstance(value, (int, float)) or (isinstance(value, int) and not -(1 << 63) <= value < (1 << 63)):
+                if self.fold is None:
+                    raise _GpuPlanUnfit(f"value {value!r} of type {type(value)!r}")
+                raise TypeError(f"step {self.step_id!r}: the CUDA fold needs numeric values in the int64 / float64 range; got {value!r}")
             keys.append(self._key_id(key))
             vals.append(value)
         if not keys:
@@ -250,7 +266,8 @@ class _GpuFinalStep(_GpuWindowStep):
             self.fold = self._mk("f64" if self.float_vals else "i64")
         if v.dtype.kind == "f" and not self.float_vals:
             raise TypeError(f"step {self.step_id!r}: value type changed from integer to float mid-stream")
-        self.fold.ingest(np.array(keys, dtype=np.uint64), v, None, epoch)
+        self.fold.ingest(np.array(keys, dtype=np.uint64), v, None, max(epoch, self.last_epoch))
+        self.last_epoch = max(epoch, self.last_epoch)
         return []
 
     def on_eof(self) -> list:
@@ -488,23 +505,35 @@ class _Run:
                     routed[_route(key, self.W)][epoch].append(item)
         now = datetime.now(timezone.utc)
         last_out = S.setdefault("last_out", [0] * self.W)
+        # Frontier over the inputs (src/timely.rs:95-133, src/operators.rs:687-728): every input partition advances its
+        # own epoch, so an item of epoch e is held back until no partition can still produce an earlier epoch; closed
+        # epochs are processed in order and the frontier epoch itself eagerly.  At EOF everything left is flushed.
+        pending = S.setdefault("pending", [defaultdict(list) for _ in range(self.W)])
+        open_epochs = [ip.epoch for parts in self.inputs.values() for ip in parts if not ip.eof]
+        frontier = min(open_epochs) if (open_epochs and not eof) else None
         for w in range(self.W):
+            for epoch, items in routed[w].items():
+                pending[w][epoch].extend(items)
+            ready = {e: pending[w].pop(e) for e in sorted(pending[w]) if frontier is None or e <= frontier}
             g = S["gpu"][w]
             # Epochs of this activation, in order; the epoch of the previous activation is walked again (without items) so
             # that notifications which came due since then fire BEFORE this activation's new items, as the reference does by
             # re-inserting `last_output_epoch` into `process_epochs` (src/operators.rs:698-707, notify phase :808-858).
-            epochs = sorted(set(routed[w]) | ({last_out[w]} if last_out[w] else set()))
+            epochs = sorted(set(ready) | ({last_out[w]} if last_out[w] else set()))
             last_epoch = 0
             for epoch in epochs:
                 last_epoch = epoch
-                items = routed[w].get(epoch)
+                items = ready.get(epoch)
                 if g is not None:
                     if items:
                         try:
                             self._emit(st.down, w, epoch, g.on_epoch(epoch, items))
+                        except _GpuPlanUnfit:
+                            g = S["gpu"][w] = None  # values the CUDA fold cannot carry: this step stays on the host logic
                         except Exception as ex:
                             _reraise(f"error in the CUDA fold of step {st.step_id}", ex)
-                    continue
+                    if g is not None:
+                        continue
                 if items:
                     self._host_on_batch(st, S, w, epoch, items)
                 self._host_notify(st, S, w, epoch, now)

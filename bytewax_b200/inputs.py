@@ -188,6 +188,10 @@ def batch_async(aib, timeout: timedelta, batch_size: int, loop=None) -> Iterator
     """Batch an async iterator with a time limit per batch (inputs.py:546)."""
     loop = loop if loop is not None else asyncio.new_event_loop()
     task = None
+    ait = aib.__aiter__()  # an async iterable need not be its own iterator
+
+    async def anext_coro():  # __anext__ may return any awaitable: create_task needs a coroutine
+        return await ait.__anext__()
 
     async def anext_batch():
         nonlocal task
@@ -196,7 +200,7 @@ def batch_async(aib, timeout: timedelta, batch_size: int, loop=None) -> Iterator
         try:
             while len(chunk) < batch_size:
                 if task is None:
-                    task = loop.create_task(aib.__anext__())
+                    task = loop.create_task(anext_coro())
                 remain = deadline - loop.time()
                 done, _ = await asyncio.wait({task}, timeout=max(remain, 0))
                 if not done:

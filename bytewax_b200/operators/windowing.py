@@ -713,7 +713,7 @@ class _JoinWindowLogic(WindowLogic):
 
 @operator
 def join_window(step_id: str, clock: Clock, windower: Windower, *sides: KeyedStream, insert_mode: str = "last",
-                emit_mode: str = "final") -> WindowOut:
+                emit_mode: str = "final", ordered: bool = True) -> WindowOut:
     """Join keyed streams within windows (windowing.py:2055).  The clock sees the bare value."""
     if insert_mode not in ("first", "last", "product"):
         raise ValueError(f"unknown join insert mode {insert_mode!r}")
@@ -730,4 +730,4 @@ def join_window(step_id: str, clock: Clock, windower: Windower, *sides: KeyedStr
         inner = clock.ts_getter
         clock = EventClock(lambda side_v: inner(side_v[1]), clock.wait_for_system_duration, clock.now_getter, clock.to_system_utc)
     merged = op._join_label_merge("add_names", *sides)
-    return window("window", merged, clock, windower, shim_builder, ordered=True)
+    return window("window", merged, clock, windower, shim_builder, ordered=ordered)

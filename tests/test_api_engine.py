@@ -310,3 +310,55 @@ def test_c0_wordcount_via_run_module():
     counts = dict(eval(ln) for ln in lines)
     assert counts["to"] == 4 and counts["be"] == 2 and counts["of"] == 2 and counts["them"] == 1
     assert [eval(ln)[0] for ln in lines] == sorted(counts)  # EOF emission in ascending word order
+
+
+def test_stateful_steps_see_epochs_in_order_across_input_partitions():
+    """Every input partition advances its own epoch; a stateful step must still see epochs in order (the engine holds an
+    item back until no partition can produce an earlier epoch: src/timely.rs:95-133, src/operators.rs:687-728)."""
+    from bytewax_b200.inputs import DynamicSource, StatelessSourcePartition
+
+    class _Part(StatelessSourcePartition):
+        def __init__(self, name, n, gap_ms):
+            self.name, self.left, self.gap = name, n, timedelta(milliseconds=gap_ms)
+            self.awake = None
+
+        def next_batch(self):
+            if self.left == 0:
+                raise StopIteration()
+            self.left -= 1
+            self.awake = datetime.now(timezone.utc) + self.gap
+            return [(self.name, 1)]
+
+        def next_awake(self):
+            return self.awake
+
+    class _Src(DynamicSource):
+        def __init__(self, name, n, gap_ms):
+            self.args = (name, n, gap_ms)
+
+        def build(self, step_id, worker_index, worker_count):
+            return _Part(*self.args)
+
+    seen = []
+    flow = Dataflow("df")
+    fast = op.input("fast", flow, _Src("f", 40, 1))
+    slow = op.input("slow", flow, _Src("s", 8, 25))
+    s = op.merge("m", fast, slow)
+    s = op.stateful_map("sm", s, lambda st, v: ((st or 0) + v, (st or 0) + v))
+    op.inspect_debug("insp", s, lambda step_id, item, epoch, worker: seen.append(epoch))
+    op.output("out", s, TestingSink([]))
+    run_main(flow, epoch_interval=timedelta(milliseconds=5))
+    assert len(seen) == 48 and seen == sorted(seen) and seen[-1] > seen[0]
+
+
+def test_gpu_key_ids_do_not_collide():
+    """Numeric-looking keys take their own value as device id only when that is unambiguous (ASCII, canonical, < 2^63);
+    everything else is interned from 2^63 up."""
+    from bytewax_b200.engine import _GpuWindowStep
+
+    st = _GpuWindowStep.__new__(_GpuWindowStep)
+    st.key_ids, st.id_keys, st.resort = {}, {}, False
+    ids = [st._key_id(k) for k in ["3", "٣", "²", "9223372036854775808", "007", "abc", "9223372036854775807"]]
+    assert ids[0] == 3 and ids[6] == (1 << 63) - 1
+    assert all(i >= (1 << 63) for i in ids[1:6]) and len(set(ids)) == len(ids)
+    assert [st._key_str(i) for i in ids] == ["3", "٣", "²", "9223372036854775808", "007", "abc", "9223372036854775807"]
