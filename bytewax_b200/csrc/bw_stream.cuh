@@ -58,6 +58,15 @@ struct StreamVerdict {
   u32 n_spill; // rows in this activation's spill list
   u32 pad;
 };
+// what every rank tells the others about its slice of an activation (multi-GPU verdict: the slices are chained in
+// source-rank order, the arrival order at every destination)
+struct VerdictGather {
+  i64 tmin, tmax;  // span of the rank's rows (tmin > tmax: no rows)
+  u32 bad;         // some row of the slice is later than an earlier one by more than `wait`
+  u32 flags;       // BW_SV_* of the rank's scatter
+  u32 n_spill;     // rows the rank's scatter set aside
+  u32 pad;
+};
 #define BW_SV_RANGE 1u   // a timestamp is further than 2^31 us from row 0: the activation takes the direct kernel
 #define BW_SV_LOST 2u    // the spill list overflowed during the scatter: rows were dropped from the buckets
 
@@ -152,6 +161,7 @@ struct ScatterArgs {
   u32 nstage;        // TMA stages in shared memory (2 or 3)
   u32 rec_idx;       // 1: records carry the arrival index; 0: the slot / fingerprint tag
   u32 dbg;           // diagnostics only (env BW_SC_DBG): 1 skip the record stores, 2 skip the position atomics, 4 skip the verdict
+  u32 world, nb_local;  // multi-GPU: bucket = owning rank * nb_local + segment of the key in the owner's table
   u32 stg_cap;       // records per bucket assembled in shared memory before they are written out (0: every record straight out)
   u32 stg_every;     // ... every this many tiles
 };
@@ -364,7 +374,8 @@ __global__ void __launch_bounds__(BW_SC_THREADS, 1) k_scatter(ScatterArgs A, Fol
       if (k != BW_EMPTY_KEY) {  // (the alias slot lives outside every segment: general path)
         const u64 hh = bw_khash(k);
         const u64 slot = bw_slot_of_khash(hh, A.cap);
-        const u32 b = (u32)(slot >> A.seg_shift);
+        u32 b = (u32)(slot >> A.seg_shift);
+        if (A.world > 1) b += bw_route_hash(bw_mix64(k), A.world) * A.nb_local;
         const u32 pos = (A.dbg & 2u) ? (u32)(row & 7u) : bw_atoms_add_u32(lcur + 4 * b, 1u);
         const uint4 rec4 = make_uint4((u32)k, (u32)(k >> 32), (u32)rel, A.rec_idx ? (u32)row : bw_rec_tag(hh, slot, seg_mask));
         const u32 soff = pos - bw_lds_u32(fbase + 4 * b);  // rows of the bucket since the last write-out
@@ -423,7 +434,7 @@ __global__ void __launch_bounds__(BW_SC_THREADS, 1) k_scatter(ScatterArgs A, Fol
 // for its ranges; publish the verdict, the span and the base timestamp.
 __global__ void __launch_bounds__(1024)
 k_verdict(const i64* tile_min, const i64* tile_max, const u32* tile_bad, u32 ntiles, FoldParams p, Counters* ctr, StreamVerdict* sv,
-          const i64* ts_col, const u64* val_col) {
+          const i64* ts_col, const u64* val_col, VerdictGather* vg) {
   __shared__ i64 s_mn[32], s_mx[32];
   __shared__ u32 s_bad[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -441,34 +452,69 @@ k_verdict(const i64* tile_min, const i64* tile_max, const u32* tile_bad, u32 nti
   if (warp == 0) {
     Trip act = bw_trip_warp(Trip{s_mn[lane], s_mx[lane], s_bad[lane]}, p.wait_us);
     if (lane == 31) {
-      const i64 gprev = (i64)ctr->gmax_ts;
-      // everything ingested before this activation: only its maximum matters
-      const Trip all = bw_trip_cat(Trip{INT64_MAX, gprev, 0u}, act, p.wait_us);
-      ctr->gmax_ts = (unsigned long long)all.mx;
-      const u32 clean = (!p.track_wm || !all.bad) ? 1u : 0u;
-      ctr->batch_clean = clean;
-      sv->clean = clean;
       sv->tmin = act.mn;
       sv->tmax = act.mx;
-      sv->ts0 = ts_col ? ts_col[0] : p.align_us + (i64)val_col[0];
+      sv->ts0 = (ntiles == 0) ? p.align_us : (ts_col ? ts_col[0] : p.align_us + (i64)val_col[0]);
+      if (vg) {
+        // multi-GPU: this rank's slice only; the slices are chained on the host once gathered
+        vg->tmin = act.mn;
+        vg->tmax = act.mx;
+        vg->bad = act.bad;
+        vg->flags = sv->flags;
+        vg->n_spill = sv->n_spill;
+        sv->clean = 0u;
+      } else {
+        const i64 gprev = (i64)ctr->gmax_ts;
+        // everything ingested before this activation: only its maximum matters
+        const Trip all = bw_trip_cat(Trip{INT64_MAX, gprev, 0u}, act, p.wait_us);
+        ctr->gmax_ts = (unsigned long long)all.mx;
+        const u32 clean = (!p.track_wm || !all.bad) ? 1u : 0u;
+        ctr->batch_clean = clean;
+        sv->clean = clean;
+      }
     }
   }
 }
 // the *_final folds have no event time: everything is window 0 at align_to
-__global__ void k_verdict_none(FoldParams p, Counters* ctr, StreamVerdict* sv) {
+__global__ void k_verdict_none(FoldParams p, Counters* ctr, StreamVerdict* sv, VerdictGather* vg, u64 rows) {
   ctr->batch_clean = 1u;
   sv->clean = 1u;
   sv->tmin = p.align_us;
   sv->tmax = p.align_us;
   sv->ts0 = p.align_us;
+  if (vg) {
+    vg->tmin = rows ? p.align_us : INT64_MAX;
+    vg->tmax = rows ? p.align_us : INT64_MIN;
+    vg->bad = 0u;
+    vg->flags = sv->flags;
+    vg->n_spill = sv->n_spill;
+  }
 }
+__global__ void k_set_gmax(Counters* ctr, i64 gmax) { ctr->gmax_ts = (unsigned long long)gmax; }
 
 // ---------------------------------------------------------------------------
 // segment fold
 // ---------------------------------------------------------------------------
+// A key's delta over one pane of one activation, as one rank hands it to the rank that owns the key (multi-GPU:
+// every rank first combines its own slice, then the partials -- not the rows -- cross NVLink: SURVEY 8e, the
+// precedent is `reduce_final`'s pre-reducer, operators/__init__.py:2836-2847).
+struct __align__(16) Partial {
+  u64 key;
+  u64 acc;   // delta in accumulator representation (a count for counts)
+  i64 ts;    // a timestamp of the pane; the key's newest one when this is its newest pane
+  u32 seq;   // arrival index (at the source) of the first row it stands for
+  u32 cnt;   // rows it stands for
+};
+
 struct SegArgs {
   StreamSide in;
   u32 nb, nlanes, lane_cap, spill_cap;
+  // multi-GPU (MODE 1 / 2 of k_segfold)
+  u32 world, rank, nb_local, part_cap;
+  Partial* pout[BW_MAX_WORLD];   // MODE 1: rank d's receive region for THIS source: [nb_local][part_cap] (peer memory over NVLink)
+  u32* pcnt_out[BW_MAX_WORLD];   // MODE 1: ... and its counts [nb_local]
+  const Partial* pin;            // MODE 2: this rank's receive region [world][nb_local][part_cap]
+  const u32* pcnt_in;            // MODE 2: [world][nb_local]
   u32 nlanes_used;  // blocks of the scatter that filled this side
   int val_bytes;
   u32 seg_shift;
@@ -506,6 +552,11 @@ struct SegOp {
       bw_reds_max_u64(a, operand);
     }
   }
+  // a pre-combined delta (a partial from another rank)
+  __device__ __forceinline__ static void merge(u32 a, u64 d) {
+    if (OP == BW_OP_ADD_ONE) bw_reds_add_u32(a, (u32)d);
+    else apply(a, d);
+  }
   __device__ __forceinline__ static u64 load(u32 a) { return narrow ? (u64)bw_lds_u32(a) : bw_lds_u64(a); }
   __device__ __forceinline__ static void store(u32 a, u64 v) {
     if (narrow) bw_sts_u32(a, (u32)v);
@@ -533,7 +584,11 @@ struct MPane {
 
 // The fold kernel proper.  C = FoldCfg<op, -1, cnt> (compile-time op), SEQ: keep first-open indices
 // (folds whose emission order is not simply ascending window id).
-template <class C, bool SEQ>
+// MODE 0: one GPU -- rows of the bucket's lanes into the table.
+// MODE 1: multi-GPU, at the source -- rows of a (destination rank, bucket) combined from an empty segment; what the
+//         merge phase would put in the table goes to the destination's receive region as partials (stores over NVLink).
+// MODE 2: multi-GPU, at the destination -- the partials every source left for this bucket into the table.
+template <class C, bool SEQ, int MODE>
 __global__ void __launch_bounds__(BW_SF_THREADS)
 k_segfold(SegArgs A, Table t, FoldParams p, EmitBufs e) {
   constexpr int OP = C::kOp;
@@ -544,6 +599,7 @@ k_segfold(SegArgs A, Table t, FoldParams p, EmitBufs e) {
   extern __shared__ __align__(16) unsigned char sf_raw[];
   __shared__ DirtySink sink;
   __shared__ u32 sink_buf[512];
+  __shared__ u32 part_n;  // MODE 1: partials written for the bucket
   const u32 S = 1u << A.seg_shift, smask = S - 1;
   const u32 a_key = bw_smem_addr(sf_raw);
   const u32 a_fp = a_key + S * 8;  // one byte per slot: 0 == free, else 0x80 | 7 hash bits of the key in the slot
@@ -563,11 +619,12 @@ k_segfold(SegArgs A, Table t, FoldParams p, EmitBufs e) {
   for (u32 b = blockIdx.x; b < A.nb; b += gridDim.x) {
     const u64 slot_base = (u64)b << A.seg_shift;
     __syncthreads();  // the previous segment's merge is done with shared memory
+    if (MODE == 1 && threadIdx.x == 0) part_n = 0u;
     for (u32 i = threadIdx.x; i < S / 4; i += BW_SF_THREADS) {  // four slots per thread: one 32-bit word of fingerprints
       u32 w = 0;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const u64 key = t.hot[slot_base + 4 * i + k].key;
+        const u64 key = (MODE == 1) ? BW_EMPTY_KEY : t.hot[slot_base + 4 * i + k].key;
         bw_sts_u64(a_key + 8 * (4 * i + k), key);
         if (key != BW_EMPTY_KEY) w |= bw_fp_of(bw_khash(key)) << (8 * k);
       }
@@ -598,113 +655,184 @@ k_segfold(SegArgs A, Table t, FoldParams p, EmitBufs e) {
         }
       }
       __syncthreads();
-      // ---- events of the bucket: its lanes (one per scatter block) are dealt to the warps round-robin ----
-      for (u32 ln = (u32)warp; ln < A.nlanes_used; ln += BW_SF_THREADS / 32) {
-      const size_t lane_base = ((size_t)b * A.nlanes + ln) * A.lane_cap;
-      const u32 n = min(A.in.cnt[(size_t)b * A.nlanes + ln], A.lane_cap);
-      const uint4* rec = A.in.rec + lane_base;
-      for (u32 base = 0; base < n; base += 32 * BW_SF_UNROLL) {
-        uint4 r[BW_SF_UNROLL];
-        u64 v[BW_SF_UNROLL];
-#pragma unroll
-        for (int u = 0; u < BW_SF_UNROLL; ++u) {
-          const u32 i = base + (u32)u * 32 + (u32)lane;
-          r[u] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0);  // no record: the empty key
-          v[u] = 0;
-          if (i < n) {
-            r[u] = bw_ld_stream_rec(rec + i);
-            if (OP != BW_OP_ADD_ONE) {
-              const size_t at = lane_base + i;
-              v[u] = (A.val_bytes == 8) ? bw_ld_stream_u64((const u64*)A.in.val + at) : (u64)bw_ld_stream_u32((const u32*)A.in.val + at);
+      // One event (a row, or another rank's partial): find or claim the key's slot, update the slot's deltas.
+      // Linear probing from the home slot, wrapping inside the segment, is the table's placement rule
+      // (bw_find_slot); here it is walked 16 slots at a time: one LDS.128 brings the fingerprint bytes of an aligned
+      // window, byte-parallel compares give the candidate and the free positions, and only a candidate's 8-byte key
+      // is read.  The loop is warp-uniform (every lane stays until the last one has its slot) so that the
+      // accumulator updates issue once per warp.  Call with all 32 lanes.
+      auto fold_one = [&](bool valid, u64 key, int rel, u32 ls, u32 fp, u64 operand, u32 seqv, u32 cntv) {
+        const u32 fp4 = fp * 0x01010101u;
+        u32 wb = ls & ~15u;                 // window base
+        u32 ahead = 0xFFFFu << (ls & 15u);  // positions of the window at or after the home slot
+        bool searching = valid, found = false;
+        u32 tries = 0;
+        while (__any_sync(0xffffffffu, searching)) {
+          if (searching) {
+            u32 w0, w1, w2, w3;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(a_fp + wb) : "memory");
+            // free positions: bytes with bit 7 clear; matches: zero bytes of (word ^ fingerprint x 4), exact
+            auto zmask = [](u32 x) { return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu); };  // 0x80 per zero byte
+            auto pack4 = [](u32 m80) { return (m80 * 0x00204081u) >> 28; };                                // -> 4 bits
+            const u32 freem = (pack4(~w0 & 0x80808080u) | (pack4(~w1 & 0x80808080u) << 4) | (pack4(~w2 & 0x80808080u) << 8) |
+                               (pack4(~w3 & 0x80808080u) << 12)) & ahead;
+            u32 cand = (pack4(zmask(w0 ^ fp4)) | (pack4(zmask(w1 ^ fp4)) << 4) | (pack4(zmask(w2 ^ fp4)) << 8) |
+                        (pack4(zmask(w3 ^ fp4)) << 12)) & ahead;
+            // the key, if present, sits before the first free position of its probe sequence
+            if (freem) cand &= (freem & (0u - freem)) - 1u;
+            bool hit = false;
+            while (cand) {
+              const u32 pos = __ffs(cand) - 1;
+              cand &= cand - 1;
+              if (bw_lds_u64(a_key + 8 * (wb + pos)) == key) {
+                ls = wb + pos;
+                hit = true;
+                break;
+              }
+            }
+            if (!hit && freem) {
+              const u32 pos = __ffs(freem) - 1;
+              const u64 old = bw_atoms_cas_u64(a_key + 8 * (wb + pos), BW_EMPTY_KEY, key);
+              if (old == BW_EMPTY_KEY) {
+                asm volatile("st.shared.u8 [%0], %1;" ::"r"(a_fp + wb + pos), "r"(fp) : "memory");
+                ls = wb + pos;
+                hit = true;
+              } else if (old == key) {
+                ls = wb + pos;
+                hit = true;
+              }
+              // else: another key won the slot (its fingerprint may not be visible yet): look at the window again
+            } else if (!hit) {
+              wb = (wb + 16) & smask;
+              ahead = 0xFFFFu;
+              tries += 16;
+            }
+            if (hit) {
+              found = true;
+              searching = false;
+            } else if (tries > S + 16) {
+              searching = false;
             }
           }
         }
+        if (valid && !found) bw_raise(t.ctr, 3u);  // segment full: capacity_hint too small
+        if (found) {
+          const u32 j = (rel >= mid32) ? 1u : 0u;
+          if (MODE == 2) SO::merge((j ? a_d1 : a_d0) + DTB * ls, operand);
+          else SO::apply((j ? a_d1 : a_d0) + DTB * ls, operand);
+          if (!SO::narrow) bw_reds_or_u32(a_tm + 4 * (ls >> 4), 1u << (2 * (ls & 15) + j));
+          bw_reds_max_s32(a_mts + 4 * ls, rel);
+          if (SEQ) bw_reds_min_u32((j ? a_sq1 : a_sq0) + 4 * ls, seqv);
+          if (CNT) bw_reds_add_u32((j ? a_cn1 : a_cn0) + 4 * ls, cntv);
+        }
+      };
+      if (MODE != 2) {
+        // ---- rows of the bucket: its lanes (one per scatter block) are dealt to the warps round-robin ----
+        for (u32 ln = (u32)warp; ln < A.nlanes_used; ln += BW_SF_THREADS / 32) {
+          const size_t lane_base = ((size_t)b * A.nlanes + ln) * A.lane_cap;
+          const u32 n = min(A.in.cnt[(size_t)b * A.nlanes + ln], A.lane_cap);
+          const uint4* rec = A.in.rec + lane_base;
+          for (u32 base = 0; base < n; base += 32 * BW_SF_UNROLL) {
+            uint4 r[BW_SF_UNROLL];
+            u64 v[BW_SF_UNROLL];
 #pragma unroll
-        for (int u = 0; u < BW_SF_UNROLL; ++u) {
-          const u64 key = (u64)r[u].x | ((u64)r[u].y << 32);
-          const int rel = (int)r[u].z;
-          const bool valid = key != BW_EMPTY_KEY && rel >= lo32 && rel < hi32;  // a record, and of this pass
-          u32 ls, fp;
-          if (SEQ) {  // the 4th word is the arrival index: hash here
-            const u64 hh = bw_khash(key);
-            ls = (u32)bw_slot_of_khash(hh, t.cap) & smask;
-            fp = bw_fp_of(hh);
-          } else {
-            ls = r[u].w & smask;
-            fp = (r[u].w >> 16) & 0xFFu;
-          }
-          // Find or claim the key's slot.  Linear probing from the home slot, wrapping inside the segment, is the
-          // table's placement rule (bw_find_slot); here it is walked 16 slots at a time: one LDS.128 brings the
-          // fingerprint bytes of an aligned window, byte-parallel compares give the candidate and the free
-          // positions, and only a candidate's 8-byte key is read.  The loop is warp-uniform (every lane stays until
-          // the last one has its slot) so that the accumulator updates below issue once per warp.
-          const u32 fp4 = fp * 0x01010101u;
-          u32 wb = ls & ~15u;                 // window base
-          u32 ahead = 0xFFFFu << (ls & 15u);  // positions of the window at or after the home slot
-          bool searching = valid, found = false;
-          u32 tries = 0;
-          while (__any_sync(0xffffffffu, searching)) {
-            if (searching) {
-              u32 w0, w1, w2, w3;
-              asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(a_fp + wb) : "memory");
-              // free positions: bytes with bit 7 clear; matches: zero bytes of (word ^ fingerprint x 4), exact
-              auto zmask = [](u32 x) { return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu); };  // 0x80 per zero byte
-              auto pack4 = [](u32 m80) { return (m80 * 0x00204081u) >> 28; };                                // -> 4 bits
-              const u32 freem = (pack4(~w0 & 0x80808080u) | (pack4(~w1 & 0x80808080u) << 4) | (pack4(~w2 & 0x80808080u) << 8) |
-                                 (pack4(~w3 & 0x80808080u) << 12)) & ahead;
-              u32 cand = (pack4(zmask(w0 ^ fp4)) | (pack4(zmask(w1 ^ fp4)) << 4) | (pack4(zmask(w2 ^ fp4)) << 8) |
-                          (pack4(zmask(w3 ^ fp4)) << 12)) & ahead;
-              // the key, if present, sits before the first free position of its probe sequence
-              if (freem) cand &= (freem & (0u - freem)) - 1u;
-              bool hit = false;
-              while (cand) {
-                const u32 pos = __ffs(cand) - 1;
-                cand &= cand - 1;
-                if (bw_lds_u64(a_key + 8 * (wb + pos)) == key) {
-                  ls = wb + pos;
-                  hit = true;
-                  break;
+            for (int u = 0; u < BW_SF_UNROLL; ++u) {
+              const u32 i = base + (u32)u * 32 + (u32)lane;
+              r[u] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0);  // no record: the empty key
+              v[u] = 0;
+              if (i < n) {
+                r[u] = bw_ld_stream_rec(rec + i);
+                if (OP != BW_OP_ADD_ONE) {
+                  const size_t at = lane_base + i;
+                  v[u] = (A.val_bytes == 8) ? bw_ld_stream_u64((const u64*)A.in.val + at) : (u64)bw_ld_stream_u32((const u32*)A.in.val + at);
                 }
-              }
-              if (!hit && freem) {
-                const u32 pos = __ffs(freem) - 1;
-                const u64 old = bw_atoms_cas_u64(a_key + 8 * (wb + pos), BW_EMPTY_KEY, key);
-                if (old == BW_EMPTY_KEY) {
-                  asm volatile("st.shared.u8 [%0], %1;" ::"r"(a_fp + wb + pos), "r"(fp) : "memory");
-                  ls = wb + pos;
-                  hit = true;
-                } else if (old == key) {
-                  ls = wb + pos;
-                  hit = true;
-                }
-                // else: another key won the slot (its fingerprint may not be visible yet): look at the window again
-              } else if (!hit) {
-                wb = (wb + 16) & smask;
-                ahead = 0xFFFFu;
-                tries += 16;
-              }
-              if (hit) {
-                found = true;
-                searching = false;
-              } else if (tries > S + 16) {
-                searching = false;
               }
             }
+#pragma unroll
+            for (int u = 0; u < BW_SF_UNROLL; ++u) {
+              const u64 key = (u64)r[u].x | ((u64)r[u].y << 32);
+              const int rel = (int)r[u].z;
+              const bool valid = key != BW_EMPTY_KEY && rel >= lo32 && rel < hi32;  // a record, and of this pass
+              u32 ls, fp;
+              if (SEQ) {  // the 4th word is the arrival index: hash here
+                const u64 hh = bw_khash(key);
+                ls = (u32)bw_slot_of_khash(hh, t.cap) & smask;
+                fp = bw_fp_of(hh);
+              } else {
+                ls = r[u].w & smask;
+                fp = (r[u].w >> 16) & 0xFFu;
+              }
+              u64 operand = 0;
+              if (OP != BW_OP_ADD_ONE) bw_operand(p, v[u], operand);
+              fold_one(valid, key, rel, ls, fp, operand, r[u].w, 1u);
+            }
           }
-          if (valid && !found) bw_raise(t.ctr, 3u);  // segment full: capacity_hint too small
-          if (found) {
-            const u32 j = (rel >= mid32) ? 1u : 0u;
-            u64 operand = 0;
-            if (OP != BW_OP_ADD_ONE) bw_operand(p, v[u], operand);
-            SO::apply((j ? a_d1 : a_d0) + DTB * ls, operand);
-            if (!SO::narrow) bw_reds_or_u32(a_tm + 4 * (ls >> 4), 1u << (2 * (ls & 15) + j));
-            bw_reds_max_s32(a_mts + 4 * ls, rel);
-            if (SEQ) bw_reds_min_u32((j ? a_sq1 : a_sq0) + 4 * ls, r[u].w);
-            if (CNT) bw_reds_add_u32((j ? a_cn1 : a_cn0) + 4 * ls, 1u);
+        }
+      } else {
+        // ---- partials every source rank left for this bucket, in source order ----
+        for (u32 src = 0; src < A.world; ++src) {
+          const u32 n = min(A.pcnt_in[(size_t)src * A.nb_local + b], A.part_cap);
+          const Partial* pp = A.pin + ((size_t)src * A.nb_local + b) * A.part_cap;
+          for (u32 base = (u32)warp * 32; base < n; base += BW_SF_THREADS) {
+            const u32 i = base + (u32)lane;
+            Partial pr;
+            pr.key = BW_EMPTY_KEY;
+            pr.acc = 0;
+            pr.ts = 0;
+            pr.seq = 0;
+            pr.cnt = 0;
+            if (i < n) pr = pp[i];
+            const i64 d = pr.ts - A.ts0;
+            const int rel = (int)d;  // (the host checked the activation's span fits 32 bits)
+            const bool valid = i < n && d == (i64)rel && rel >= lo32 && rel < hi32;
+            const u64 hh = bw_khash(pr.key);
+            fold_one(valid, pr.key, rel, (u32)bw_slot_of_khash(hh, t.cap) & smask, bw_fp_of(hh), pr.acc, (src << 28) | (pr.seq & 0x0FFFFFFFu),
+                     pr.cnt);
           }
         }
       }
-      }  // lane
+      if (MODE == 1) {
+        // ---- partials out: what the merge would put in the table goes to the owning rank ----
+        __syncthreads();
+        const u32 d_rank = b / A.nb_local, bl = b % A.nb_local;
+        Partial* out = A.pout[d_rank] + (size_t)bl * A.part_cap;
+        for (u32 ls = threadIdx.x; ls < S; ls += BW_SF_THREADS) {
+          const int m = (int)bw_lds_u32(a_mts + 4 * ls);
+          if (m == INT32_MIN) continue;
+          const u64 key = bw_lds_u64(a_key + 8 * ls);
+          const u64 dvv[2] = {SO::load(a_d0 + DTB * ls), SO::load(a_d1 + DTB * ls)};
+          bool tch[2];
+          if (SO::narrow) {
+            tch[0] = dvv[0] != 0;
+            tch[1] = dvv[1] != 0;
+          } else {
+            const u32 bits = bw_lds_u32(a_tm + 4 * (ls >> 4)) >> (2 * (ls & 15));
+            tch[0] = bits & 1u;
+            tch[1] = bits & 2u;
+          }
+          const i64 ts_new = A.ts0 + (i64)m;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            if (!tch[j]) continue;
+            const u32 pos = atomicAdd(&part_n, 1u);
+            if (pos >= A.part_cap) continue;  // (raised below)
+            Partial pr;
+            pr.key = key;
+            pr.acc = dvv[j];
+            // the key's newest timestamp goes with its newest pane; the older pane just needs a timestamp inside it
+            pr.ts = (j == 0 && tch[1]) ? A.ts0 + pb1 - 1 : ts_new;
+            pr.seq = SEQ ? bw_lds_u32((j ? a_sq1 : a_sq0) + 4 * ls) : 0u;
+            pr.cnt = CNT ? bw_lds_u32((j ? a_cn1 : a_cn0) + 4 * ls) : 0u;
+            out[pos] = pr;
+          }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          if (part_n > A.part_cap) bw_raise(t.ctr, 3u);
+          A.pcnt_out[d_rank][bl] = min(part_n, A.part_cap);
+        }
+        continue;  // (npass == 1: next bucket)
+      }
       __syncthreads();
       // ---- merge: one thread per touched slot; the block owns the segment ----
       for (u32 ls = threadIdx.x; ls < S; ls += BW_SF_THREADS) {
@@ -933,6 +1061,7 @@ k_segfold(SegArgs A, Table t, FoldParams p, EmitBufs e) {
   }
   __syncthreads();
   bw_sinks_flush(&sink, t);
+  if (MODE == 1) __threadfence_system();  // the partials are in peer memory before the exchange barrier is entered
 }
 
 // Rows / partials that the streaming scheme set aside, through the general path of the direct kernel.

@@ -202,6 +202,18 @@ struct bw_fold {
   size_t segfold_smem = 0, scatter_smem = 0;
   int scatter_nstage = 3;
   u32 last_scatter_grid = 0, scatter_stg_cap = 0, scatter_stg_every = 1;
+  // multi-GPU streaming path: combine at the source, partials over NVLink, merge at the owner
+  segfold_kernel_t combine_kernel = nullptr, merge_kernel = nullptr;
+  int combine_grid = 0, merge_grid = 0;
+  u32 nb_local = 0, part_cap = 0;
+  void* precv_base = nullptr;            // this rank's receive regions (IPC-shared): [side]{cnt[W][nb_local], rec[W][nb_local][part_cap]}
+  void* precv_peer[BW_MAX_WORLD] = {nullptr};
+  size_t precv_cnt_off[2] = {0, 0}, precv_rec_off[2] = {0, 0};
+  VerdictGather* d_vg_local = nullptr;   // [2]
+  VerdictGather* d_vg_all = nullptr;     // [2][W]
+  VerdictGather* h_vg = nullptr;         // pinned [2][W]
+  i64 h_gmax = INT64_MIN;                // running maximum event time over all ranks (the verdict chain's memory)
+  u32* d_barrier_word = nullptr;
   cudaEvent_t ev_sv[2] = {nullptr, nullptr};
   StreamVerdict* h_sv = nullptr;  // pinned mirror of the two sides' verdicts
   Deferred dq{};            // the activation whose fold has not been launched yet
@@ -423,21 +435,23 @@ static fold_kernel_t pick_fold_kernel(const FoldParams& p) {
 }
 
 // k_segfold instantiations: accumulator op (+ counts for MEAN) x first-open indices
-template <int OP, int CNT>
+template <int OP, int CNT, int MODE>
 static segfold_kernel_t pick_seq(bool seq) {
-  return seq ? (segfold_kernel_t)k_segfold<FoldCfg<OP, -1, CNT>, true> : (segfold_kernel_t)k_segfold<FoldCfg<OP, -1, CNT>, false>;
+  return seq ? (segfold_kernel_t)k_segfold<FoldCfg<OP, -1, CNT>, true, MODE> : (segfold_kernel_t)k_segfold<FoldCfg<OP, -1, CNT>, false, MODE>;
 }
+// MODE: 0 one GPU, 1 combine at the source rank, 2 merge at the owning rank (bw_stream.cuh)
+template <int MODE>
 static segfold_kernel_t pick_segfold_kernel(const FoldParams& p) {
   const bool seq = !p.seq_by_id;
-  if (p.need_count) return pick_seq<BW_OP_ADD_F64, 1>(seq);
+  if (p.need_count) return pick_seq<BW_OP_ADD_F64, 1, MODE>(seq);
   switch (p.op) {
-    case BW_OP_ADD_ONE: return pick_seq<BW_OP_ADD_ONE, 0>(seq);
-    case BW_OP_ADD_U64: return pick_seq<BW_OP_ADD_U64, 0>(seq);
-    case BW_OP_ADD_F64: return pick_seq<BW_OP_ADD_F64, 0>(seq);
-    case BW_OP_MIN_S64: return pick_seq<BW_OP_MIN_S64, 0>(seq);
-    case BW_OP_MIN_U64: return pick_seq<BW_OP_MIN_U64, 0>(seq);
-    case BW_OP_MAX_S64: return pick_seq<BW_OP_MAX_S64, 0>(seq);
-    default: return pick_seq<BW_OP_MAX_U64, 0>(seq);
+    case BW_OP_ADD_ONE: return pick_seq<BW_OP_ADD_ONE, 0, MODE>(seq);
+    case BW_OP_ADD_U64: return pick_seq<BW_OP_ADD_U64, 0, MODE>(seq);
+    case BW_OP_ADD_F64: return pick_seq<BW_OP_ADD_F64, 0, MODE>(seq);
+    case BW_OP_MIN_S64: return pick_seq<BW_OP_MIN_S64, 0, MODE>(seq);
+    case BW_OP_MIN_U64: return pick_seq<BW_OP_MIN_U64, 0, MODE>(seq);
+    case BW_OP_MAX_S64: return pick_seq<BW_OP_MAX_S64, 0, MODE>(seq);
+    default: return pick_seq<BW_OP_MAX_U64, 0, MODE>(seq);
   }
 }
 // k_scatter instantiations: timestamp source x value bytes read / stored
@@ -455,9 +469,12 @@ static bw_status stream_alloc(bw_fold* f) {
   bw_ctx* ctx = f->ctx;
   StreamBufs& sb = f->sb;
   const u64 rows = f->spec.max_batch_rows;
-  const u64 nb = f->t.cap >> f->t.seg_shift;
+  const int W = ctx->world;
+  f->nb_local = (u32)(f->t.cap >> f->t.seg_shift);
+  const u64 nb = (u64)f->nb_local * W;  // buckets of the scatter: (owning rank, segment of its table)
   if (const char* e = getenv("BW_STREAM")) f->stream_mode = atoi(e) ? 1 : 0;
-  if (!f->stream_mode || ctx->world != 1 || nb > BW_STREAM_MAX_NB || rows >= (1ULL << 32)) return BW_OK;
+  if (!f->stream_mode || nb > BW_STREAM_MAX_NB || rows >= (1ULL << 28)) return BW_OK;
+  if (W > 1 && f->spec.exchange != BW_XCHG_P2P) return BW_OK;  // the partials travel as peer stores
   // wait == forever with event time: nothing closes before EOF, every key grows an overflow list of panes --
   // the shape the direct kernel's general path is for
   if (!f->p.track_wm && f->p.ts_from_value != 2) return BW_OK;
@@ -469,7 +486,7 @@ static bw_status stream_alloc(bw_fold* f) {
   const u64 max_tiles = (rows + BW_SC_TILE - 1) / BW_SC_TILE;
   const double block_rows = (double)((max_tiles + sb.nlanes - 1) / sb.nlanes) * BW_SC_TILE;
   const double mean = block_rows / (double)nb;
-  const double keys_per_bucket = std::max(1.0, (double)std::max<u64>(f->spec.capacity_hint, 1) / (double)nb);
+  const double keys_per_bucket = std::max(1.0, (double)std::max<u64>(f->spec.capacity_hint, 1) / (double)f->nb_local);
   const double sigma = std::sqrt(mean + mean * mean / keys_per_bucket);
   sb.lane_cap = (u32)std::min<double>(block_rows, mean + 6.0 * sigma + 24.0);
   sb.lane_cap = (sb.lane_cap + 7u) & ~7u;
@@ -519,11 +536,63 @@ static bw_status stream_alloc(bw_fold* f) {
   int occ = 0;
   CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)f->scatter_kernel, BW_SC_THREADS, f->scatter_smem));
   f->scatter_grid = ctx->sm_count * std::max(occ, 1);
-  f->segfold_kernel = pick_segfold_kernel(f->p);
+  f->segfold_kernel = pick_segfold_kernel<0>(f->p);
   f->segfold_smem = bw_segfold_smem(1u << f->t.seg_shift, f->p.op, !f->p.seq_by_id, f->p.need_count != 0);
   CU(ctx, cudaFuncSetAttribute((const void*)f->segfold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
   CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)f->segfold_kernel, BW_SF_THREADS, f->segfold_smem));
   f->segfold_grid = ctx->sm_count * std::max(occ, 1);
+  if (W > 1) {
+    f->combine_kernel = pick_segfold_kernel<1>(f->p);
+    f->merge_kernel = pick_segfold_kernel<2>(f->p);
+    for (segfold_kernel_t k : {f->combine_kernel, f->merge_kernel}) {
+      CU(ctx, cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+      CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)k, BW_SF_THREADS, f->segfold_smem));
+      (k == f->combine_kernel ? f->combine_grid : f->merge_grid) = ctx->sm_count * std::max(occ, 1);
+    }
+    // receive regions: a source can leave at most two partials (two panes) per slot of a segment
+    f->part_cap = 2u << f->t.seg_shift;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+      size_t o = off;
+      off += (bytes + 255) & ~(size_t)255;
+      return o;
+    };
+    for (int sd = 0; sd < 2; ++sd) {
+      f->precv_cnt_off[sd] = take(sizeof(u32) * (size_t)W * f->nb_local);
+      f->precv_rec_off[sd] = take(sizeof(Partial) * (size_t)W * f->nb_local * f->part_cap);
+    }
+    CU(ctx, cudaMalloc(&f->precv_base, off));
+    CU(ctx, cudaMemset(f->precv_base, 0, off));
+    {
+      cudaIpcMemHandle_t mine;
+      CU(ctx, cudaIpcGetMemHandle(&mine, f->precv_base));
+      unsigned char *d_in = nullptr, *d_all = nullptr;
+      CU(ctx, cudaMalloc(&d_in, 64));
+      CU(ctx, cudaMalloc(&d_all, 64 * W));
+      CU(ctx, cudaMemcpy(d_in, &mine, 64, cudaMemcpyHostToDevice));
+      NC(ctx, ncclAllGather(d_in, d_all, 64, ncclChar, ctx->comm, f->s_compute));
+      CU(ctx, cudaStreamSynchronize(f->s_compute));
+      std::vector<cudaIpcMemHandle_t> all(W);
+      CU(ctx, cudaMemcpy(all.data(), d_all, 64 * W, cudaMemcpyDeviceToHost));
+      cudaFree(d_in);
+      cudaFree(d_all);
+      for (int r = 0; r < W; ++r) {
+        if (r == ctx->rank) f->precv_peer[r] = f->precv_base;
+        else CU(ctx, cudaIpcOpenMemHandle(&f->precv_peer[r], all[r], cudaIpcMemLazyEnablePeerAccess));
+      }
+    }
+    CU(ctx, dmalloc(&f->d_vg_local, 2));
+    CU(ctx, dmalloc(&f->d_vg_all, 2 * (size_t)W));
+    CU(ctx, cudaHostAlloc((void**)&f->h_vg, sizeof(VerdictGather) * 2 * W, cudaHostAllocDefault));
+    CU(ctx, dmalloc(&f->d_barrier_word, 1));
+    CU(ctx, cudaMemset(f->d_barrier_word, 0, 4));
+    // the legacy path is now the fallback of single activations: it runs in line with the rest (its own stream only
+    // bought overlap between consecutive legacy activations, and its lateness pass must see the maximum set here)
+    if (f->s_x && f->s_x != f->s_compute) {
+      cudaStreamDestroy(f->s_x);
+      f->s_x = f->s_compute;
+    }
+  }
   f->stream_ok = true;
   return BW_OK;
 }
@@ -539,6 +608,11 @@ static bw_status fold_alloc(bw_fold* f) {
     if (v >= 10 && v <= 90) load_pct = v;
   }
   u32 seg_shift = BW_SEG_SHIFT_DEFAULT;
+  {
+    // multi-GPU: the scatter buckets by (owning rank, segment): keep world x segments near the one-GPU bucket count
+    const u64 want = (std::max<u64>(s.capacity_hint, 1) * 100 + load_pct - 1) / load_pct;
+    if (ctx->world > 1 && (u64)ctx->world * ((want >> seg_shift) + 1) > 1024) seg_shift = 12;
+  }
   if (const char* e = getenv("BW_SEG_SHIFT")) seg_shift = (u32)std::max(10, std::min(12, atoi(e)));
   const u64 seg_slots = 1ULL << seg_shift;
   u64 cap = std::max<u64>(seg_slots, (std::max<u64>(s.capacity_hint, 1) * 100 + load_pct - 1) / load_pct);
@@ -1109,10 +1183,18 @@ static bw_status stream_front(bw_fold* f, const u64* d_keys, const void* d_vals,
   A.stg_cap = f->scatter_stg_cap;
   A.stg_every = f->scatter_stg_every;
   A.batch_no = batch_no;
+  A.world = (u32)ctx->world;
+  A.nb_local = f->nb_local;
+  const bool multi = ctx->world > 1;
+  // multi-GPU: every rank goes through here for every activation (the verdicts are gathered collectively); a rank
+  // whose columns the scatter cannot read (no rows, unaligned) sends no rows / asks everyone for the legacy path
+  const bool usable = stream_usable(f, d_keys, d_vals, d_ts, rows);
+  VerdictGather* vg = multi ? f->d_vg_local + side : nullptr;
   const u64 T = BW_SC_TILE;
-  const u64 ntiles = (rows + T - 1) / T;
+  const u64 ntiles = usable ? (rows + T - 1) / T : 0;
   const int grid = (int)std::min<u64>(ntiles, (u64)std::min<u32>((u32)f->scatter_grid, sb.nlanes));
   f->last_scatter_grid = (u32)grid;
+  if (multi && !usable && rows) CU(ctx, cudaMemsetAsync(&sb.side[side].sv->flags, 0xFF, sizeof(u32), s));  // every flag: legacy path
   EventPair* ep = next_timer(f);
   if (ep) {
     ep->rows = rows;
@@ -1120,21 +1202,214 @@ static bw_status stream_front(bw_fold* f, const u64* d_keys, const void* d_vals,
     CU(ctx, cudaEventRecord(ep->a, s));
   }
   f->pt.mark(5, 0, s);
-  f->scatter_kernel<<<grid, BW_SC_THREADS, f->scatter_smem, s>>>(A, f->p);
-  if (f->p.ts_from_value == 2) k_verdict_none<<<1, 1, 0, s>>>(f->p, f->d_ctr, sb.side[side].sv);
+  if (grid) f->scatter_kernel<<<grid, BW_SC_THREADS, f->scatter_smem, s>>>(A, f->p);
+  if (f->p.ts_from_value == 2) k_verdict_none<<<1, 1, 0, s>>>(f->p, f->d_ctr, sb.side[side].sv, vg, rows);
   else
     k_verdict<<<1, 1024, 0, s>>>(sb.tile_min, sb.tile_max, sb.tile_bad, (u32)ntiles, f->p, f->d_ctr, sb.side[side].sv,
-                                 f->has_ts ? d_ts : nullptr, (const u64*)d_vals);
+                                 f->has_ts ? d_ts : nullptr, (const u64*)d_vals, vg);
   CU(ctx, cudaGetLastError());
   f->pt.mark(5, 1, s);
   if (ep) CU(ctx, cudaEventRecord(ep->b, s));
   f->st.kernel_launches += 2;
   CU(ctx, cudaMemcpyAsync(&f->h_sv[side], sb.side[side].sv, sizeof(StreamVerdict), cudaMemcpyDeviceToHost, s));
+  if (multi) {
+    VerdictGather* all = f->d_vg_all + (size_t)side * ctx->world;
+    NC(ctx, ncclAllGather(vg, all, sizeof(VerdictGather), ncclChar, ctx->comm, s));
+    CU(ctx, cudaMemcpyAsync(f->h_vg + (size_t)side * ctx->world, all, sizeof(VerdictGather) * ctx->world, cudaMemcpyDeviceToHost, s));
+  }
   CU(ctx, cudaEventRecord(f->ev_sv[side], s));
   return BW_OK;
 }
 
 static bw_status slow_path(bw_fold* f, const BatchView& bv, u64 total, u64 epoch_ord, u32 batch_no);
+
+static bw_status slow_path(bw_fold* f, const BatchView& bv, u64 total, u64 epoch_ord, u32 batch_no);
+
+// The direct path of one activation, start to finish: (world > 1: partition + exchange of the rows) -> lateness pass ->
+// k_fold or the exact path -> K4.
+static bw_status legacy_batch(bw_fold* f, const u64* d_keys, const void* d_vals, const i64* d_ts, u64 rows, u32 batch_no, u64 ord, Stage* stage) {
+  bw_ctx* ctx = f->ctx;
+  BatchView bv;
+  memset(&bv, 0, sizeof bv);
+  u64 max_total = rows;
+  cudaStream_t pre_stream = f->s_pre;
+  if (ctx->world > 1) {
+    bw_status st = exchange(f, d_keys, d_vals, d_ts, rows, &bv);
+    if (st != BW_OK) return st;
+    max_total = f->max_recv_rows;
+    pre_stream = f->s_x;  // the verdict is computed right behind the exchange, beside the previous fold
+  } else {
+    bv.nseg = 1;
+    bv.keys[0] = d_keys;
+    bv.vals[0] = d_vals;
+    bv.ts[0] = f->has_ts ? d_ts : nullptr;
+    bv.h_counts[0] = rows;
+    bv.max_rows = rows;
+    f->st.rows_received += rows;
+  }
+  bool clean = true;
+  if (f->p.track_wm && max_total > 0) {
+    if (pre_stream != f->s_compute && ctx->world == 1 && f->pre_wait) CU(ctx, cudaStreamWaitEvent(pre_stream, f->pre_wait, 0));
+    const u64 nranges = (max_total + BW_RANGE_ROWS - 1) / BW_RANGE_ROWS;
+    // one warp per 2048-row range; cap at 64 warps per SM in total (the block size is small so that a block fits beside the fold)
+    int grid = (int)std::min<u64>((nranges * 32 + BW_PRE_THREADS - 1) / BW_PRE_THREADS, (u64)ctx->sm_count * (2048 / BW_PRE_THREADS));
+    if (grid < 1) grid = 1;
+    f->pt.mark(2, 0, pre_stream);
+    k_prepass_ranges<<<grid, BW_PRE_THREADS, 0, pre_stream>>>(bv, f->p, f->d_rmin, f->d_rmax, f->d_rbad);
+    k_prepass_scan<<<1, 1024, 0, pre_stream>>>(bv, f->p, f->d_rmin, f->d_rmax, f->d_rbad, f->d_ctr, f->d_verdict, f->d_span);
+    CU(ctx, cudaGetLastError());
+    f->st.kernel_launches += 2;
+    f->pt.mark(2, 1, pre_stream);
+    CU(ctx, cudaMemcpyAsync(f->h_verdict, f->d_verdict, sizeof(u32), cudaMemcpyDeviceToHost, pre_stream));
+    CU(ctx, cudaMemcpyAsync(f->h_verdict + 4, f->d_span, 2 * sizeof(i64), cudaMemcpyDeviceToHost, pre_stream));
+    CU(ctx, cudaEventRecord(f->ev_pre, pre_stream));
+    CU(ctx, cudaEventSynchronize(f->ev_pre));
+    clean = (*f->h_verdict != 0);
+    if (pre_stream != f->s_compute) CU(ctx, cudaStreamWaitEvent(f->s_compute, f->ev_pre, 0));
+  }
+  if (ctx->world > 1) {  // the fold may start once the exchange (and the verdict pass behind it) is done
+    CU(ctx, cudaEventRecord(f->ev_xchg_done, f->s_x));
+    CU(ctx, cudaStreamWaitEvent(f->s_compute, f->ev_xchg_done, 0));
+  }
+  if (max_total > 0) {
+    if (clean) {
+      const u64 known = (ctx->world == 1) ? rows : max_total;
+      const i64 tmin = ((const i64*)(f->h_verdict + 4))[0], tmax = ((const i64*)(f->h_verdict + 4))[1];
+      bw_status st = direct_fold(f, bv, known, batch_no, ord, f->p.track_wm ? tmin : 0, f->p.track_wm ? tmax : 0);
+      if (st != BW_OK) return st;
+    } else {
+      u64 total = rows;
+      if (ctx->world > 1) {
+        u64 hc[BW_MAX_WORLD];
+        CU(ctx, cudaMemcpyAsync(hc, bv.d_counts, sizeof(u64) * ctx->world, cudaMemcpyDeviceToHost, f->s_compute));
+        CU(ctx, cudaStreamSynchronize(f->s_compute));
+        total = 0;
+        for (int r = 0; r < ctx->world; ++r) total += hc[r];
+      }
+      bw_status st = slow_path(f, bv, total, ord, batch_no);
+      if (st != BW_OK) return st;
+      f->st.slow_batches++;
+    }
+    bw_status st = close_stage(f, ord, batch_no, nullptr);
+    if (st != BW_OK) return st;
+  }
+  if (ctx->world > 1) {
+    CU(ctx, cudaEventRecord(f->ev_fold_done, f->s_compute));
+    f->fold_recorded = true;
+  }
+  if (stage) {
+    CU(ctx, cudaEventRecord(stage->consumed, f->s_compute));
+    stage->used = true;
+  }
+  return BW_OK;
+}
+
+
+// Multi-GPU fold stage of the deferred activation.  Every rank has the same gathered verdicts, so every rank takes
+// the same branch (the collectives below line up): either combine -> partials over NVLink -> barrier -> merge, or
+// the legacy path (partition + exchange of the raw rows, direct / exact fold).
+static bw_status stream_resolve_multi(bw_fold* f, const Deferred& d) {
+  bw_ctx* ctx = f->ctx;
+  const StreamBufs& sb = f->sb;
+  const FoldParams& p = f->p;
+  cudaStream_t s = f->s_compute;
+  const int W = ctx->world, R = ctx->rank;
+  const StreamVerdict sv = f->h_sv[d.side];
+  const VerdictGather* vg = f->h_vg + (size_t)d.side * W;
+  // chain the ranks' slices in source order: the arrival order at every destination (bw_prepass.cuh's rule)
+  i64 running = f->h_gmax, gmin = INT64_MAX, gmax = INT64_MIN;
+  bool bad = false, unfit = false;
+  for (int r = 0; r < W; ++r) {
+    if (vg[r].flags || vg[r].n_spill) unfit = true;  // a row some scatter set aside belongs to another rank's table
+    if (vg[r].tmax < vg[r].tmin) continue;            // no rows on that rank
+    if (vg[r].bad || vg[r].tmin < bw_sub_sat(running, p.wait_us)) bad = true;
+    running = std::max(running, vg[r].tmax);
+    gmin = std::min(gmin, vg[r].tmin);
+    gmax = std::max(gmax, vg[r].tmax);
+    // the combine folds a rank's slice in one pass: two panes
+    if (bw_floordiv(vg[r].tmax - p.align_us, p.pane_us) - bw_floordiv(vg[r].tmin - p.align_us, p.pane_us) > 1) unfit = true;
+  }
+  const bool any_rows = gmax >= gmin;
+  const bool clean = !p.track_wm || !bad;
+  i64 q_lo = 0, q_hi = 0;
+  if (any_rows) {
+    q_lo = bw_floordiv(gmin - p.align_us, p.pane_us);
+    q_hi = bw_floordiv(gmax - p.align_us, p.pane_us);
+    if ((u64)(gmax - gmin) >= 0x7FFFFFF0ULL || q_hi - q_lo >= 2 * 64) unfit = true;
+  }
+  f->h_gmax = running;
+  k_set_gmax<<<1, 1, 0, s>>>(f->d_ctr, running);  // (the legacy path's lateness pass chains from the same maximum)
+  f->st.kernel_launches++;
+  if (!clean || unfit) {
+    bw_status st = legacy_batch(f, d.d_keys, d.d_vals, d.d_ts, d.rows, d.batch_no, d.ord, d.stage);
+    if (st != BW_OK) return st;
+    k_stream_reset<<<1, 1, 0, s>>>(f->t, sb.side[d.side].sv);
+    k_set_gmax<<<1, 1, 0, s>>>(f->d_ctr, running);
+    return BW_OK;
+  }
+  f->st.rows_received += d.rows;  // (this rank's share of the rows arrives as partials)
+  SegArgs A;
+  memset(&A, 0, sizeof A);
+  A.in = sb.side[d.side];
+  A.nb = sb.nb;
+  A.nlanes = sb.nlanes;
+  A.lane_cap = sb.lane_cap;
+  A.nlanes_used = d.lanes;
+  A.spill_cap = sb.spill_cap;
+  A.val_bytes = sb.val_bytes;
+  A.seg_shift = f->t.seg_shift;
+  A.world = (u32)W;
+  A.rank = (u32)R;
+  A.nb_local = f->nb_local;
+  A.part_cap = f->part_cap;
+  A.batch_no = d.batch_no;
+  A.epoch = d.ord;
+  for (int r = 0; r < W; ++r) {
+    char* base = (char*)f->precv_peer[r];
+    A.pcnt_out[r] = (u32*)(base + f->precv_cnt_off[d.side]) + (size_t)R * f->nb_local;
+    A.pout[r] = (Partial*)(base + f->precv_rec_off[d.side]) + (size_t)R * f->nb_local * f->part_cap;
+  }
+  A.pcnt_in = (const u32*)((char*)f->precv_base + f->precv_cnt_off[d.side]);
+  A.pin = (const Partial*)((char*)f->precv_base + f->precv_rec_off[d.side]);
+  EventPair* ep = next_timer(f);
+  if (ep) {
+    ep->rows = d.rows;
+    ep->kind = 0;
+    CU(ctx, cudaEventRecord(ep->a, s));
+  }
+  // combine this rank's slice (one pass over its own two panes) and store the partials in their owners' regions
+  A.ts0 = sv.ts0;
+  A.q_lo = (sv.tmax >= sv.tmin) ? bw_floordiv(sv.tmin - p.align_us, p.pane_us) : 0;
+  A.npass = 1;
+  f->pt.mark(6, 0, s);
+  f->combine_kernel<<<(int)std::min<u32>(sb.nb, (u32)f->combine_grid), BW_SF_THREADS, f->segfold_smem, s>>>(A, f->t, f->p, f->e);
+  CU(ctx, cudaGetLastError());
+  // every rank's partials are in place once every rank has entered this collective
+  f->pt.mark(1, 0, s);
+  NC(ctx, ncclAllReduce(f->d_barrier_word, f->d_barrier_word, 1, ncclUint32, ncclMax, ctx->comm, s));
+  f->pt.mark(1, 1, s);
+  // merge what every source left for this rank's segments, in source order, over the activation's whole span
+  A.nb = f->nb_local;
+  A.ts0 = any_rows ? gmin : p.align_us;
+  A.q_lo = q_lo;
+  A.npass = (u32)((q_hi - q_lo) / 2 + 1);
+  f->merge_kernel<<<(int)std::min<u32>(f->nb_local, (u32)f->merge_grid), BW_SF_THREADS, f->segfold_smem, s>>>(A, f->t, f->p, f->e);
+  CU(ctx, cudaGetLastError());
+  f->pt.mark(6, 1, s);
+  if (ep) CU(ctx, cudaEventRecord(ep->b, s));
+  f->pt.mark(7, 0, s);
+  k_spill<<<ctx->sm_count, 256, 0, s>>>(f->t, f->p, sb.side[d.side].spill, sb.side[d.side].sv, sb.spill_cap, d.batch_no, 0u, 0xFFFFFFFFu);
+  f->st.kernel_launches += 3;
+  f->st.fold_launches++;
+  f->st.combined_folds++;
+  bw_status st = close_stage(f, d.ord, d.batch_no, sb.side[d.side].sv);
+  f->pt.mark(7, 1, s);
+  if (d.stage) {
+    CU(ctx, cudaEventRecord(d.stage->consumed, s));
+    d.stage->used = true;
+  }
+  return st;
+}
 
 // The fold stage of the deferred activation: the segment fold when its verdict allows, else what the
 // direct path would have done (its scatter output is dropped; the input columns are still there).
@@ -1146,6 +1421,7 @@ static bw_status stream_resolve(bw_fold* f) {
   const StreamBufs& sb = f->sb;
   cudaStream_t s = f->s_compute;
   CU(ctx, cudaEventSynchronize(f->ev_sv[d.side]));
+  if (ctx->world > 1) return stream_resolve_multi(f, d);
   const StreamVerdict sv = f->h_sv[d.side];
   const FoldParams& p = f->p;
   i64 q_lo = 0, q_hi = 0;
@@ -1245,11 +1521,11 @@ static bw_status run_batch(bw_fold* f, const u64* d_keys, const void* d_vals, co
   f->have_epoch = true;
   const u64 ord = epoch;
   f->st.rows_ingested += rows;
-  if (ctx->world == 1 && stream_usable(f, d_keys, d_vals, d_ts, rows)) {
+  if (ctx->world > 1 ? f->stream_ok : stream_usable(f, d_keys, d_vals, d_ts, rows)) {
     // queue this activation's scatter + verdict BEFORE looking at the previous verdict: the device
     // always has the next stage waiting while the host decides
     const int side = (int)(batch_no & 1u);
-    f->st.rows_received += rows;
+    if (ctx->world == 1) f->st.rows_received += rows;
     bw_status st = stream_front(f, d_keys, d_vals, d_ts, rows, batch_no, side);
     if (st != BW_OK) return st;
     st = stream_resolve(f);
@@ -1271,79 +1547,7 @@ static bw_status run_batch(bw_fold* f, const u64* d_keys, const void* d_vals, co
     bw_status st = stream_resolve(f);
     if (st != BW_OK) return st;
   }
-  BatchView bv;
-  memset(&bv, 0, sizeof bv);
-  u64 max_total = rows;
-  cudaStream_t pre_stream = f->s_pre;
-  if (ctx->world > 1) {
-    bw_status st = exchange(f, d_keys, d_vals, d_ts, rows, &bv);
-    if (st != BW_OK) return st;
-    max_total = f->max_recv_rows;
-    pre_stream = f->s_x;  // the verdict is computed right behind the exchange, beside the previous fold
-  } else {
-    bv.nseg = 1;
-    bv.keys[0] = d_keys;
-    bv.vals[0] = d_vals;
-    bv.ts[0] = f->has_ts ? d_ts : nullptr;
-    bv.h_counts[0] = rows;
-    bv.max_rows = rows;
-    f->st.rows_received += rows;
-  }
-  bool clean = true;
-  if (f->p.track_wm && max_total > 0) {
-    if (pre_stream != f->s_compute && ctx->world == 1 && f->pre_wait) CU(ctx, cudaStreamWaitEvent(pre_stream, f->pre_wait, 0));
-    const u64 nranges = (max_total + BW_RANGE_ROWS - 1) / BW_RANGE_ROWS;
-    // one warp per 2048-row range; cap at 64 warps per SM in total (the block size is small so that a block fits beside the fold)
-    int grid = (int)std::min<u64>((nranges * 32 + BW_PRE_THREADS - 1) / BW_PRE_THREADS, (u64)ctx->sm_count * (2048 / BW_PRE_THREADS));
-    if (grid < 1) grid = 1;
-    f->pt.mark(2, 0, pre_stream);
-    k_prepass_ranges<<<grid, BW_PRE_THREADS, 0, pre_stream>>>(bv, f->p, f->d_rmin, f->d_rmax, f->d_rbad);
-    k_prepass_scan<<<1, 1024, 0, pre_stream>>>(bv, f->p, f->d_rmin, f->d_rmax, f->d_rbad, f->d_ctr, f->d_verdict, f->d_span);
-    CU(ctx, cudaGetLastError());
-    f->st.kernel_launches += 2;
-    f->pt.mark(2, 1, pre_stream);
-    CU(ctx, cudaMemcpyAsync(f->h_verdict, f->d_verdict, sizeof(u32), cudaMemcpyDeviceToHost, pre_stream));
-    CU(ctx, cudaMemcpyAsync(f->h_verdict + 4, f->d_span, 2 * sizeof(i64), cudaMemcpyDeviceToHost, pre_stream));
-    CU(ctx, cudaEventRecord(f->ev_pre, pre_stream));
-    CU(ctx, cudaEventSynchronize(f->ev_pre));
-    clean = (*f->h_verdict != 0);
-    if (pre_stream != f->s_compute) CU(ctx, cudaStreamWaitEvent(f->s_compute, f->ev_pre, 0));
-  }
-  if (ctx->world > 1) {  // the fold may start once the exchange (and the verdict pass behind it) is done
-    CU(ctx, cudaEventRecord(f->ev_xchg_done, f->s_x));
-    CU(ctx, cudaStreamWaitEvent(f->s_compute, f->ev_xchg_done, 0));
-  }
-  if (max_total > 0) {
-    if (clean) {
-      const u64 known = (ctx->world == 1) ? rows : max_total;
-      const i64 tmin = ((const i64*)(f->h_verdict + 4))[0], tmax = ((const i64*)(f->h_verdict + 4))[1];
-      bw_status st = direct_fold(f, bv, known, batch_no, ord, f->p.track_wm ? tmin : 0, f->p.track_wm ? tmax : 0);
-      if (st != BW_OK) return st;
-    } else {
-      u64 total = rows;
-      if (ctx->world > 1) {
-        u64 hc[BW_MAX_WORLD];
-        CU(ctx, cudaMemcpyAsync(hc, bv.d_counts, sizeof(u64) * ctx->world, cudaMemcpyDeviceToHost, f->s_compute));
-        CU(ctx, cudaStreamSynchronize(f->s_compute));
-        total = 0;
-        for (int r = 0; r < ctx->world; ++r) total += hc[r];
-      }
-      bw_status st = slow_path(f, bv, total, ord, batch_no);
-      if (st != BW_OK) return st;
-      f->st.slow_batches++;
-    }
-    bw_status st = close_stage(f, ord, batch_no, nullptr);
-    if (st != BW_OK) return st;
-  }
-  if (ctx->world > 1) {
-    CU(ctx, cudaEventRecord(f->ev_fold_done, f->s_compute));
-    f->fold_recorded = true;
-  }
-  if (stage) {
-    CU(ctx, cudaEventRecord(stage->consumed, f->s_compute));
-    stage->used = true;
-  }
-  return BW_OK;
+  return legacy_batch(f, d_keys, d_vals, d_ts, rows, batch_no, ord, stage);
 }
 
 bw_status bw_ingest_commit(bw_fold* f, const bw_batch* batch, uint64_t rows, uint64_t epoch) {
@@ -1744,6 +1948,7 @@ bw_status bw_snapshot_load(bw_fold* f, const bw_snapshot* in) {
   CU(ctx, cudaStreamSynchronize(s));
   if (f->h_ctr->err) FAIL(f, (bw_status)f->h_ctr->err, "restore failed on the device with status %u (capacity_hint too small?)", f->h_ctr->err);
   f->batch_no = (u32)in->batch_no;
+  f->h_gmax = std::max<i64>(f->h_gmax, (i64)in->gmax_ts_us);
   f->last_epoch = in->last_epoch;
   f->have_epoch = in->last_epoch != 0;
   return BW_OK;

@@ -71,7 +71,7 @@ def main():
             mine = dict(
                 ck=np.concatenate([em.closed_key, em2.closed_key]), cw=np.concatenate([em.closed_window_id, em2.closed_window_id]),
                 ca=np.concatenate([em.closed_acc, em2.closed_acc]).astype(np.int64), lk=em.late_key, lw=em.late_window_id,
-                lv=em.late_val.astype(np.int64), slow=int(st.slow_batches))
+                lv=em.late_val.astype(np.int64), slow=int(st.slow_batches), stream=int(st.combined_folds))
             fold.close()
             gathered = [None] * world
             dist.all_gather_object(gathered, pickle.dumps(mine))
@@ -95,6 +95,9 @@ def main():
                         failures.append((xname, case, red, d, len(ck), len(got["ck"]), len(lk), len(got["lk"])))
                     if case == "inorder" and got["slow"] != 0:
                         failures.append((xname, case, "unexpected slow path", d))
+                    # in-order slices over P2P take the streaming path: combine at the source, partials over NVLink, merge
+                    if case == "inorder" and xname == "p2p" and os.environ.get("BW_STREAM", "1") != "0" and got["stream"] != len(batches):
+                        failures.append((xname, case, "streaming path not taken", d, got["stream"]))
     if rank == 0:
         print("MULTI_GPU_PARITY", "FAIL " + repr(failures) if failures else "OK", flush=True)
     ctx.close()
