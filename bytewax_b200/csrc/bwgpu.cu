@@ -212,6 +212,8 @@ struct bw_fold {
   VerdictGather* d_vg_local = nullptr;   // [2]
   VerdictGather* d_vg_all = nullptr;     // [2][W]
   VerdictGather* h_vg = nullptr;         // pinned [2][W]
+  bool vg_pending[2] = {false, false};   // a side's local verdict is computed but not gathered yet
+  cudaEvent_t ev_vg[2] = {nullptr, nullptr};
   i64 h_gmax = INT64_MIN;                // running maximum event time over all ranks (the verdict chain's memory)
   u32* d_barrier_word = nullptr;
   cudaEvent_t ev_sv[2] = {nullptr, nullptr};
@@ -1212,11 +1214,7 @@ static bw_status stream_front(bw_fold* f, const u64* d_keys, const void* d_vals,
   if (ep) CU(ctx, cudaEventRecord(ep->b, s));
   f->st.kernel_launches += 2;
   CU(ctx, cudaMemcpyAsync(&f->h_sv[side], sb.side[side].sv, sizeof(StreamVerdict), cudaMemcpyDeviceToHost, s));
-  if (multi) {
-    VerdictGather* all = f->d_vg_all + (size_t)side * ctx->world;
-    NC(ctx, ncclAllGather(vg, all, sizeof(VerdictGather), ncclChar, ctx->comm, s));
-    CU(ctx, cudaMemcpyAsync(f->h_vg + (size_t)side * ctx->world, all, sizeof(VerdictGather) * ctx->world, cudaMemcpyDeviceToHost, s));
-  }
+  if (multi) f->vg_pending[side] = true;  // gathered by the next collective on the stream (gather_verdict)
   CU(ctx, cudaEventRecord(f->ev_sv[side], s));
   return BW_OK;
 }
@@ -1305,6 +1303,21 @@ static bw_status legacy_batch(bw_fold* f, const u64* d_keys, const void* d_vals,
 }
 
 
+// One collective per activation: the all-gather that brings every rank's verdict of the activation just scattered is
+// also the barrier behind the previous activation's combine (a rank enters it after its peer stores, in stream order).
+static bw_status gather_verdict(bw_fold* f, int side) {
+  bw_ctx* ctx = f->ctx;
+  cudaStream_t s = f->s_compute;
+  const int W = ctx->world;
+  VerdictGather* all = f->d_vg_all + (size_t)side * W;
+  NC(ctx, ncclAllGather(f->d_vg_local + side, all, sizeof(VerdictGather), ncclChar, ctx->comm, s));
+  CU(ctx, cudaMemcpyAsync(f->h_vg + (size_t)side * W, all, sizeof(VerdictGather) * W, cudaMemcpyDeviceToHost, s));
+  if (!f->ev_vg[side]) CU(ctx, cudaEventCreateWithFlags(&f->ev_vg[side], cudaEventDisableTiming));
+  CU(ctx, cudaEventRecord(f->ev_vg[side], s));
+  f->vg_pending[side] = false;
+  return BW_OK;
+}
+
 // Multi-GPU fold stage of the deferred activation.  Every rank has the same gathered verdicts, so every rank takes
 // the same branch (the collectives below line up): either combine -> partials over NVLink -> barrier -> merge, or
 // the legacy path (partition + exchange of the raw rows, direct / exact fold).
@@ -1315,6 +1328,14 @@ static bw_status stream_resolve_multi(bw_fold* f, const Deferred& d) {
   cudaStream_t s = f->s_compute;
   const int W = ctx->world, R = ctx->rank;
   const StreamVerdict sv = f->h_sv[d.side];
+  // this activation's verdicts: gathered by the previous activation's exchange barrier, else (first activation, or
+  // after a flush) by a collective of their own
+  if (f->vg_pending[d.side]) {
+    bw_status gst = gather_verdict(f, d.side);
+    if (gst != BW_OK) return gst;
+  }
+  CU(ctx, cudaEventSynchronize(f->ev_vg[d.side]));
+  const int next_side = d.side ^ 1;  // the activation scattered after this one (if any) waits for its gather
   const VerdictGather* vg = f->h_vg + (size_t)d.side * W;
   // chain the ranks' slices in source order: the arrival order at every destination (bw_prepass.cuh's rule)
   i64 running = f->h_gmax, gmin = INT64_MAX, gmax = INT64_MIN;
@@ -1341,6 +1362,10 @@ static bw_status stream_resolve_multi(bw_fold* f, const Deferred& d) {
   k_set_gmax<<<1, 1, 0, s>>>(f->d_ctr, running);  // (the legacy path's lateness pass chains from the same maximum)
   f->st.kernel_launches++;
   if (!clean || unfit) {
+    if (f->vg_pending[next_side]) {
+      bw_status gst = gather_verdict(f, next_side);
+      if (gst != BW_OK) return gst;
+    }
     bw_status st = legacy_batch(f, d.d_keys, d.d_vals, d.d_ts, d.rows, d.batch_no, d.ord, d.stage);
     if (st != BW_OK) return st;
     k_stream_reset<<<1, 1, 0, s>>>(f->t, sb.side[d.side].sv);
@@ -1384,9 +1409,15 @@ static bw_status stream_resolve_multi(bw_fold* f, const Deferred& d) {
   f->pt.mark(6, 0, s);
   f->combine_kernel<<<(int)std::min<u32>(sb.nb, (u32)f->combine_grid), BW_SF_THREADS, f->segfold_smem, s>>>(A, f->t, f->p, f->e);
   CU(ctx, cudaGetLastError());
-  // every rank's partials are in place once every rank has entered this collective
+  // every rank's partials are in place once every rank has entered this collective -- which also carries the verdicts
+  // of the activation scattered after this one
   f->pt.mark(1, 0, s);
-  NC(ctx, ncclAllReduce(f->d_barrier_word, f->d_barrier_word, 1, ncclUint32, ncclMax, ctx->comm, s));
+  if (f->vg_pending[next_side]) {
+    bw_status gst = gather_verdict(f, next_side);
+    if (gst != BW_OK) return gst;
+  } else {
+    NC(ctx, ncclAllReduce(f->d_barrier_word, f->d_barrier_word, 1, ncclUint32, ncclMax, ctx->comm, s));
+  }
   f->pt.mark(1, 1, s);
   // merge what every source left for this rank's segments, in source order, over the activation's whole span
   A.nb = f->nb_local;
