@@ -663,14 +663,17 @@ k_segfold(SegArgs A, Table t, FoldParams p, EmitBufs e) {
       // accumulator updates issue once per warp.  Call with all 32 lanes.
       auto fold_one = [&](bool valid, u64 key, int rel, u32 ls, u32 fp, u64 operand, u32 seqv, u32 cntv) {
         const u32 fp4 = fp * 0x01010101u;
-        u32 wb = ls & ~15u;                 // window base
-        u32 ahead = 0xFFFFu << (ls & 15u);  // positions of the window at or after the home slot
+        // the window starts at the 8-aligned slot at or below the home slot: at least nine positions lie ahead of
+        // the home slot, so a second window is rare (a key is seldom displaced that far at load 0.5)
+        u32 wb = ls & ~7u;                 // window base
+        u32 ahead = 0xFFFFu << (ls & 7u);  // positions of the window at or after the home slot
         bool searching = valid, found = false;
         u32 tries = 0;
         while (__any_sync(0xffffffffu, searching)) {
           if (searching) {
             u32 w0, w1, w2, w3;
-            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(a_fp + wb) : "memory");
+            bw_lds_2u32(a_fp + wb, w0, w1);
+            bw_lds_2u32(a_fp + ((wb + 8) & smask), w2, w3);
             // free positions: bytes with bit 7 clear; matches: zero bytes of (word ^ fingerprint x 4), exact
             auto zmask = [](u32 x) { return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu); };  // 0x80 per zero byte
             auto pack4 = [](u32 m80) { return (m80 * 0x00204081u) >> 28; };                                // -> 4 bits
@@ -684,21 +687,21 @@ k_segfold(SegArgs A, Table t, FoldParams p, EmitBufs e) {
             while (cand) {
               const u32 pos = __ffs(cand) - 1;
               cand &= cand - 1;
-              if (bw_lds_u64(a_key + 8 * (wb + pos)) == key) {
-                ls = wb + pos;
+              if (bw_lds_u64(a_key + 8 * ((wb + pos) & smask)) == key) {
+                ls = (wb + pos) & smask;
                 hit = true;
                 break;
               }
             }
             if (!hit && freem) {
-              const u32 pos = __ffs(freem) - 1;
-              const u64 old = bw_atoms_cas_u64(a_key + 8 * (wb + pos), BW_EMPTY_KEY, key);
+              const u32 pos = (wb + __ffs(freem) - 1) & smask;
+              const u64 old = bw_atoms_cas_u64(a_key + 8 * pos, BW_EMPTY_KEY, key);
               if (old == BW_EMPTY_KEY) {
-                asm volatile("st.shared.u8 [%0], %1;" ::"r"(a_fp + wb + pos), "r"(fp) : "memory");
-                ls = wb + pos;
+                asm volatile("st.shared.u8 [%0], %1;" ::"r"(a_fp + pos), "r"(fp) : "memory");
+                ls = pos;
                 hit = true;
               } else if (old == key) {
-                ls = wb + pos;
+                ls = pos;
                 hit = true;
               }
               // else: another key won the slot (its fingerprint may not be visible yet): look at the window again
