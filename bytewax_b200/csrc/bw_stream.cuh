@@ -263,14 +263,16 @@ __global__ void __launch_bounds__(BW_SC_THREADS, 1) k_scatter(ScatterArgs A, Fol
       const u64 tile = blockIdx.x + (u64)s * gridDim.x;
       if (tile < ntiles) issue(tile, s);
     }
-  u32 it = 0;
+  // (running counters: the tile loop has no division by a run-time value -- each was ~25 instructions per warp and tile)
+  u32 it = 0, stage = 0, parity = 0, ring = 0, since_flush = 0;
+  const u64 bucket_stride = (u64)A.nlanes * A.lane_cap;    // rows between the regions of consecutive buckets
+  const u64 my_lane_off = (u64)blockIdx.x * A.lane_cap;   // this block's lane inside a bucket's region
   for (u64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-    const u32 stage = it % A.nstage;
     const u32 sk = stage0 + stage * STAGE, sv = sk + COLB_K, st = sv + COLB_V;
     const u64 tbase = tile * (u64)T;
     const u32 rows = (u32)((A.n - tbase < (u64)T) ? A.n - tbase : (u64)T);
     const u32 tr = rows & ~3u;
-    bw_mbar_wait(bars + 8 * stage, (it / A.nstage) & 1u);
+    bw_mbar_wait(bars + 8 * stage, parity);
     const u32 r0 = 2u * threadIdx.x;  // this thread's two rows of the tile
     const bool va = r0 < rows, vb = r0 + 1 < rows;
     u64 ka = 0, kb = 0, xa = 0, xb = 0;
@@ -338,7 +340,7 @@ __global__ void __launch_bounds__(BW_SC_THREADS, 1) k_scatter(ScatterArgs A, Fol
           ct.bad = __shfl_sync(0xffffffffu, ct.bad, 31);
         }
       }
-      const u32 ring = it % (2u * A.nstage);  // a warp is never nstage tiles ahead of another: 2 * nstage slots never collide
+      // (ring: a warp is never nstage tiles ahead of another, so 2 * nstage slots never collide)
       u32 last = 0;
       if (lane == 0) {
         ((volatile i64*)c_min[ring])[warp] = ct.mn;
@@ -386,7 +388,7 @@ __global__ void __launch_bounds__(BW_SC_THREADS, 1) k_scatter(ScatterArgs A, Fol
                        : "memory");
           stored = true;
         } else if (pos < A.lane_cap) {
-          const size_t at = ((size_t)b * A.nlanes + blockIdx.x) * A.lane_cap + pos;
+          const size_t at = (size_t)(b * bucket_stride + my_lane_off + pos);
           A.out.rec[at] = rec4;
           if (VB_OUT == 8) ((u64*)A.out.val)[at] = x;
           else if (VB_OUT == 4) ((u32*)A.out.val)[at] = (u32)x;
@@ -401,7 +403,13 @@ __global__ void __launch_bounds__(BW_SC_THREADS, 1) k_scatter(ScatterArgs A, Fol
       }
     }
     // every stg_every tiles (and after the last): write out what the buckets have assembled
-    if (VB_OUT == 0 && A.stg_cap && ((it + 1) % A.stg_every == 0 || it + 1 == my_tiles)) {
+    if (++stage == A.nstage) {
+      stage = 0;
+      parity ^= 1u;
+    }
+    if (++ring == 2u * A.nstage) ring = 0;
+    if (VB_OUT == 0 && A.stg_cap && (++since_flush == A.stg_every || it + 1 == my_tiles)) {
+      since_flush = 0;
       __syncthreads();
       for (u32 bb = (u32)warp * 4; bb < A.nb; bb += BW_SC_WARPS * 4) {  // uniform trip count per warp: four buckets at a time
         const u32 b = bb + ((u32)lane >> 3);
@@ -413,7 +421,7 @@ __global__ void __launch_bounds__(BW_SC_THREADS, 1) k_scatter(ScatterArgs A, Fol
           for (u32 r = (u32)lane & 7u; r < nrec && fb + r < A.lane_cap; r += 8) {
             uint4 v;
             asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(stg + 16 * (b * A.stg_cap + r)) : "memory");
-            A.out.rec[((size_t)b * A.nlanes + blockIdx.x) * A.lane_cap + fb + r] = v;
+            A.out.rec[(size_t)(b * bucket_stride + my_lane_off + fb + r)] = v;
           }
         }
         __syncwarp();
