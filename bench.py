@@ -175,7 +175,7 @@ def share_nccl_id(dist, rank, local):
     return bytes(buf.cpu().numpy().tobytes())
 
 
-def check_counts(em, em_eof, K, B, world, dist, local, ts_stride):
+def check_counts(em, em_eof, K, B, world, dist, local, ts_stride, late_frac=0.0):
     """Size-independent checks of a whole job, over ALL ranks: the counts add up to the rows ingested,
     and -- ts_i = i us -- every full 60 s window of the global stream holds exactly 6e7 / ts_stride events."""
     import numpy as np
@@ -192,6 +192,17 @@ def check_counts(em, em_eof, K, B, world, dist, local, ts_stride):
         per_window = t.cpu().numpy()
     total = int(per_window.sum())
     nfull = (K * B * world * ts_stride) // WINDOW_US
+    if late_frac > 0:  # diagnostic stream with late rows: every row is either counted or in the late stream (one window each)
+        n_late = len(em.late_key) + len(em_eof.late_key)
+        if dist is not None:
+            import torch
+
+            t = torch.tensor([n_late], dtype=torch.int64, device=f"cuda:{local}")
+            dist.all_reduce(t)
+            n_late = int(t.item())
+        if total + n_late != K * B * world:
+            raise SystemExit(f"bench: WRONG RESULT: counted {total} + late {n_late} != {K * B * world}")
+        return total, f"late rows {n_late}"
     ok = bool(total == K * B * world and (per_window[:nfull] == WINDOW_US // ts_stride).all())
     if not ok:
         raise SystemExit(f"bench: WRONG RESULT: sum of counts {total} != {K * B * world} or a full window is not {WINDOW_US // ts_stride}")
@@ -199,7 +210,7 @@ def check_counts(em, em_eof, K, B, world, dist, local, ts_stride):
 
 
 def run_gpu(args):
-    if args.ts_stride != 1:
+    if args.ts_stride != 1 or args.late_frac > 0:
         import torch  # noqa: F401  (diagnostic mode only; torch must load its own NCCL before libbwgpu loads the system one)
     from bytewax_b200 import _native as N, gpu
 
@@ -213,7 +224,8 @@ def run_gpu(args):
         return gpu.WindowFold(
             ctx, "count", WINDOW_US, None, ALIGN_US, 0, val_dtype="u64", ts_from_value=True,
             emit_order=emit_order, capacity_hint=N_KEYS if world == 1 else (N_KEYS * 3) // (2 * world) + 1024,
-            max_batch_rows=B, max_emit_rows=max(1 << 20, (K + W + 2) * B // 40), max_late_rows=1 << 16,
+            max_batch_rows=B, max_emit_rows=max(1 << 20, (K + W + 2) * B // 40),
+            max_late_rows=(1 << 16) if args.late_frac <= 0 else int((K + W + 2) * B * args.late_frac * 1.5) + (1 << 16),
             ring_slots=ring_slots, exchange=N.XCHG_NCCL if args.exchange == "nccl" else N.XCHG_P2P)
 
     # ---- device-resident inputs: step s of this rank = global rows [(s*world+rank)*B, +B) ----
@@ -236,6 +248,20 @@ def run_gpu(args):
             torch.cuda.synchronize(local)
             ctx.lib.bw_memcpy(ctx.h, C.c_void_p(dv[s]), C.c_void_p(scratch.data_ptr()), B * 8, 2)
         del scratch
+    if args.late_frac > 0:
+        # diagnostic: every 1/late_frac-th row is sent 120 s into the past (two windows late): its activation cannot be
+        # proven clean and takes the exact path
+        import torch
+
+        period = max(2, int(round(1.0 / args.late_frac)))
+        scratch = torch.empty(B, dtype=torch.int64, device=f"cuda:{local}")
+        mask = (torch.arange(B, device=f"cuda:{local}") % period) == (period // 2)
+        for s in range(nbuf):
+            ctx.lib.bw_memcpy(ctx.h, C.c_void_p(scratch.data_ptr()), C.c_void_p(dv[s]), B * 8, 2)
+            scratch[mask] = torch.clamp(scratch[mask] - 120_000_000, min=0)
+            torch.cuda.synchronize(local)
+            ctx.lib.bw_memcpy(ctx.h, C.c_void_p(dv[s]), C.c_void_p(scratch.data_ptr()), B * 8, 2)
+        del scratch, mask
     # warm-up: W untimed steps on a scratch fold (same shapes)
     for s in range(W):
         fold.ingest_device(dk[K + s], dv[K + s], None, B)
@@ -268,7 +294,7 @@ def run_gpu(args):
             # correctness of what was timed (first and last repetition): every row counted once, in the right window
             em = fold.advance()
             em_eof = fold.eof()
-            checks = check_counts(em, em_eof, K, B, world, dist, local, args.ts_stride)
+            checks = check_counts(em, em_eof, K, B, world, dist, local, args.ts_stride, args.late_frac)
         fold.close()
         if not more:
             break
@@ -498,6 +524,7 @@ def main():
     ap.add_argument("--ts-stride", type=int, default=1, help="diagnostic: event time advances this many us per row")
     ap.add_argument("--min-timed-s", type=float, default=1.0, help="repeat the K-step job until this much timed device work")
     ap.add_argument("--max-repeats", type=int, default=200)
+    ap.add_argument("--late-frac", type=float, default=0.0, help="diagnostic: this fraction of the rows arrives 120 s late (exact path)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -446,11 +446,21 @@ k_verdict(const i64* tile_min, const i64* tile_max, const u32* tile_bad, u32 nti
   __shared__ i64 s_mn[32], s_mx[32];
   __shared__ u32 s_bad[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const u32 per = (ntiles + blockDim.x - 1) / blockDim.x;
-  const u32 lo = threadIdx.x * per, hi = (lo + per < ntiles) ? lo + per : ntiles;
+  // warp w takes a contiguous run of tiles, 32 at a time with coalesced loads: ordered concatenation inside the 32
+  // (lane order == arrival order), then across the run
+  const u32 nwarps = blockDim.x >> 5;
+  const u32 per = ((ntiles + nwarps - 1) / nwarps + 31) & ~31u;
+  const u32 lo = (u32)warp * per, hi = (lo + per < ntiles) ? lo + per : ntiles;
   Trip tt = bw_trip_id();
-  for (u32 r = lo; r < hi; ++r) tt = bw_trip_cat(tt, Trip{tile_min[r], tile_max[r], tile_bad[r]}, p.wait_us);
-  tt = bw_trip_warp(tt, p.wait_us);  // ordered concatenation: lane 31 holds the warp's
+  for (u32 base = lo; base < hi; base += 32) {
+    const u32 r = base + (u32)lane;
+    Trip x = (r < hi) ? Trip{tile_min[r], tile_max[r], tile_bad[r]} : bw_trip_id();
+    x = bw_trip_warp(x, p.wait_us);
+    x.mn = __shfl_sync(0xffffffffu, x.mn, 31);
+    x.mx = __shfl_sync(0xffffffffu, x.mx, 31);
+    x.bad = __shfl_sync(0xffffffffu, x.bad, 31);
+    tt = bw_trip_cat(tt, x, p.wait_us);
+  }
   if (lane == 31) {
     s_mn[warp] = tt.mn;
     s_mx[warp] = tt.mx;
