@@ -99,6 +99,9 @@ SYMBOLS = {
     "bw_nccl_unique_id": (C.c_int32, [_P]),
     "bw_ctx_create": (C.c_int32, [C.c_int, C.c_int, C.c_int, _P, C.POINTER(_P)]),
     "bw_ctx_destroy": (None, [_P]),
+    "bw_loopback_create": (C.c_int32, [C.c_int, C.POINTER(_P)]),
+    "bw_loopback_destroy": (None, [_P]),
+    "bw_ctx_create_loopback": (C.c_int32, [C.c_int, C.c_int, _P, C.POINTER(_P)]),
     "bw_fold_create": (C.c_int32, [_P, C.POINTER(BwFoldSpec), C.POINTER(_P)]),
     "bw_fold_destroy": (None, [_P]),
     "bw_ingest_acquire": (C.c_int32, [_P, C.c_uint64, C.POINTER(BwBatch)]),

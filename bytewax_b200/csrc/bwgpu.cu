@@ -16,6 +16,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -35,9 +37,42 @@
 
 static thread_local std::string g_last_error;
 
+// A "world" whose ranks are threads of ONE process on ONE GPU (bw_loopback_create): the collectives become host
+// rendezvous + device-to-device copies and peer memory is plain pointers.  Every multi-rank code path -- routing
+// hash, partition, exchange, combine / merge -- then runs on a single-GPU box (tests/test_gpu_loopback.py); the
+// kernels and their arguments are the very same as over NCCL + CUDA IPC.
+struct bw_loopback {
+  int world = 0;
+  std::mutex mu;
+  std::condition_variable cv;
+  int arrived = 0;
+  unsigned long long generation = 0;
+  const void* slot[BW_MAX_WORLD] = {nullptr};  // what each rank published for the collective in flight
+  bool broken = false;
+  // false when a peer thread never arrives (it failed and left): the world is then unusable, and says so
+  bool barrier() {
+    std::unique_lock<std::mutex> lk(mu);
+    if (broken) return false;
+    const unsigned long long g = generation;
+    if (++arrived == world) {
+      arrived = 0;
+      ++generation;
+      cv.notify_all();
+      return true;
+    }
+    if (!cv.wait_for(lk, std::chrono::seconds(120), [&] { return generation != g || broken; }) || broken) {
+      broken = true;
+      cv.notify_all();
+      return false;
+    }
+    return true;
+  }
+};
+
 struct bw_ctx {
   int device = 0, rank = 0, world = 1, sm_count = BW_SM_COUNT_FALLBACK;
   ncclComm_t comm = nullptr;
+  bw_loopback* loop = nullptr;
   std::string err;
   void* flush_buf = nullptr;
   size_t flush_bytes = 0;
@@ -66,6 +101,65 @@ struct bw_ctx {
       CTX_FAIL(ctx, BW_ERR_NCCL, "%s failed: %s (%s:%d)", #call, ncclGetErrorString(_e), __FILE__,  \
                __LINE__);                                                                           \
   } while (0)
+
+// ---- collectives: NCCL, or the loopback world's rendezvous ----
+// all-gather of `bytes` per rank, device buffers, in stream order on `s`
+static bw_status coll_allgather(bw_ctx* ctx, const void* send, void* recv, size_t bytes, cudaStream_t s) {
+  if (!ctx->loop) {
+    NC(ctx, ncclAllGather(send, recv, bytes, ncclChar, ctx->comm, s));
+    return BW_OK;
+  }
+  bw_loopback* L = ctx->loop;
+  CU(ctx, cudaStreamSynchronize(s));  // my contribution is complete
+  L->slot[ctx->rank] = send;
+  if (!L->barrier()) CTX_FAIL(ctx, BW_ERR_NCCL, "loopback world: a rank did not reach the all-gather");
+  for (int r = 0; r < ctx->world; ++r)
+    CU(ctx, cudaMemcpyAsync((char*)recv + (size_t)r * bytes, L->slot[r], bytes, cudaMemcpyDeviceToDevice, s));
+  CU(ctx, cudaStreamSynchronize(s));
+  // everyone has read everyone's buffer: it may be reused
+  if (!L->barrier()) CTX_FAIL(ctx, BW_ERR_NCCL, "loopback world: a rank did not leave the all-gather");
+  return BW_OK;
+}
+// barrier in stream order: completes on `s` once every rank's earlier work on its stream is done
+static bw_status coll_barrier(bw_ctx* ctx, u32* d_word, cudaStream_t s) {
+  if (!ctx->loop) {
+    NC(ctx, ncclAllReduce(d_word, d_word, 1, ncclUint32, ncclMax, ctx->comm, s));
+    return BW_OK;
+  }
+  CU(ctx, cudaStreamSynchronize(s));
+  if (!ctx->loop->barrier()) CTX_FAIL(ctx, BW_ERR_NCCL, "loopback world: a rank did not reach the barrier");
+  return BW_OK;
+}
+// every rank's `base` pointer as seen from this rank (CUDA IPC mappings, or the pointers themselves)
+static bw_status coll_share_base(bw_ctx* ctx, void* base, void** peers, cudaStream_t s) {
+  const int W = ctx->world;
+  if (ctx->loop) {
+    bw_loopback* L = ctx->loop;
+    L->slot[ctx->rank] = base;
+    if (!L->barrier()) CTX_FAIL(ctx, BW_ERR_NCCL, "loopback world: a rank did not publish its buffer");
+    for (int r = 0; r < W; ++r) peers[r] = const_cast<void*>(L->slot[r]);
+    if (!L->barrier()) CTX_FAIL(ctx, BW_ERR_NCCL, "loopback world: a rank did not read the buffers");
+    return BW_OK;
+  }
+  cudaIpcMemHandle_t mine;
+  CU(ctx, cudaIpcGetMemHandle(&mine, base));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+  unsigned char *d_in = nullptr, *d_all = nullptr;
+  CU(ctx, cudaMalloc(&d_in, 64));
+  CU(ctx, cudaMalloc(&d_all, 64 * W));
+  CU(ctx, cudaMemcpy(d_in, &mine, 64, cudaMemcpyHostToDevice));
+  NC(ctx, ncclAllGather(d_in, d_all, 64, ncclChar, ctx->comm, s));
+  CU(ctx, cudaStreamSynchronize(s));
+  std::vector<cudaIpcMemHandle_t> all(W);
+  CU(ctx, cudaMemcpy(all.data(), d_all, 64 * W, cudaMemcpyDeviceToHost));
+  cudaFree(d_in);
+  cudaFree(d_all);
+  for (int r = 0; r < W; ++r) {
+    if (r == ctx->rank) peers[r] = base;
+    else CU(ctx, cudaIpcOpenMemHandle(&peers[r], all[r], cudaIpcMemLazyEnablePeerAccess));
+  }
+  return BW_OK;
+}
 
 struct Slot {
   u64* h_keys = nullptr;
@@ -356,6 +450,29 @@ bw_status bw_ctx_create(int device, int rank, int world, const void* nccl_unique
   return BW_OK;
 }
 
+bw_status bw_loopback_create(int world, bw_loopback** out) {
+  bw_ctx* null_ctx = nullptr;
+  if (!out || world < 2 || world > BW_MAX_WORLD) CTX_FAIL(null_ctx, BW_ERR_SPEC, "bw_loopback_create: world must be in 2..%d", BW_MAX_WORLD);
+  bw_loopback* L = new bw_loopback();
+  L->world = world;
+  *out = L;
+  return BW_OK;
+}
+void bw_loopback_destroy(bw_loopback* world) { delete world; }
+
+bw_status bw_ctx_create_loopback(int device, int rank, bw_loopback* world, bw_ctx** out) {
+  bw_ctx* null_ctx = nullptr;
+  if (!out || !world || rank < 0 || rank >= world->world) CTX_FAIL(null_ctx, BW_ERR_SPEC, "bw_ctx_create_loopback: bad arguments");
+  bw_ctx* c = nullptr;
+  bw_status st = bw_ctx_create(device, 0, 1, nullptr, &c);  // device checks; no communicator
+  if (st != BW_OK) return st;
+  c->rank = rank;
+  c->world = world->world;
+  c->loop = world;
+  *out = c;
+  return BW_OK;
+}
+
 void bw_ctx_destroy(bw_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
@@ -566,22 +683,8 @@ static bw_status stream_alloc(bw_fold* f) {
     CU(ctx, cudaMalloc(&f->precv_base, off));
     CU(ctx, cudaMemset(f->precv_base, 0, off));
     {
-      cudaIpcMemHandle_t mine;
-      CU(ctx, cudaIpcGetMemHandle(&mine, f->precv_base));
-      unsigned char *d_in = nullptr, *d_all = nullptr;
-      CU(ctx, cudaMalloc(&d_in, 64));
-      CU(ctx, cudaMalloc(&d_all, 64 * W));
-      CU(ctx, cudaMemcpy(d_in, &mine, 64, cudaMemcpyHostToDevice));
-      NC(ctx, ncclAllGather(d_in, d_all, 64, ncclChar, ctx->comm, f->s_compute));
-      CU(ctx, cudaStreamSynchronize(f->s_compute));
-      std::vector<cudaIpcMemHandle_t> all(W);
-      CU(ctx, cudaMemcpy(all.data(), d_all, 64 * W, cudaMemcpyDeviceToHost));
-      cudaFree(d_in);
-      cudaFree(d_all);
-      for (int r = 0; r < W; ++r) {
-        if (r == ctx->rank) f->precv_peer[r] = f->precv_base;
-        else CU(ctx, cudaIpcOpenMemHandle(&f->precv_peer[r], all[r], cudaIpcMemLazyEnablePeerAccess));
-      }
+      bw_status cst = coll_share_base(ctx, f->precv_base, f->precv_peer, f->s_compute);
+      if (cst != BW_OK) return cst;
     }
     CU(ctx, dmalloc(&f->d_vg_local, 2));
     CU(ctx, dmalloc(&f->d_vg_all, 2 * (size_t)W));
@@ -746,27 +849,9 @@ static bw_status xchg_setup(bw_fold* f) {
   u64 ntiles = (f->spec.max_batch_rows + BW_PART_TILE - 1) / BW_PART_TILE + 1;
   CU(ctx, dmalloc(&f->d_tile_counts, ntiles * BW_MAX_WORLD));
   if (f->spec.exchange == BW_XCHG_P2P) {
-    // all-gather the IPC handles through NCCL (device buffers), then map every peer
-    cudaIpcMemHandle_t mine;
-    CU(ctx, cudaIpcGetMemHandle(&mine, f->xchg_base));
-    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
-    unsigned char *d_in = nullptr, *d_all = nullptr;
-    CU(ctx, cudaMalloc(&d_in, 64));
-    CU(ctx, cudaMalloc(&d_all, 64 * W));
-    CU(ctx, cudaMemcpy(d_in, &mine, 64, cudaMemcpyHostToDevice));
-    NC(ctx, ncclAllGather(d_in, d_all, 64, ncclChar, ctx->comm, f->s_compute));
-    CU(ctx, cudaStreamSynchronize(f->s_compute));
-    std::vector<cudaIpcMemHandle_t> all(W);
-    CU(ctx, cudaMemcpy(all.data(), d_all, 64 * W, cudaMemcpyDeviceToHost));
-    cudaFree(d_in);
-    cudaFree(d_all);
-    for (int r = 0; r < W; ++r) {
-      if (r == ctx->rank) {
-        f->peer_base[r] = f->xchg_base;
-      } else {
-        CU(ctx, cudaIpcOpenMemHandle(&f->peer_base[r], all[r], cudaIpcMemLazyEnablePeerAccess));
-      }
-    }
+    // every peer's receive buffer as seen from here (CUDA IPC mappings exchanged through NCCL)
+    bw_status cst = coll_share_base(ctx, f->xchg_base, f->peer_base, f->s_compute);
+    if (cst != BW_OK) return cst;
   } else {
     const size_t rows = (size_t)f->region_cap * W;
     CU(ctx, dmalloc(&f->send_keys, rows));
@@ -790,6 +875,7 @@ bw_status bw_fold_create(bw_ctx* ctx, const bw_fold_spec* spec, bw_fold** out) {
   if (spec->length_us <= 0 || spec->offset_us <= 0 || spec->offset_us > spec->length_us)
     CTX_FAIL(ctx, BW_ERR_SPEC, "need 0 < offset_us <= length_us (windowing.py:880-883)");
   if (spec->wait_us < 0) CTX_FAIL(ctx, BW_ERR_SPEC, "wait_us must be >= 0");
+  if (ctx->loop && spec->exchange != BW_XCHG_P2P) CTX_FAIL(ctx, BW_ERR_SPEC, "a loopback world exchanges over peer memory only (BW_XCHG_P2P)");
   if (spec->ts_source < BW_TS_COLUMN || spec->ts_source > BW_TS_NONE) CTX_FAIL(ctx, BW_ERR_SPEC, "bad ts_source %d", spec->ts_source);
   if (spec->ts_source == BW_TS_FROM_VALUE && spec->val_dtype > BW_VAL_I64)
     CTX_FAIL(ctx, BW_ERR_SPEC, "BW_TS_FROM_VALUE needs an integer val_dtype");
@@ -886,7 +972,10 @@ void bw_fold_destroy(bw_fold* f) {
   cudaDeviceSynchronize();
   f->pt.report(f->ctx->rank);
   for (int r = 0; r < f->ctx->world; ++r)
-    if (f->peer_base[r] && r != f->ctx->rank && f->spec.exchange == BW_XCHG_P2P) cudaIpcCloseMemHandle(f->peer_base[r]);
+    if (r != f->ctx->rank && !f->ctx->loop) {
+      if (f->peer_base[r] && f->spec.exchange == BW_XCHG_P2P) cudaIpcCloseMemHandle(f->peer_base[r]);
+      if (f->precv_peer[r]) cudaIpcCloseMemHandle(f->precv_peer[r]);
+    }
   void* dev[] = {f->t.hot, f->t.p1, f->t.closed_upto, f->t.aux, f->t.nodes, f->t.node_acc2, f->t.free_stack, f->t.dirty, f->d_ctr, f->e.c_key,
                  f->e.c_wid, f->e.c_acc, f->e.c_count, f->e.c_seq, f->e.c_epoch, f->e.l_key, f->e.l_wid, f->e.l_val,
                  f->e.l_ts, f->e.l_seq, f->e.l_epoch, f->d_rmin, f->d_rmax, f->d_rbad, f->d_verdict, f->d_kflat,
@@ -1042,7 +1131,10 @@ static bw_status exchange(bw_fold* f, const u64* d_keys, const void* d_vals, con
   if (p2p) {
     // every rank's stores are complete once it enters this collective (stream
     // order); its completion here means all peers have entered it.
-    NC(ctx, ncclAllReduce(f->d_verdict, f->d_verdict, 1, ncclUint32, ncclMax, ctx->comm, s));
+    {
+      bw_status cst = coll_barrier(ctx, f->d_verdict, s);
+      if (cst != BW_OK) return cst;
+    }
   } else {
     NC(ctx, ncclAllGather(f->d_send_counts, f->d_all_counts, BW_MAX_WORLD, ncclUint64, ctx->comm, s));
     CU(ctx, cudaMemcpyAsync(f->h_all_counts, f->d_all_counts, sizeof(u64) * BW_MAX_WORLD * W, cudaMemcpyDeviceToHost, s));
@@ -1310,7 +1402,10 @@ static bw_status gather_verdict(bw_fold* f, int side) {
   cudaStream_t s = f->s_compute;
   const int W = ctx->world;
   VerdictGather* all = f->d_vg_all + (size_t)side * W;
-  NC(ctx, ncclAllGather(f->d_vg_local + side, all, sizeof(VerdictGather), ncclChar, ctx->comm, s));
+  {
+    bw_status cst = coll_allgather(ctx, f->d_vg_local + side, all, sizeof(VerdictGather), s);
+    if (cst != BW_OK) return cst;
+  }
   CU(ctx, cudaMemcpyAsync(f->h_vg + (size_t)side * W, all, sizeof(VerdictGather) * W, cudaMemcpyDeviceToHost, s));
   if (!f->ev_vg[side]) CU(ctx, cudaEventCreateWithFlags(&f->ev_vg[side], cudaEventDisableTiming));
   CU(ctx, cudaEventRecord(f->ev_vg[side], s));
@@ -1416,7 +1511,8 @@ static bw_status stream_resolve_multi(bw_fold* f, const Deferred& d) {
     bw_status gst = gather_verdict(f, next_side);
     if (gst != BW_OK) return gst;
   } else {
-    NC(ctx, ncclAllReduce(f->d_barrier_word, f->d_barrier_word, 1, ncclUint32, ncclMax, ctx->comm, s));
+    bw_status cst = coll_barrier(ctx, f->d_barrier_word, s);
+    if (cst != BW_OK) return cst;
   }
   f->pt.mark(1, 1, s);
   // merge what every source left for this rank's segments, in source order, over the activation's whole span

@@ -33,6 +33,25 @@ class Context:
         N.check(self.lib.bw_ctx_create(device, rank, world, idbuf, C.byref(h)))
         self.h = h
 
+    @classmethod
+    def loopback_world(cls, world: int, device: int = 0) -> "list[Context]":
+        """``world`` ranks on ONE device, to be driven by one thread each (``bw_loopback_create``): the multi-rank
+        path without a second GPU.  The contexts share the world object; closing the last one frees it."""
+        lib = N.load()
+        w = C.c_void_p()
+        N.check(lib.bw_loopback_create(world, C.byref(w)))
+        shared = {"handle": w, "open": world}
+        out = []
+        for r in range(world):
+            c = cls.__new__(cls)
+            c.lib, c.rank, c.world, c.device = lib, r, world, device
+            h = C.c_void_p()
+            N.check(lib.bw_ctx_create_loopback(device, r, w, C.byref(h)))
+            c.h = h
+            c._loop = shared
+            out.append(c)
+        return out
+
     @staticmethod
     def new_nccl_id() -> bytes:
         lib = N.load()
@@ -44,6 +63,11 @@ class Context:
         if self.h:
             self.lib.bw_ctx_destroy(self.h)
             self.h = None
+            loop = getattr(self, "_loop", None)
+            if loop is not None:
+                loop["open"] -= 1
+                if loop["open"] == 0:
+                    self.lib.bw_loopback_destroy(loop["handle"])
 
     # plain device memory (tests / bench)
     def dev_alloc(self, nbytes: int) -> int:

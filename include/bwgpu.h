@@ -193,6 +193,14 @@ bw_status bw_nccl_unique_id(void* out128);
 /* `nccl_unique_id` may be NULL iff world == 1. */
 bw_status bw_ctx_create(int device, int rank, int world, const void* nccl_unique_id, bw_ctx** out);
 void bw_ctx_destroy(bw_ctx* ctx);
+/* Test harness for boxes with one GPU: a world whose ranks are THREADS of one process on one device.  The collectives
+ * become host rendezvous, peer memory plain pointers; kernels, arguments and results are those of the NCCL / CUDA-IPC
+ * world, so the whole multi-rank path (bw_route, partition, exchange, combine / merge -- src/timely.rs:455-569, 809-815)
+ * can be checked without a second GPU.  Only the P2P exchange; every rank thread makes the same sequence of calls. */
+typedef struct bw_loopback bw_loopback;
+bw_status bw_loopback_create(int world, bw_loopback** out);
+void bw_loopback_destroy(bw_loopback* world);
+bw_status bw_ctx_create_loopback(int device, int rank, bw_loopback* world, bw_ctx** out);
 const char* bw_last_error(const bw_ctx* ctx);
 /* Message of the last failure that had no ctx (bw_ctx_create itself). */
 const char* bw_last_global_error(void);
