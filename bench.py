@@ -370,6 +370,10 @@ def run_gpu(args):
                           "note": "the design moves ~52 B/event: 16 in + 16 B record out (scatter), 16 B record in + table slice (fold)"},
             },
         }
+        if args.late_frac > 0:  # diagnostic line: how the not-clean activations were handled in the last repetition
+            out["config"]["late_frac"] = args.late_frac
+            out["config"]["late_path"] = {"split_batches": int(st1.split_batches - st0.split_batches),
+                                          "sort_batches": int(st1.slow_batches - st0.slow_batches), "steps": K}
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(sample_rows=1 << 22)
     ctx.close()

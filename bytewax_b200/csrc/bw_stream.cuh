@@ -57,6 +57,7 @@ struct StreamVerdict {
   i64 ts0;     // base of the records' 32-bit relative timestamps (event time of row 0)
   u32 n_spill; // rows in this activation's spill list
   u32 pad;
+  i64 gprev;   // running maximum over everything ingested before this activation
 };
 // what every rank tells the others about its slice of an activation (multi-GPU verdict: the slices are chained in
 // source-rank order, the arrival order at every destination)
@@ -82,8 +83,9 @@ struct StreamBufs {
   StreamSide side[2];
   u32 nb, nlanes, lane_cap, spill_cap;  // every scatter block owns one lane of lane_cap rows in every bucket's region
   int val_bytes;       // value bytes stored beside the records: 0 (counts), 4 or 8
-  i64 *tile_min, *tile_max;
+  i64 *tile_min, *tile_max;  // [2 sides][tiles_cap]
   u32* tile_bad;
+  i64* chunk_max;            // [2 sides][tiles_cap][32]
   u32 tiles_cap;
 };
 
@@ -155,6 +157,7 @@ struct ScatterArgs {
   u32 nb, nlanes, lane_cap, spill_cap;
   i64 *tile_min, *tile_max;
   u32* tile_bad;
+  i64* chunk_max;    // [tiles][32]: maximum of every warp's 64 rows (read again only when the activation has late rows: bw_late.cuh)
   u64 cap;           // table capacity (slots)
   u32 seg_shift;
   u32 batch_no;
@@ -164,6 +167,10 @@ struct ScatterArgs {
   u32 world, nb_local;  // multi-GPU: bucket = owning rank * nb_local + segment of the key in the owner's table
   u32 stg_cap;       // records per bucket assembled in shared memory before they are written out (0: every record straight out)
   u32 stg_every;     // ... every this many tiles
+  // second run over an activation that has late rows (bw_late.cuh): rows whose bit is set are left out
+  const u32* late_bits;
+  u32 ts0_set;       // take ts0 from here instead of row 0 (which may be one of the late rows, far in the past)
+  i64 ts0;
 };
 
 __device__ __forceinline__ void bw_spill_push(SpillRec* list, u32* n, u32 cap, u32* flags, u32 lost_flag, Counters* ctr, u64 key,
@@ -229,6 +236,7 @@ __global__ void __launch_bounds__(BW_SC_THREADS, 1) k_scatter(ScatterArgs A, Fol
   i64 ts0 = p.align_us;
   if (TSM == 0) ts0 = A.ts[0];
   else if (TSM == 1) ts0 = p.align_us + (i64)((const u64*)A.vals)[0];
+  if (A.ts0_set) ts0 = A.ts0;
   u32* flags = &A.out.sv->flags;
   u32* n_spill = &A.out.sv->n_spill;
   const u32 seg_mask = (1u << A.seg_shift) - 1u;
@@ -274,7 +282,8 @@ __global__ void __launch_bounds__(BW_SC_THREADS, 1) k_scatter(ScatterArgs A, Fol
     const u32 tr = rows & ~3u;
     bw_mbar_wait(bars + 8 * stage, parity);
     const u32 r0 = 2u * threadIdx.x;  // this thread's two rows of the tile
-    const bool va = r0 < rows, vb = r0 + 1 < rows;
+    bool va = r0 < rows, vb = r0 + 1 < rows;
+    const bool ina = va, inb = vb;
     u64 ka = 0, kb = 0, xa = 0, xb = 0;
     i64 ta = p.align_us, tb = p.align_us;
     if (r0 + 1 < tr) {
@@ -292,21 +301,26 @@ __global__ void __launch_bounds__(BW_SC_THREADS, 1) k_scatter(ScatterArgs A, Fol
         ta = (i64)a;
         tb = (i64)b;
       }
-    } else if (va) {  // the last (< 4) rows of the input
+    } else if (ina) {  // the last (< 4) rows of the input
       ka = A.keys[tbase + r0];
-      if (vb) kb = A.keys[tbase + r0 + 1];
+      if (inb) kb = A.keys[tbase + r0 + 1];
       if (VB_IN == 8) {
         xa = ((const u64*)A.vals)[tbase + r0];
-        if (vb) xb = ((const u64*)A.vals)[tbase + r0 + 1];
+        if (inb) xb = ((const u64*)A.vals)[tbase + r0 + 1];
       }
       if (VB_IN == 4) {
         xa = ((const u32*)A.vals)[tbase + r0];
-        if (vb) xb = ((const u32*)A.vals)[tbase + r0 + 1];
+        if (inb) xb = ((const u32*)A.vals)[tbase + r0 + 1];
       }
       if (TSM == 0) {
         ta = A.ts[tbase + r0];
-        if (vb) tb = A.ts[tbase + r0 + 1];
+        if (inb) tb = A.ts[tbase + r0 + 1];
       }
+    }
+    if (A.late_bits && ina) {  // (tbase is a multiple of 32 and r0 is even: both bits are in one word)
+      const u32 w = A.late_bits[(tbase + r0) >> 5] >> (r0 & 31u);
+      va = !(w & 1u);
+      vb = inb && !(w & 2u);
     }
     if (TSM == 1) {
       ta = p.align_us + (i64)xa;
@@ -350,8 +364,9 @@ __global__ void __launch_bounds__(BW_SC_THREADS, 1) k_scatter(ScatterArgs A, Fol
       }
       last = __shfl_sync(0xffffffffu, last, 0);
       if (last) {
-        Trip tt = bw_trip_warp(Trip{((volatile i64*)c_min[ring])[lane], ((volatile i64*)c_max[ring])[lane], ((volatile u32*)c_bad[ring])[lane]},
-                               p.wait_us);
+        const i64 cmx = ((volatile i64*)c_max[ring])[lane];
+        A.chunk_max[tile * BW_SC_WARPS + (u64)lane] = cmx;  // (one 256-byte line per tile)
+        Trip tt = bw_trip_warp(Trip{((volatile i64*)c_min[ring])[lane], cmx, ((volatile u32*)c_bad[ring])[lane]}, p.wait_us);
         if (lane == 31) {
           A.tile_min[tile] = tt.mn;
           A.tile_max[tile] = tt.mx;
@@ -483,6 +498,7 @@ k_verdict(const i64* tile_min, const i64* tile_max, const u32* tile_bad, u32 nti
         sv->clean = 0u;
       } else {
         const i64 gprev = (i64)ctr->gmax_ts;
+        sv->gprev = gprev;
         // everything ingested before this activation: only its maximum matters
         const Trip all = bw_trip_cat(Trip{INT64_MAX, gprev, 0u}, act, p.wait_us);
         ctr->gmax_ts = (unsigned long long)all.mx;

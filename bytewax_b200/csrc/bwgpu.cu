@@ -34,6 +34,7 @@
 #include "bw_keyed.cuh"
 #include "bw_prepass.cuh"
 #include "bw_slow.cuh"
+#include "bw_late.cuh"
 
 static thread_local std::string g_last_error;
 
@@ -312,6 +313,12 @@ struct bw_fold {
   u32* d_barrier_word = nullptr;
   cudaEvent_t ev_sv[2] = {nullptr, nullptr};
   StreamVerdict* h_sv = nullptr;  // pinned mirror of the two sides' verdicts
+  // activations with a few late rows (bw_late.cuh); buffers are made on first use
+  LateBufs late = {};
+  bool late_ready = false;
+  bool late_split = true;   // env BW_LATE_SPLIT=0: every not-clean activation takes the sort path
+  u32* h_late_ctr = nullptr;  // pinned: suspects seen, table overflow
+  i64* late_chunk_pre = nullptr;  // [tiles][32] running maximum before every 64-row chunk
   Deferred dq{};            // the activation whose fold has not been launched yet
   i64* d_span = nullptr;   // [min ts, max ts] of the activation (prepass)
   // snapshot staging (bw_snapshot_take)
@@ -628,9 +635,13 @@ static bw_status stream_alloc(bw_fold* f) {
   const int vb_in = (tsm == 1) ? 8 : (sb.val_bytes ? f->val_bytes : 0);
   f->scatter_kernel = pick_scatter_kernel(tsm, vb_in, sb.val_bytes);
   sb.tiles_cap = (u32)((rows + BW_SC_TILE - 1) / BW_SC_TILE + 1);  // one lateness triple per scatter tile
-  CU(ctx, dmalloc(&sb.tile_min, sb.tiles_cap));
-  CU(ctx, dmalloc(&sb.tile_max, sb.tiles_cap));
-  CU(ctx, dmalloc(&sb.tile_bad, sb.tiles_cap));
+  // (one set per side: the tile triples of activation b are read again when it turns out to have late rows, after the
+  // scatter of b + 1 has run)
+  CU(ctx, dmalloc(&sb.tile_min, 2 * (size_t)sb.tiles_cap));
+  CU(ctx, dmalloc(&sb.tile_max, 2 * (size_t)sb.tiles_cap));
+  CU(ctx, dmalloc(&sb.tile_bad, 2 * (size_t)sb.tiles_cap));
+  CU(ctx, dmalloc(&sb.chunk_max, 2 * (size_t)sb.tiles_cap * BW_SC_WARPS));
+  if (const char* e = getenv("BW_LATE_SPLIT")) f->late_split = atoi(e) != 0;
   // Shared memory of the scatter: up to 8 records per bucket assembled before they are written out (counts only: the
   // value column is not staged), then as many TMA stages of the input tile (2..4) as still fit.
   const size_t smem_budget = 208 * 1024;
@@ -991,10 +1002,14 @@ void bw_fold_destroy(bw_fold* f) {
     if (f->ev_sv[i]) cudaEventDestroy(f->ev_sv[i]);
   }
   {
-    void* sp[] = {f->sb.tile_min, f->sb.tile_max, f->sb.tile_bad};
+    void* sp[] = {f->sb.tile_min, f->sb.tile_max, f->sb.tile_bad, f->sb.chunk_max};
     for (void* q : sp)
       if (q) cudaFree(q);
     if (f->h_sv) cudaFreeHost(f->h_sv);
+    void* lp[] = {f->late.key_bits, f->late.late_bits, f->late.ent, f->late.counters, f->late.gpre, f->late_chunk_pre, f->late.s_key, f->late.s_ts, f->late.s_idx, f->late.s_slot};
+    for (void* q : lp)
+      if (q) cudaFree(q);
+    if (f->h_late_ctr) cudaFreeHost(f->h_late_ctr);
   }
   for (auto& s : f->stages) {
     if (s.d_keys) cudaFree(s.d_keys);
@@ -1251,7 +1266,8 @@ static bool stream_usable(const bw_fold* f, const u64* d_keys, const void* d_val
   return true;
 }
 
-static bw_status stream_front(bw_fold* f, const u64* d_keys, const void* d_vals, const i64* d_ts, u64 rows, u32 batch_no, int side) {
+static bw_status stream_front(bw_fold* f, const u64* d_keys, const void* d_vals, const i64* d_ts, u64 rows, u32 batch_no, int side,
+                              const u32* late_bits = nullptr, i64 ts0 = 0) {
   bw_ctx* ctx = f->ctx;
   const StreamBufs& sb = f->sb;
   cudaStream_t s = f->s_compute;
@@ -1266,9 +1282,13 @@ static bw_status stream_front(bw_fold* f, const u64* d_keys, const void* d_vals,
   A.nlanes = sb.nlanes;
   A.lane_cap = sb.lane_cap;
   A.spill_cap = sb.spill_cap;
-  A.tile_min = sb.tile_min;
-  A.tile_max = sb.tile_max;
-  A.tile_bad = sb.tile_bad;
+  A.tile_min = sb.tile_min + (size_t)side * sb.tiles_cap;
+  A.tile_max = sb.tile_max + (size_t)side * sb.tiles_cap;
+  A.tile_bad = sb.tile_bad + (size_t)side * sb.tiles_cap;
+  A.chunk_max = sb.chunk_max + (size_t)side * sb.tiles_cap * BW_SC_WARPS;
+  A.late_bits = late_bits;  // second run over an activation with late rows: they are left out
+  A.ts0_set = late_bits ? 1u : 0u;
+  A.ts0 = ts0;
   A.cap = f->t.cap;
   A.seg_shift = f->t.seg_shift;
   A.nstage = (u32)f->scatter_nstage;
@@ -1299,7 +1319,7 @@ static bw_status stream_front(bw_fold* f, const u64* d_keys, const void* d_vals,
   if (grid) f->scatter_kernel<<<grid, BW_SC_THREADS, f->scatter_smem, s>>>(A, f->p);
   if (f->p.ts_from_value == 2) k_verdict_none<<<1, 1, 0, s>>>(f->p, f->d_ctr, sb.side[side].sv, vg, rows);
   else
-    k_verdict<<<1, 1024, 0, s>>>(sb.tile_min, sb.tile_max, sb.tile_bad, (u32)ntiles, f->p, f->d_ctr, sb.side[side].sv,
+    k_verdict<<<1, 1024, 0, s>>>(A.tile_min, A.tile_max, A.tile_bad, (u32)ntiles, f->p, f->d_ctr, sb.side[side].sv,
                                  f->has_ts ? d_ts : nullptr, (const u64*)d_vals, vg);
   CU(ctx, cudaGetLastError());
   f->pt.mark(5, 1, s);
@@ -1540,6 +1560,74 @@ static bw_status stream_resolve_multi(bw_fold* f, const Deferred& d) {
 
 // The fold stage of the deferred activation: the segment fold when its verdict allows, else what the
 // direct path would have done (its scatter output is dropped; the input columns are still there).
+// An activation the verdict could not prove clean (one GPU): find its late rows without sorting it (bw_late.cuh), then
+// scatter it again without them.  *ok: *sv is now the verdict of the rows that are left -- none of them late, so the
+// streaming fold is exact for them -- and the late rows wait in f->late for k_late_emit.  Not ok (more suspects than
+// the table takes, or the second scatter raised a flag): nothing has been folded or emitted, take the sort path.
+static bw_status late_split(bw_fold* f, const Deferred& d, const BatchView& bv, StreamVerdict* sv, bool* ok) {
+  bw_ctx* ctx = f->ctx;
+  const StreamBufs& sb = f->sb;
+  cudaStream_t s = f->s_compute;
+  *ok = false;
+  LateBufs& L = f->late;
+  if (!f->late_ready) {
+    const u64 maxr = f->spec.max_batch_rows;
+    L.cap = (u32)std::max<u64>(1024, maxr / 16);
+    u32 M = 2048;
+    while (M < 2 * L.cap) M <<= 1;
+    L.m_mask = M - 1;
+    u32 kb = 1u << 16;
+    while (kb < 16 * L.cap && kb < (1u << 27)) kb <<= 1;
+    L.kb_mask = kb - 1;
+    CU(ctx, dmalloc(&L.key_bits, kb / 32));
+    CU(ctx, dmalloc(&L.late_bits, maxr / 32 + 2));
+    CU(ctx, dmalloc(&L.ent, M));
+    CU(ctx, cudaMemsetAsync(L.ent, 0, (size_t)M * sizeof(LateEnt), s));  // generation 0: every entry free, once
+    CU(ctx, dmalloc(&L.counters, 2));
+    CU(ctx, dmalloc(&L.s_key, L.cap));
+    CU(ctx, dmalloc(&L.s_ts, L.cap));
+    CU(ctx, dmalloc(&L.s_idx, L.cap));
+    CU(ctx, dmalloc(&L.s_slot, L.cap));
+    CU(ctx, dmalloc(&L.gpre, sb.tiles_cap));
+    CU(ctx, dmalloc(&f->late_chunk_pre, (size_t)sb.tiles_cap * BW_SC_WARPS));
+    CU(ctx, cudaHostAlloc((void**)&f->h_late_ctr, 2 * sizeof(u32), cudaHostAllocDefault));
+    f->late_ready = true;
+  }
+  const u64 rows = d.rows;
+  const u32 ntiles = (u32)((rows + BW_SC_TILE - 1) / BW_SC_TILE);
+  CU(ctx, cudaMemsetAsync(L.key_bits, 0, ((size_t)L.kb_mask + 1) / 8, s));
+  CU(ctx, cudaMemsetAsync(L.late_bits, 0, (rows / 32 + 2) * sizeof(u32), s));
+  L.gen = d.batch_no + 1u;  // (batch numbers of a fold never repeat)
+  CU(ctx, cudaMemsetAsync(L.counters, 0, 2 * sizeof(u32), s));
+  const size_t toff = (size_t)d.side * sb.tiles_cap;
+  const int wide = ctx->sm_count * 8;
+  k_late_gpre<<<1, 1024, 0, s>>>(sb.tile_max + toff, ntiles, sv->gprev, L.gpre);
+  k_late_chunkpre<<<(int)std::min<u32>((ntiles + 7u) / 8u, (u32)wide), 256, 0, s>>>(sb.chunk_max + toff * BW_SC_WARPS, L.gpre, ntiles, f->late_chunk_pre);
+  k_late_suspect<<<wide, 256, 0, s>>>(bv, f->p, rows, f->late_chunk_pre, L);
+  k_late_build<<<wide, 256, 0, s>>>(L);
+  k_late_prefmax<<<wide, 256, 0, s>>>(bv, f->p, rows, L);
+  k_late_classify<<<wide, 256, 0, s>>>(f->t, f->p, L);
+  k_stream_reset<<<1, 1, 0, s>>>(f->t, sb.side[d.side].sv);  // what the first scatter set aside / flagged is void
+  CU(ctx, cudaGetLastError());
+  f->st.kernel_launches += 7;
+  CU(ctx, cudaMemcpyAsync(f->h_late_ctr, L.counters, 2 * sizeof(u32), cudaMemcpyDeviceToHost, s));
+  // base of the records' 32-bit relative timestamps: row 0 may be a late row from far back, so count from the
+  // activation's newest timestamp instead
+  i64 ts0 = sv->tmin;
+  if (sv->tmax - (i64)0x7FFFFFF0 > ts0) ts0 = sv->tmax - (i64)0x7FFFFFF0;
+  bw_status st = stream_front(f, d.d_keys, d.d_vals, d.d_ts, rows, d.batch_no, d.side, L.late_bits, ts0);
+  if (st != BW_OK) return st;
+  CU(ctx, cudaEventSynchronize(f->ev_sv[d.side]));
+  if (f->h_late_ctr[0] > L.cap || f->h_late_ctr[1]) return BW_OK;
+  const StreamVerdict sv2 = f->h_sv[d.side];
+  if (sv2.flags) return BW_OK;
+  *sv = sv2;
+  sv->clean = 1u;
+  sv->ts0 = ts0;
+  *ok = true;
+  return BW_OK;
+}
+
 static bw_status stream_resolve(bw_fold* f) {
   bw_ctx* ctx = f->ctx;
   Deferred d = f->dq;
@@ -1549,8 +1637,21 @@ static bw_status stream_resolve(bw_fold* f) {
   cudaStream_t s = f->s_compute;
   CU(ctx, cudaEventSynchronize(f->ev_sv[d.side]));
   if (ctx->world > 1) return stream_resolve_multi(f, d);
-  const StreamVerdict sv = f->h_sv[d.side];
+  StreamVerdict sv = f->h_sv[d.side];
   const FoldParams& p = f->p;
+  BatchView bv;
+  memset(&bv, 0, sizeof bv);
+  bv.nseg = 1;
+  bv.keys[0] = d.d_keys;
+  bv.vals[0] = d.d_vals;
+  bv.ts[0] = f->has_ts ? d.d_ts : nullptr;
+  bv.h_counts[0] = d.rows;
+  bv.max_rows = d.rows;
+  bool split = false;
+  if (!sv.clean && p.track_wm && f->late_split) {
+    bw_status lst = late_split(f, d, bv, &sv, &split);
+    if (lst != BW_OK) return lst;
+  }
   i64 q_lo = 0, q_hi = 0;
   if (sv.tmax >= sv.tmin) {
     q_lo = bw_floordiv(sv.tmin - p.align_us, p.pane_us);
@@ -1594,6 +1695,12 @@ static bw_status stream_resolve(bw_fold* f) {
               sb.nb, d.lanes, sb.lane_cap, (unsigned long long)d.rows, (unsigned long long)sum, mx, sv.n_spill, sv.flags, (long long)sv.tmin,
               (long long)sv.tmax);
     }
+    if (split) {
+      k_late_emit<<<ctx->sm_count * 4, 256, 0, s>>>(bv, f->t, f->p, f->e, f->late, d.batch_no,
+                                                                                                            d.ord);
+      f->st.kernel_launches++;
+      f->st.split_batches++;
+    }
     const u32 n_pre = std::min<u32>(sv.n_spill, sb.spill_cap);  // rows the scatter set aside: fold them first
     if (n_pre) {
       k_spill<<<(int)std::min<u32>((n_pre + 255) / 256, (u32)ctx->sm_count * 4), 256, 0, s>>>(f->t, f->p, sb.side[d.side].spill, sb.side[d.side].sv,
@@ -1615,14 +1722,7 @@ static bw_status stream_resolve(bw_fold* f) {
     f->pt.mark(7, 1, s);
   } else {
     // (the scatter output of this activation is simply not read)
-    BatchView bv;
-    memset(&bv, 0, sizeof bv);
-    bv.nseg = 1;
-    bv.keys[0] = d.d_keys;
-    bv.vals[0] = d.d_vals;
-    bv.ts[0] = f->has_ts ? d.d_ts : nullptr;
-    bv.h_counts[0] = d.rows;
-    bv.max_rows = d.rows;
+    if (split) sv = f->h_sv[d.side], sv.clean = 0u;  // (split, but too many panes for the segment fold: the sort path; nothing was emitted)
     if (sv.clean) {
       st = direct_fold(f, bv, d.rows, d.batch_no, d.ord, sv.tmin, sv.tmax);
     } else {
@@ -1655,6 +1755,7 @@ static bw_status run_batch(bw_fold* f, const u64* d_keys, const void* d_vals, co
     if (ctx->world == 1) f->st.rows_received += rows;
     bw_status st = stream_front(f, d_keys, d_vals, d_ts, rows, batch_no, side);
     if (st != BW_OK) return st;
+    const u32 lanes = f->last_scatter_grid;  // (resolving the previous activation may scatter it a second time)
     st = stream_resolve(f);
     if (st != BW_OK) return st;
     Deferred& d = f->dq;
@@ -1666,7 +1767,7 @@ static bw_status run_batch(bw_fold* f, const u64* d_keys, const void* d_vals, co
     d.rows = rows;
     d.ord = ord;
     d.batch_no = batch_no;
-    d.lanes = f->last_scatter_grid;
+    d.lanes = lanes;
     d.stage = stage;
     return BW_OK;
   }
@@ -2131,6 +2232,7 @@ bw_status bw_fold_reset_timers(bw_fold* f) {
   f->st.fold_rows = 0;
   f->st.fold_launches = 0;
   f->st.combined_folds = 0;
+  f->st.split_batches = 0;
   return BW_OK;
 }
 bw_status bw_fold_sync(bw_fold* f) {

@@ -182,6 +182,7 @@ typedef struct bw_stats {
   float sum_scatter_ms;     /* CUDA-event time of the scatter + verdict stage of those activations */
   float reserved0;
   uint64_t scatter_launches;
+  uint64_t split_batches;   /* not-clean activations whose late rows were found without the sort (streaming fold for the rest) */
 } bw_stats;
 
 /* ---- context ---------------------------------------------------------- */

@@ -151,11 +151,84 @@ def test_against_c_oracle_medium(ctx, fold_mode, red, length, offset, wait, jitt
     assert em.late_val.astype(np.int64).tolist() == lv.tolist() and em.late_ts_us.tolist() == lts.tolist()
     st = fold.stats()
     if jitter > (wait if wait is not None else 10**9):
-        assert st.slow_batches > 0
+        assert st.slow_batches + st.split_batches > 0
     if fold_mode == "stream" and wait is not None:  # every clean activation took the streaming path
         assert st.combined_folds == st.fold_launches and st.fold_launches + st.slow_batches == len(batches)
     if fold_mode == "direct":
         assert st.combined_folds == 0
+    fold.close()
+    orc.close()
+
+
+@pytest.mark.parametrize("red,length,offset,wait,dtype,shape", [
+    ("count", 10, None, 0, "i64", "stragglers"),
+    ("sum", 10, None, 2, "i64", "stragglers"),
+    ("sum", 10, 5, 1, "i64", "stragglers"),        # sliding: a late row is reported once per window it would have joined
+    ("min", 10, None, 2, "i64", "stragglers"),
+    ("sum", 10, None, 1, "f64", "stragglers"),
+    ("sum", 10, None, 1, "i64", "jump"),           # a row from the future makes the same key's next rows late
+    ("count", 10, 5, 1, "i64", "jump"),
+    ("max", 10, None, 0, "i64", "first-row"),      # row 0 of every activation is an hour old (base of the relative timestamps)
+])
+def test_stragglers_without_the_sort(ctx, fold_mode, red, length, offset, wait, dtype, shape):
+    """An in-order stream with a few late rows: the streaming path finds them with the suspect table (bw_late.cuh) and
+    folds the rest as a clean activation; rows, late rows and their order must be the exact path's (= the oracle's)."""
+    S = 1_000_000
+    A = 1_640_995_200_000_000
+    n, nb, n_keys = 60_000, 6, 4000
+    rnd = np.random.default_rng(hash((red, length, shape)) & 0xFFFF)
+    is_float = dtype == "f64"
+    orc = coracle.COracle(red, length * S, offset * S if offset else None, A, wait * S, False, is_float=is_float)
+    fold = _make_fold(ctx, dict(reduction=red, length_us=length * S, offset_us=offset * S if offset else None, align_us=A,
+                                wait_us=wait * S, ordered=False), is_float, capacity_hint=8192, max_batch_rows=1 << 16,
+                      max_emit_rows=1 << 20, max_late_rows=1 << 20)
+    n_dirty = 0
+    for b in range(nb):
+        keys = rnd.integers(0, n_keys, n).astype(np.uint64)
+        ts = (A + b * 8 * S + (np.arange(n) * 8 * S) // n).astype(np.int64)
+        if b != 2 and not (shape == "first-row" and b == 0):  # (one activation stays clean; the very first row ever is never late)
+            n_dirty += 1
+            if shape == "stragglers":
+                late = rnd.random(n) < 0.005
+                ts[late] -= rnd.integers(3 * S, 40 * S, int(late.sum()))
+            elif shape == "jump":
+                at = int(rnd.integers(n // 4, n // 2))
+                ts[at] += wait * S + S // 2          # the rows of the next half second are behind it by more than `wait`
+                keys[at + 1: at + 2000: 7] = keys[at]  # ... and some of them are this key's: late; the others are not
+                late = rnd.random(n) < 0.001
+                ts[late] -= 20 * S
+            else:
+                ts[0] -= 3600 * S
+                ts[n // 2] -= 3 * S
+        vals = rnd.normal(0, 100, n) if is_float else rnd.integers(-1000, 1000, n)
+        orc.on_batch(keys, ts, vals)
+        fold.ingest(keys, vals, ts)
+    orc.on_eof()
+    em, em_eof = fold.advance(), fold.eof()
+    ck, cw, ca, cc, cact = orc.closed()
+    lk, lw, lv, lts, lact = orc.late()
+    cat = np.concatenate
+    assert len(lk) > 0
+    assert cat([em.closed_key, em_eof.closed_key]).tolist() == ck.tolist()
+    assert cat([em.closed_window_id, em_eof.closed_window_id]).tolist() == cw.tolist()
+    got_acc = cat([em.closed_acc, em_eof.closed_acc])
+    if is_float:
+        assert np.allclose(got_acc.astype(np.float64), np.asarray(ca, dtype=np.float64), rtol=REL_TOL, atol=1e-9)
+    else:
+        assert got_acc.astype(np.int64).tolist() == ca.tolist()
+    assert em.closed_epoch.tolist() == (cact[: len(em.closed_epoch)] + 1).tolist()
+    assert em.late_key.tolist() == lk.tolist() and em.late_window_id.tolist() == lw.tolist()
+    assert em.late_ts_us.tolist() == lts.tolist()
+    if is_float:
+        assert np.array_equal(em.late_val.astype(np.float64), np.asarray(lv, dtype=np.float64))
+    else:
+        assert em.late_val.astype(np.int64).tolist() == lv.tolist()
+    st = fold.stats()
+    if fold_mode == "stream":
+        assert st.split_batches == n_dirty and st.slow_batches == 0, (st.split_batches, st.slow_batches)
+        assert st.combined_folds == nb
+    else:
+        assert st.slow_batches == n_dirty
     fold.close()
     orc.close()
 
