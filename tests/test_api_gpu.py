@@ -185,3 +185,79 @@ def test_max_min_window_numeric_on_gpu():
     assert [(k, (w, int(v))) for k, (w, v) in gpu[0]] == [("a", (0, 9)), ("a", (1, 10))]
     assert [(k, (w, int(v))) for k, (w, v) in gpu[1]] == [("a", (0, 1)), ("a", (1, 4))]
     assert [[(k, (w, int(v))) for k, (w, v) in o] for o in host] == [[(k, (w, int(v))) for k, (w, v) in o] for o in gpu]
+
+
+def test_stateful_map_detector_runs_on_k5():
+    """`op.stateful_map` with the declared z-score detector (BASELINE config C2's mapper, examples/anomaly_detector.py) is
+    handed to bw_smap_* by the recogniser; items must equal the host engine's, which calls the mapper per item."""
+    from bytewax_b200 import engine
+    from bytewax_b200.detectors import ZScoreDetector
+
+    rnd = np.random.default_rng(5)
+    n = 20_000
+    vals = rnd.normal(10.0, 2.0, n)
+    vals[rnd.random(n) < 0.01] += 25.0  # anomalies
+    items = [(f"m{int(k)}", float(v)) for k, v in zip(rnd.integers(0, 300, n), vals)]
+    made = []
+    orig = engine._gpu_step_for
+
+    def spy(step_id, plan):
+        st = orig(step_id, plan)
+        made.append(type(st).__name__)
+        return st
+
+    def build():
+        out = []
+        flow = Dataflow("test_df")
+        s = op.input("inp", flow, TestingSource(items, batch_size=2500))
+        d = op.stateful_map("detector", s, ZScoreDetector(window=10, threshold_z=2.0))
+        op.output("out", d, TestingSink(out))
+        return flow, out
+
+    engine._gpu_step_for = spy
+    try:
+        host, gpu = _both(build)
+    finally:
+        engine._gpu_step_for = orig
+    assert made == ["_GpuSmapStep"]
+    assert len(gpu) == n and any(r[1][3] for r in gpu)
+    # key order, values, means and flags are identical (K5 sums in CPython's order: compensated, newest first); sigma is
+    # a correctly rounded sqrt on the device and `x ** 0.5` (libm pow, not always correctly rounded) in the mapper: 1 ulp
+    assert [(k, v[0], v[1], v[3]) for k, v in gpu] == [(k, v[0], v[1], v[3]) for k, v in host]
+    assert np.allclose([v[2] for _k, v in gpu], [v[2] for _k, v in host], rtol=1e-15, atol=0.0)
+
+
+@pytest.mark.parametrize("insert_mode,emit_mode", [("last", "complete"), ("first", "final"), ("last", "running")])
+def test_join_runs_on_k6(insert_mode, emit_mode):
+    """Two-sided `op.join` on bw_join_* (values travel as handles): rows and their order equal the host `_JoinLogic`."""
+    from bytewax_b200 import engine
+
+    rnd = np.random.default_rng(9)
+    n = 6000
+    left = [(f"u{int(k)}", {"name": f"n{i}"}) for i, k in enumerate(rnd.integers(0, 1500, n))]
+    right = [(f"u{int(k)}", ("mail", i)) for i, k in enumerate(rnd.integers(0, 1500, n))]
+    made = []
+    orig = engine._gpu_step_for
+
+    def spy(step_id, plan):
+        st = orig(step_id, plan)
+        made.append(type(st).__name__)
+        return st
+
+    def build():
+        out = []
+        flow = Dataflow("test_df")
+        a = op.input("a", flow, TestingSource(left, batch_size=500))
+        b = op.input("b", flow, TestingSource(right, batch_size=500))
+        j = op.join("j", a, b, insert_mode=insert_mode, emit_mode=emit_mode)
+        op.output("out", j, TestingSink(out))
+        return flow, out
+
+    engine._gpu_step_for = spy
+    try:
+        host, gpu = _both(build)
+    finally:
+        engine._gpu_step_for = orig
+    assert made == ["_GpuJoinStep"]
+    assert len(gpu) > 0
+    assert gpu == host
