@@ -108,6 +108,7 @@ SYMBOLS = {
     "bw_ingest_acquire": (C.c_int32, [_P, C.c_uint64, C.POINTER(BwBatch)]),
     "bw_ingest_commit": (C.c_int32, [_P, C.POINTER(BwBatch), C.c_uint64, C.c_uint64]),
     "bw_ingest_device": (C.c_int32, [_P, _P, _P, _P, C.c_uint64, C.c_uint64]),
+    "bw_fold_set_system_now": (C.c_int32, [_P, C.c_int64]),
     "bw_advance": (C.c_int32, [_P, C.c_uint64, C.c_int64, C.POINTER(BwEmit)]),
     "bw_eof": (C.c_int32, [_P, C.POINTER(BwEmit)]),
     "bw_snapshot_take": (C.c_int32, [_P, C.POINTER(BwSnapshot)]),

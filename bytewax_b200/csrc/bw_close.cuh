@@ -317,4 +317,25 @@ __global__ void k_close_all(Table t, FoldParams p, EmitBufs e, u64 epoch, u32 cl
     bw_close_key(t, p, e, s, true, epoch, close_batch);
   }
 }
+// Notify phase (src/operators.rs:808-858): system time has moved on with no items.  A key is DUE when the close time of
+// its earliest open window has been reached by the system clock (`notify_at` = min close of the opened windows,
+// windowing.py:656-659, passed through `to_system_utc`'s default identity); a due key closes what its watermark
+//   max_j(ts_j - now_j) - wait + now   allows (`on_notify`, windowing.py:1137-1144).  In the kernels' frame the system
+// time is 0 (FoldParams::now_us).
+__global__ void k_close_wake(Table t, FoldParams p, EmitBufs e, u64 epoch, u32 close_batch) {
+  const u64 n = t.cap + 1;
+  const i64 a = p.panes_per_offset, b = p.panes_per_window;
+  for (u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += (u64)gridDim.x * blockDim.x) {
+    const HotSlot h = t.hot[s];
+    if (s < t.cap && h.key == BW_EMPTY_KEY) continue;
+    if (h.wt0 == BW_EMPTY_WIDTAG) continue;
+    i64 q_old = bw_widtag_q(h.wt0);
+    if (t.p1[s].seq1 != ~0ULL) q_old = min(q_old, bw_widtag_q1(h.wt0));
+    for (u32 nd = t.aux[s].spill_head; nd; nd = t.nodes[nd].next) q_old = min(q_old, t.nodes[nd].wid);
+    i64 w_first = bw_floordiv(q_old - b + a, a);  // earliest window over the oldest pane ...
+    if (!(a == 1 && b == 1) && t.closed_upto[s] != INT64_MIN && w_first <= t.closed_upto[s]) w_first = t.closed_upto[s] + 1;  // ... not yet emitted
+    if (p.align_us + w_first * p.offset_us + p.length_us > 0) continue;  // not due
+    bw_close_key(t, p, e, s, false, epoch, close_batch);
+  }
+}
 __global__ void k_reset_dirty(Table t) { t.ctr->dirty_count = 0; }

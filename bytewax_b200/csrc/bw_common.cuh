@@ -158,6 +158,11 @@ struct FoldParams {
   int seq_by_id;         // first-opened order == ascending window id (ordered flush, or wait == 0: a key's accepted
                          // timestamps never decrease), so emission order needs no arrival sequence
   u64 acc_identity;
+  // System time (windowing.py:263-302).  The watermark of a key is  max_j(ts_j - now_j) - wait + now  (now_j: system time
+  // when item j arrived): everything the kernels do is invariant under shifting all times by -now, so they work in the
+  // frame where the current system time is 0: every timestamp is taken as ts - now_us, align_us is
+  // spec.align_us - now_us, and a slot's max_ts holds max_j(ts_j - now_j).  now_us == 0 (never set): the frozen clock.
+  i64 now_us;
 };
 
 struct Table {

@@ -244,7 +244,9 @@ __device__ __forceinline__ void bw_after_fold(const Table& t, const FoldParams& 
   if (C::wm(p)) {
     if (ts > mts) bw_red_max_s64(&hs->max_ts, ts);
     if (!(tag0 & BW_TAG_DIRTY)) {
-      bool mark = created;
+      // (a moving system clock, FoldParams::now_us: the key's watermark also grew while it was idle, so what this
+      // event's own timestamp proves closable is not the whole story: K4 looks at every key the activation touched)
+      bool mark = created || p.now_us != 0;
       if (!mark) {
         const u32 delta = bw_widtag_delta(tag0);
         const i64 qc = q - p.close_back - ((rem < p.wait_rem) ? 1 : 0);
@@ -418,7 +420,7 @@ __device__ __forceinline__ void bw_load_event(const BatchView& bv, int seg, u64 
   if (p.ts_from_value) {
     ts = p.align_us + ((p.ts_from_value == 1) ? (i64)raw : 0);  // 2 == BW_TS_NONE: everything in window 0
   } else {
-    ts = (i64)bw_ld_stream_u64((const u64*)bv.ts[seg] + i);
+    ts = (i64)bw_ld_stream_u64((const u64*)bv.ts[seg] + i) - p.now_us;
   }
   // operand in accumulator representation
   if (p.val_dtype >= 2) {
@@ -451,7 +453,7 @@ __device__ __forceinline__ i64 bw_event_ts(const BatchView& bv, const u64* seg_s
   int seg = 0;
   u64 off = g;
   if (bv.nseg > 1) bw_locate(bv, seg_start, g, seg, off);
-  return (i64)bw_ld_stream_u64((const u64*)bv.ts[seg] + off);
+  return (i64)bw_ld_stream_u64((const u64*)bv.ts[seg] + off) - p.now_us;
 }
 
 // The fold kernel.  Launched only for batches the prepass proved free of late

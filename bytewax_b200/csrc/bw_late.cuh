@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(256) k_late_suspect(BatchView bv, FoldParams p
   const u64 gw = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((u64)gridDim.x * blockDim.x) >> 5;
   const u64 ntask = (n + BW_LATE_CHUNK - 1) / BW_LATE_CHUNK;
   const u64* col = p.ts_from_value ? (const u64*)bv.vals[0] : (const u64*)bv.ts[0];
-  const i64 add = p.ts_from_value ? p.align_us : 0;
+  const i64 add = p.ts_from_value ? p.align_us : -p.now_us;
   // (the next step's loads are issued before this step's rows are looked at: the memory system stays busy while the
   // warp scans)
   auto load4 = [&](u64 t0, i64* ta, i64* tb, i64* pre) {
@@ -393,6 +393,7 @@ __global__ void __launch_bounds__(256) k_late_emit(BatchView bv, Table t, FoldPa
     for (int u = 0; u < 4; ++u) {
       if (!nw[u]) continue;
       const u32 i = x[u].idx;
+      if (p.now_us != 0) bw_wake_key(t, x[u].key);
       u64 raw = 0;
       if (bv.vals[0]) raw = (p.val_dtype == 2) ? (u64)((const u32*)bv.vals[0])[i] : ((const u64*)bv.vals[0])[i];
       // late rows carry the raw value bits widened to 64 (f32 -> f64 bits)
@@ -403,7 +404,7 @@ __global__ void __launch_bounds__(256) k_late_emit(BatchView bv, Table t, FoldPa
         e.l_key[at + j] = x[u].key;
         e.l_wid[at + j] = w0[u] + j;
         e.l_val[at + j] = vbits;
-        e.l_ts[at + j] = x[u].ts;
+        e.l_ts[at + j] = x[u].ts + p.now_us;  // (back from the frame where system time is 0)
         e.l_seq[at + j] = seq;
         e.l_epoch[at + j] = epoch;
       }

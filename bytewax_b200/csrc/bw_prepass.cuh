@@ -25,7 +25,7 @@ __device__ __forceinline__ i64 bw_load_ts(const BatchView& bv, int seg, u64 off,
                                  : bw_ld_stream_u64((const u64*)bv.vals[seg] + off);
     return p.align_us + (i64)raw;
   }
-  return (i64)bw_ld_stream_u64((const u64*)bv.ts[seg] + off);
+  return (i64)bw_ld_stream_u64((const u64*)bv.ts[seg] + off) - p.now_us;  // (the frame where system time is 0: FoldParams)
 }
 
 // one warp per range: exact within-range check + (min, max) for the cross-range scan

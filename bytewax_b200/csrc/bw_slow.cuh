@@ -56,6 +56,25 @@ __device__ __forceinline__ i64 bw_lookup_max_ts(const Table& t, u64 key) {
   return INT64_MIN;
 }
 
+// A key whose only items of an activation were late still had `on_batch` run (windowing.py:1115-1133): under a moving
+// system clock its watermark may have grown since its last activation, so K4 has to look at it.
+__device__ __forceinline__ void bw_wake_key(const Table& t, u64 key) {
+  u64 s = bw_home_slot(t, key);
+  if (key != BW_EMPTY_KEY) {
+    u64 probe = 0;
+    for (; probe <= (u64)t.seg_mask; ++probe) {
+      const u64 k = t.hot[s].key;
+      if (k == key) break;
+      if (k == BW_EMPTY_KEY) return;
+      s = bw_probe_next(t, s, 1);
+    }
+    if (probe > (u64)t.seg_mask) return;
+  }
+  if (t.hot[s].wt0 == BW_EMPTY_WIDTAG) return;  // no open window
+  const unsigned long long old = atomicOr((unsigned long long*)&t.hot[s].wt0, (unsigned long long)BW_TAG_DIRTY);
+  if (!(old & (unsigned long long)BW_TAG_DIRTY)) t.dirty[atomicAdd(&t.ctr->dirty_count, 1u)] = (u32)s;
+}
+
 // sorted order i -> late flag at arrival index
 __global__ void k_slow_classify(Table t, FoldParams p, const u64* keys_sorted, const u32* idx_sorted,
                                 const i64* ts_sorted, const i64* prefmax, unsigned char* late, u64 n) {
@@ -104,6 +123,7 @@ k_slow_fold(BatchView bv, Table t, FoldParams p, EmitBufs e, const unsigned char
         i64 w0 = bw_floordiv(d - p.length_us, p.offset_us) + 1;
         i64 w1 = bw_floordiv(d, p.offset_us);
         u32 nw = (w1 >= w0) ? (u32)(w1 - w0 + 1) : 0u;
+        if (p.now_us != 0) bw_wake_key(t, key);
         u64 at = bw_warp_reserve(&t.ctr->n_late, nw);
         if (at + nw > e.max_late) {
           bw_raise(t.ctr, 3u);
@@ -115,7 +135,7 @@ k_slow_fold(BatchView bv, Table t, FoldParams p, EmitBufs e, const unsigned char
             e.l_key[at + j] = key;
             e.l_wid[at + j] = w0 + j;
             e.l_val[at + j] = vbits;
-            e.l_ts[at + j] = ts;
+            e.l_ts[at + j] = ts + p.now_us;  // (back from the frame where system time is 0)
             e.l_seq[at + j] = seq;
             e.l_epoch[at + j] = epoch;
           }

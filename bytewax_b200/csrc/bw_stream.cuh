@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(BW_SC_THREADS, 1) k_scatter(ScatterArgs A, Fol
   const u64 ntiles = (A.n + T - 1) / T;
   // base of the relative timestamps: event time of row 0
   i64 ts0 = p.align_us;
-  if (TSM == 0) ts0 = A.ts[0];
+  if (TSM == 0) ts0 = A.ts[0] - p.now_us;
   else if (TSM == 1) ts0 = p.align_us + (i64)((const u64*)A.vals)[0];
   if (A.ts0_set) ts0 = A.ts0;
   u32* flags = &A.out.sv->flags;
@@ -325,6 +325,10 @@ __global__ void __launch_bounds__(BW_SC_THREADS, 1) k_scatter(ScatterArgs A, Fol
     if (TSM == 1) {
       ta = p.align_us + (i64)xa;
       tb = p.align_us + (i64)xb;
+    }
+    if (TSM == 0) {  // the frame where system time is 0 (FoldParams::now_us; 0 unless the caller moves the clock)
+      ta -= p.now_us;
+      tb -= p.now_us;
     }
     // the columns are in registers: this warp is done with the stage; the last warp to say so refills it
     __syncwarp();
@@ -487,7 +491,7 @@ k_verdict(const i64* tile_min, const i64* tile_max, const u32* tile_bad, u32 nti
     if (lane == 31) {
       sv->tmin = act.mn;
       sv->tmax = act.mx;
-      sv->ts0 = (ntiles == 0) ? p.align_us : (ts_col ? ts_col[0] : p.align_us + (i64)val_col[0]);
+      sv->ts0 = (ntiles == 0) ? p.align_us : (ts_col ? ts_col[0] - p.now_us : p.align_us + (i64)val_col[0]);
       if (vg) {
         // multi-GPU: this rank's slice only; the slices are chained on the host once gathered
         vg->tmin = act.mn;
@@ -1071,7 +1075,7 @@ k_segfold(SegArgs A, Table t, FoldParams p, EmitBufs e) {
         {
           i64 rem;
           const i64 qn = bw_pane_of_r(ts_new, p, rem);
-          bool mark = created;
+          bool mark = created || p.now_us != 0;  // (moving system clock: see bw_after_fold)
           if (WM && !mark) {
             const u32 delta = bw_widtag_delta(tag0);
             const i64 qc = qn - p.close_back - ((rem < p.wait_rem) ? 1 : 0);

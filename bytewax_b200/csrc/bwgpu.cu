@@ -2053,13 +2053,35 @@ static bw_status collect(bw_fold* f, bw_emit* out) {
   return BW_OK;
 }
 
+bw_status bw_fold_set_system_now(bw_fold* f, int64_t system_now_us) {
+  if (!f) return BW_ERR_SPEC;
+  if (f->ctx->world > 1) FAIL(f, BW_ERR_SPEC, "bw_fold_set_system_now: one rank only (every rank would need the same clock)");
+  CU(f->ctx, cudaSetDevice(f->ctx->device));
+  if (!f->p.track_wm || f->p.ts_from_value == 2) return BW_OK;  // no watermark to move
+  if (system_now_us <= f->p.now_us) return BW_OK;              // "don't let now go backwards" (windowing.py:250-261)
+  bw_status st = stream_resolve(f);  // the activation in flight was scattered in the old frame: fold it there
+  if (st != BW_OK) return st;
+  f->p.now_us = system_now_us;
+  f->p.align_us = f->spec.align_to_us - system_now_us;
+  return BW_OK;
+}
+
 bw_status bw_advance(bw_fold* f, uint64_t closed_epoch, int64_t system_now_us, bw_emit* out) {
   (void)closed_epoch;
-  (void)system_now_us;
   if (!f || !out) return BW_ERR_SPEC;
-  CU(f->ctx, cudaSetDevice(f->ctx->device));
+  bw_ctx* ctx = f->ctx;
+  CU(ctx, cudaSetDevice(ctx->device));
   bw_status st = stream_resolve(f);
   if (st != BW_OK) return st;
+  if (system_now_us > 0 && ctx->world == 1 && f->p.track_wm && f->p.ts_from_value != 2 && !f->eof_done) {
+    // the notify phase at this system time: due keys close what their watermark now allows
+    st = bw_fold_set_system_now(f, system_now_us);
+    if (st != BW_OK) return st;
+    if (!f->have_pending) { f->min_epoch = f->last_epoch; f->have_pending = true; }
+    k_close_wake<<<f->close_grid, 256, 0, f->s_compute>>>(f->t, f->p, f->e, f->last_epoch, f->batch_no);
+    CU(ctx, cudaGetLastError());
+    f->st.kernel_launches++;
+  }
   return collect(f, out);
 }
 

@@ -178,9 +178,30 @@ class _GpuWindowStep:
             self.fold = self._mk("f64" if self.float_vals else "i64")
         if v is not None and v.dtype.kind == "f" and not self.float_vals:
             raise TypeError(f"step {self.step_id!r}: value type changed from integer to float mid-stream")
+        self._set_now()
         self.fold.ingest(k, v, t, max(epoch, self.last_epoch))  # (the engine's frontier already keeps epochs in order)
         self.last_epoch = max(epoch, self.last_epoch)
         return self._rows(self.fold.advance(), orig)
+
+    def _now_us(self):
+        getter = getattr(self.plan.clock, "now_getter", None)
+        return None if getter is None else _us(getter())
+
+    def _set_now(self):
+        # what `before_batch` samples (windowing.py:250-261): the watermark drifts with the system clock
+        now = self._now_us()
+        if now is not None and now > 0:
+            self.fold.set_system_now(now)
+
+    def on_notify(self) -> list:
+        """The notify phase (src/operators.rs:808-858): keys whose earliest window's close time has come close what their
+        watermark -- which moves with the system clock -- allows, without waiting for another item or EOF."""
+        if self.fold is None:
+            return []
+        now = self._now_us()
+        if now is None or now <= 0:
+            return []
+        return self._rows(self.fold.advance(system_now_us=now), [])
 
     def on_eof(self) -> list:
         if self.fold is None:
@@ -222,6 +243,11 @@ class _GpuWindowStep:
         return rows
 
 
+class _NoClock:
+    def on_notify(self) -> list:
+        return []
+
+
 def _gpu_step_for(step_id: str, plan):
     from bytewax_b200.operators import GpuFinalPlan, GpuJoinPlan, GpuSmapPlan
 
@@ -242,7 +268,7 @@ def _split_item(step_id: str, item):
     return key, value
 
 
-class _GpuSmapStep(_GpuWindowStep):
+class _GpuSmapStep(_NoClock, _GpuWindowStep):
     """One worker's ``stateful_map`` with a declared z-score detector (``GpuSmapPlan``) on ``bw_smap_*`` (K5): one call per
     activation instead of one mapper call per item; emits what `_StatefulFlatMapLogic` would, key by key in ascending
     key-string order, a key's items in arrival order (operators/__init__.py:2860-2890, src/operators.rs:755-806)."""
@@ -286,7 +312,7 @@ class _GpuSmapStep(_GpuWindowStep):
         return []
 
 
-class _GpuJoinStep(_GpuWindowStep):
+class _GpuJoinStep(_NoClock, _GpuWindowStep):
     """One worker's two-sided ``join`` (``GpuJoinPlan``) on ``bw_join_*`` (K6).  Items are ``(key, (side, value))`` from
     ``_join_label_merge``; the values stay on the host, the device joins their handles (operators/__init__.py:2157-2190)."""
 
@@ -338,7 +364,7 @@ class _GpuJoinStep(_GpuWindowStep):
         return out
 
 
-class _GpuFinalStep(_GpuWindowStep):
+class _GpuFinalStep(_NoClock, _GpuWindowStep):
     """One worker's ``stateful_batch`` of a numeric ``*_final`` fold (``reduce_final(add|max|min)``, ``count_final``,
     ``max_final``, ``min_final``) on ``libbwgpu``: ``ts_source == BW_TS_NONE``, every key's accumulator is emitted at EOF in
     ascending key-string order (``_FoldFinalLogic.on_eof`` under the engine's sorted-key EOF walk, src/operators.rs:862-894)."""
@@ -651,6 +677,10 @@ class _Run:
                         except Exception as ex:
                             _reraise(f"error in the CUDA fold of step {st.step_id}", ex)
                     if g is not None:
+                        try:
+                            self._emit(st.down, w, epoch, g.on_notify())
+                        except Exception as ex:
+                            _reraise(f"error in the CUDA fold of step {st.step_id}", ex)
                         continue
                 if items:
                     self._host_on_batch(st, S, w, epoch, items)

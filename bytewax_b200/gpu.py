@@ -251,11 +251,16 @@ class WindowFold:
             arr(e.late_ts_us, nl, np.int64), arr(e.late_epoch, nl, np.uint64),
         )
 
-    def advance(self, copy: bool = True) -> Emitted:
+    def set_system_now(self, now_us: int):
+        """System time of the activations ingested from now on (``bw_fold_set_system_now``; never set: frozen clock)."""
+        N.check(self.lib.bw_fold_set_system_now(self.h, int(now_us)), self.ctx.h)
+
+    def advance(self, copy: bool = True, system_now_us: int = 0) -> Emitted:
         """Rows emitted since the last call.  ``copy=False`` returns views of the library's pinned
-        output buffers (the C ABI's own contract: valid until the next ``advance``/``eof``)."""
+        output buffers (the C ABI's own contract: valid until the next ``advance``/``eof``).
+        ``system_now_us`` > 0 also runs the notify phase at that system time (idle keys' windows close)."""
         e = N.BwEmit()
-        N.check(self.lib.bw_advance(self.h, 0, 0, C.byref(e)), self.ctx.h)
+        N.check(self.lib.bw_advance(self.h, 0, int(system_now_us), C.byref(e)), self.ctx.h)
         return self._wrap(e, copy)
 
     def eof(self, copy: bool = True) -> Emitted:

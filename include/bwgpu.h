@@ -237,10 +237,19 @@ bw_status bw_ingest_commit(bw_fold* fold, const bw_batch* batch, uint64_t rows, 
 bw_status bw_ingest_device(bw_fold* fold, const uint64_t* d_keys, const void* d_vals,
                            const int64_t* d_ts_us, uint64_t rows, uint64_t epoch);
 
+/* System time of the activations committed from now on (`now_getter()` sampled by `before_batch`, windowing.py:250-261;
+ * microseconds since the Unix epoch, never goes backwards).  The EventClock's watermark of a key is
+ *   max_j(ts_j - wait - now_j) + now      (windowing.py:263-287: watermark_base + (now - system_time_of_max_event))
+ * so an item is late, and a window closes, against a watermark that also drifts forward with the system clock.
+ * Never called: the frozen clock (now == 0 throughout), the watermark is max(ts) - wait.  One rank only. */
+bw_status bw_fold_set_system_now(bw_fold* fold, int64_t system_now_us);
+
 /* Wait for every committed activation and return what they emitted.
- * `closed_epoch` / `system_now_us` are accepted for the reference's notify
- * timers (src/operators.rs:810-858); with a data-driven EventClock they do not
- * change results and are currently ignored. */
+ * `system_now_us` > 0 additionally runs the reference's notify phase (src/operators.rs:808-858) at that system time:
+ * every key whose earliest open window's close time has been reached by the system clock (`notify_at`,
+ * windowing.py:656-659, 1146-1173) closes what its watermark now allows (`on_notify`, windowing.py:1137-1144) -- an
+ * idle key's windows no longer wait for EOF.  0: data-driven only (frozen clock).  `closed_epoch` is accepted and
+ * unused (epochs are closed by the order of the commits). */
 bw_status bw_advance(bw_fold* fold, uint64_t closed_epoch, int64_t system_now_us, bw_emit* out);
 
 /* End of input: watermark := UTC_MAX, every open window closes (ascending key

@@ -46,7 +46,7 @@ def us(d: datetime) -> int:
     return (delta.days * 86400 + delta.seconds) * 1_000_000 + delta.microseconds
 
 
-def build_logic_builder(spec):
+def build_logic_builder(spec, now_getter=None):
     """Return the reference ``stateful_batch`` builder for this spec.
 
     Items are ``(key_str, value, ts_us)``.
@@ -54,7 +54,7 @@ def build_logic_builder(spec):
     clock = win.EventClock(
         lambda x: dt(x[2]),
         wait_for_system_duration=timedelta(microseconds=spec["wait_us"]),
-        now_getter=lambda: NOW,
+        now_getter=now_getter or (lambda: NOW),
     )
     offset = spec["offset_us"] or spec["length_us"]
     windower = win.SlidingWindower(
@@ -342,6 +342,118 @@ def main():
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
+def run_reference_timed(spec, steps):
+    """Moving system clock.  ``steps``: ``["batch", now_us, keys, ts, vals]`` -- one activation's on_batch phase with
+    ``now_getter() == now_us`` -- or ``["notify", now_us]`` -- the notify phase (src/operators.rs:808-858): every key whose
+    ``notify_at()`` <= now gets ``on_notify()``, ascending key-string order.  Returns the rows of every step + EOF."""
+    now = [dt(steps[0][1])]
+    builder, unwrap = build_logic_builder(spec, now_getter=lambda: now[0])
+    logics, sched, acts = {}, {}, []
+
+    def conv(k, events):
+        rows = []
+        for wid, tag, payload in events:
+            if tag == "E":
+                rows.append([int(k), wid, "E", unwrap(payload)])
+            elif tag == "L":
+                rows.append([int(k), wid, "L", payload[1]])
+            else:
+                rows.append([int(k), wid, "M", [us(payload.open_time), us(payload.close_time)]])
+        return rows
+
+    def resched(ks, logic, done):
+        if done:
+            del logics[ks]
+            sched.pop(ks, None)
+            return
+        at = logic.notify_at()
+        if at is None:
+            sched.pop(ks, None)
+        else:
+            sched[ks] = at
+
+    for step in steps:
+        now[0] = dt(step[1])
+        rows = []
+        if step[0] == "batch":
+            _kind, _now, keys, ts, vals = step
+            grouped = {}
+            for k, t, v in zip(keys, ts, vals):
+                grouped.setdefault(str(k), []).append((str(k), v, t))
+            for ks in sorted(grouped):
+                logic = logics.get(ks)
+                if logic is None:
+                    logic = logics[ks] = builder(None)
+                events, done = logic.on_batch(grouped[ks])
+                rows.extend(conv(ks, list(events)))
+                resched(ks, logic, done)
+        else:
+            for ks in sorted(k for k, at in sched.items() if at <= now[0]):
+                logic = logics[ks]
+                events, done = logic.on_notify()
+                rows.extend(conv(ks, list(events)))
+                resched(ks, logic, done)
+        acts.append(rows)
+    rows = []
+    for ks in sorted(logics):
+        events, done = logics[ks].on_eof()
+        rows.extend(conv(ks, list(events)))
+    acts.append(rows)
+    return acts
+
+
+def main_timed():
+    """tests/golden/system_time_cases.json: `_WindowLogic` + `_EventClockLogic` under a MOVING system clock, by the
+    reference's own classes (windowing.py:263-302 watermark drift, :1135-1180 on_notify / notify_at)."""
+    S = 1_000_000
+    cases = {}
+
+    def add(name, spec, steps, cite=None):
+        cases[name] = dict(spec=spec, steps=steps, acts=run_reference_timed(spec, steps), cite=cite)
+
+    A = ALIGN_US
+    # an idle key's window closes once the system clock has carried the watermark past it
+    add("idle_key_closes_on_notify", spec_("count", 10 * S),
+        [["batch", A + 2 * S, [1, 1, 2], [A + 1 * S, A + int(1.5 * S), A + 1 * S], [1, 1, 1]],
+         ["notify", A + 5 * S], ["notify", A + 11 * S], ["notify", A + 30 * S]],
+        cite="windowing.py:289-298 on_notify; pytests/operators/windowing/test_event_clock.py")
+    # the watermark drifts with the system clock: after 20 idle seconds an item 1 s newer than the key's maximum is late
+    add("drift_makes_item_late", spec_("sum", 10 * S, wait_us=2 * S),
+        [["batch", A + 1 * S, [7, 8], [A + 1 * S, A + 1 * S], [5, 6]],
+         ["batch", A + 21 * S, [7], [A + 2 * S], [100]],
+         ["batch", A + 22 * S, [8], [A + 25 * S], [7]],
+         ["notify", A + 40 * S]],
+        cite="windowing.py:263-287")
+    # the wait holds the watermark back; due keys (close <= now) whose watermark has not got there yet emit nothing
+    add("due_but_watermark_behind", spec_("count", 10 * S, wait_us=5 * S),
+        [["batch", A + 9 * S, [3, 4], [A + 8 * S, A + 2 * S], [1, 1]],
+         ["notify", A + 12 * S], ["notify", A + 14 * S], ["notify", A + 16 * S]])
+    # sliding windows close one by one as the clock advances
+    add("sliding_closes_stepwise", spec_("sum", 10 * S, offset_us=5 * S),
+        [["batch", A + 8 * S, [1, 1, 2], [A + 3 * S, A + 7 * S, A + 6 * S], [1, 2, 4]],
+         ["notify", A + 11 * S], ["notify", A + 16 * S], ["batch", A + 17 * S, [1], [A + 16 * S], [8]], ["notify", A + 40 * S]])
+    for seed, (red, length, offset, wait, ordered) in enumerate([
+            ("count", 10, None, 0, False), ("sum", 10, 5, 2, False), ("max", 7, None, 3, False), ("min", 10, 5, 0, False),
+            ("count", 10, 3, 2, True), ("sum", 6, None, 1, False)]):
+        rnd = random.Random(4000 + seed)
+        now, steps = A + rnd.randint(0, 3 * S), []
+        for _ in range(40):
+            now += rnd.randint(0, 4 * S) if rnd.random() < 0.8 else rnd.randint(8 * S, 25 * S)
+            if rnd.random() < 0.65:
+                n = rnd.randint(1, 12)
+                keys = [rnd.randint(1, 5) for _ in range(n)]
+                ts = [now - rnd.randint(0, 6 * S) if rnd.random() < 0.9 else now - rnd.randint(10 * S, 40 * S) for _ in range(n)]
+                steps.append(["batch", now, keys, ts, [rnd.randint(-9, 9) for _ in range(n)]])
+            else:
+                steps.append(["notify", now])
+        add(f"random_clock_{red}_{seed}", spec_(red, length * S, offset * S if offset else None, wait * S, ordered), steps)
+    out_dir = os.path.join(os.path.dirname(HERE), "tests", "golden")
+    path = os.path.join(out_dir, "system_time_cases.json")
+    with open(path, "w") as f:
+        json.dump(cases, f, separators=(",", ":"))
+    print("wrote", path, os.path.getsize(path), "bytes,", len(cases), "cases")
+
+
 def main_keyed():
     """Goldens for config C2 (the reference example's own mapper) and C4 (the reference's `_JoinLogic`)."""
     src = open("/root/reference/examples/anomaly_detector.py").read()
@@ -388,3 +500,4 @@ def main_keyed():
 if __name__ == "__main__":
     main()
     main_keyed()
+    main_timed()

@@ -245,6 +245,22 @@ class WindowLogic:
         events.extend(self._flush(watermark))
         return events, self.is_empty()
 
+    def on_notify(self) -> Tuple[List[Tuple[int, str, Any]], bool]:
+        # windowing.py:1135-1142
+        watermark = self.clock.on_notify()
+        assert watermark >= self.last_watermark
+        self.last_watermark = watermark
+        return self._flush(watermark), self.is_empty()
+
+    def notify_at(self) -> Optional[int]:
+        # windowing.py:1153-1180 with `to_system_utc` == identity (the EventClock default, windowing.py:407):
+        # the earliest close time of an opened window; in ordered mode also the head of the queue
+        at = min((meta[1] for meta in self.windower.opened.values()), default=None)
+        if self.ordered and self.queue:
+            q = self.queue[0][1]
+            at = q if at is None else min(at, q)
+        return at
+
     def on_eof(self) -> Tuple[List[Tuple[int, str, Any]], bool]:
         # windowing.py:1144-1151
         watermark = self.clock.on_eof()
@@ -294,11 +310,42 @@ class StatefulBatchEngine:
         self.spec = spec
         self.logics: Dict[str, WindowLogic] = {}
         self._keys: Dict[str, int] = {}
+        self.now_us = spec.now_us
+        self.sched: Dict[str, int] = {}  # key -> system time of its next notification (src/operators.rs:645-650)
+
+    def set_now(self, now_us: int) -> None:
+        """What ``now_getter()`` returns from here on (every logic samples it in ``before_batch`` / ``on_notify``)."""
+        self.now_us = now_us
+        for logic in self.logics.values():
+            logic.clock.now_us = now_us
+
+    def on_notify(self, now_us: int):
+        """The notify phase at system time ``now_us`` (src/operators.rs:808-858): every key whose scheduled time has come,
+        in ascending key-string order."""
+        self.set_now(now_us)
+        out = []
+        for ks in sorted(k for k, at in self.sched.items() if at <= now_us):
+            logic = self.logics[ks]
+            events, done = logic.on_notify()
+            out.extend((self._keys[ks], wid, tag, payload) for wid, tag, payload in events)
+            self._resched(ks, logic, done)
+        return out
+
+    def _resched(self, ks: str, logic, done: bool) -> None:
+        if done:
+            del self.logics[ks]  # src/operators.rs:796-799
+            self.sched.pop(ks, None)
+            return
+        at = logic.notify_at()
+        if at is None:
+            self.sched.pop(ks, None)
+        else:
+            self.sched[ks] = at
 
     def _build(self) -> WindowLogic:
         s = self.spec
         return WindowLogic(
-            EventClock(s.wait_us, s.now_us),
+            EventClock(s.wait_us, self.now_us),
             SlidingWindower(s.length_us, s.offset_us, s.align_us),
             s.reduction,
             s.ordered,
@@ -320,8 +367,7 @@ class StatefulBatchEngine:
             events, done = logic.on_batch(grouped[ks])
             k = self._keys[ks]
             out.extend((k, wid, tag, payload) for wid, tag, payload in events)
-            if done:
-                del self.logics[ks]  # src/operators.rs:796-799
+            self._resched(ks, logic, done)
         return out
 
     def on_eof(self):

@@ -261,3 +261,43 @@ def test_join_runs_on_k6(insert_mode, emit_mode):
     assert made == ["_GpuJoinStep"]
     assert len(gpu) > 0
     assert gpu == host
+
+
+def _moving_clock_flow(gpu):
+    S = timedelta(seconds=1)
+    now_box = [ALIGN]
+    # (key, event time, system time of arrival, value)
+    raw = [("a", 1.0, 2.0, 5), ("a", 1.5, 2.0, 6), ("b", 1.8, 2.5, 1), ("c", 9.5, 9.6, 1), ("c", 11.0, 10.0, 2),
+           ("z", 12.0, 13.0, 100), ("z", 14.0, 15.0, 200),
+           ("a", 3.0, 16.0, 7),   # a's logic was discarded when its window closed: accepted again (a fresh watermark)
+           ("c", 12.0, 16.5, 4),  # c's window 1 is still open; maximum 11 seen at system time 10 -> watermark 17.5: LATE by drift alone
+           ("z", 27.0, 27.5, 300), ("b", 26.0, 28.0, 2)]
+    items = [(k, (ALIGN + ev * S, ALIGN + sy * S, v)) for k, ev, sy, v in raw]
+
+    def tick(kv):
+        now_box[0] = kv[1][1]  # the system clock reads the item's arrival time from here on
+        return kv
+
+    out, late = [], []
+    flow = Dataflow("test_df")
+    s = op.input("inp", flow, TestingSource(items, batch_size=1))
+    s = op.map("tick", s, tick)
+    clock = EventClock(lambda e: e[0], ZERO_TD, now_getter=lambda: now_box[0])
+    windower = TumblingWindower(timedelta(seconds=10), ALIGN)
+    wo = win.fold_window("sum", s, clock, windower, lambda: 0, lambda a, e: a + e[2], operator.add, ordered=False,
+                         _gpu_plan=win.GpuFoldPlan("sum", clock, windower, False, lambda e: e[2]))
+    op.output("out", wo.down, TestingSink(out))
+    # (the CUDA path's late stream carries the numeric projection of the value, the host's the item itself)
+    op.output("late", op.map_value("lv", wo.late, lambda wv: (wv[0], wv[1][2] if isinstance(wv[1], tuple) else wv[1])), TestingSink(late))
+    run_main(flow, gpu=gpu)
+    return out, late
+
+
+def test_idle_key_closes_when_the_system_clock_moves():
+    """EventClock with a moving `now_getter`: the watermark drifts with the system clock (windowing.py:263-302) and the
+    notify phase closes an idle key's window before EOF (src/operators.rs:808-858) -- on the CUDA path as on the host."""
+    host = _moving_clock_flow(False)
+    # window 0 of a, b and c closes while only z is receiving items; c's last item is late although it is its key's newest
+    assert host[0][:3] == [("c", (0, 1)), ("a", (0, 11)), ("b", (0, 1))], host[0]
+    assert host[1] == [("c", (1, 4))], host[1]
+    assert _moving_clock_flow(True) == host

@@ -89,6 +89,31 @@ def test_golden_cases_per_activation(ctx, golden_dir):
         fold.close()
 
 
+def test_moving_system_clock_per_step(ctx, golden_dir):
+    """`bw_fold_set_system_now` + the notify phase of `bw_advance(system_now_us)` against rows the reference's own
+    `_WindowLogic` / `_EventClockLogic` produced under a stepping `now_getter` (tests/golden/system_time_cases.json):
+    the watermark drifts with the system clock (an item can be late because time passed), idle keys' windows close."""
+    with open(os.path.join(golden_dir, "system_time_cases.json")) as f:
+        cases = json.load(f)
+    woke = 0
+    for name, case in cases.items():
+        s = case["spec"]
+        fold = _make_fold(ctx, s, False)
+        for i, step in enumerate(case["steps"]):
+            if step[0] == "batch":
+                _kind, now, keys, ts, vals = step
+                fold.set_system_now(now)
+                fold.ingest(keys, vals, ts)
+                em = fold.advance()
+            else:
+                em = fold.advance(system_now_us=step[1])
+                woke += len(em.closed_key)
+            _check_activation(fold, em, case["acts"][i], s, False, (name, i, step[0]))
+        _check_activation(fold, fold.eof(), case["acts"][-1], s, False, (name, "eof"))
+        fold.close()
+    assert woke > 20
+
+
 def test_golden_cases_single_advance(ctx, golden_dir):
     """All activations committed back to back, rows collected once: same rows, grouped by epoch."""
     with open(os.path.join(golden_dir, "window_fold_cases.json")) as f:

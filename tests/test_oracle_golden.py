@@ -189,3 +189,41 @@ def test_keyed_oracles_match_reference_goldens(golden_dir):
         items = case["items"]
         acts = po.run_join([([k], [s], [v]) for k, s, v in items], case["insert_mode"], case["emit_mode"])
         assert [list(r) for a in acts for r in a] == case["rows"], (case["insert_mode"], case["emit_mode"])
+
+
+def run_timed(spec, steps):
+    """`steps` of tests/golden/system_time_cases.json through the oracle engine: a moving system clock."""
+    eng = po.StatefulBatchEngine(spec)
+    acts = []
+    for step in steps:
+        if step[0] == "batch":
+            _kind, now, keys, ts, vals = step
+            eng.set_now(now)
+            acts.append(eng.on_batch(keys, ts, vals))
+        else:
+            acts.append(eng.on_notify(step[1]))
+    acts.append(eng.on_eof())
+    return acts
+
+
+def test_moving_system_clock_matches_reference_logic(golden_dir):
+    """Watermark drift with the system clock (windowing.py:263-302) and the notify phase (windowing.py:1135-1180,
+    src/operators.rs:808-858), against rows produced by the reference's own classes under a stepping `now_getter`."""
+    cases = _load(golden_dir, "system_time_cases.json")
+    assert len(cases) >= 10
+    notified = 0
+    for name, case in cases.items():
+        s = case["spec"]
+        spec = po.FoldSpec(s["reduction"], s["length_us"], s["offset_us"], s["align_us"], s["wait_us"], s["ordered"], now_us=case["steps"][0][1])
+        acts = run_timed(spec, case["steps"])
+        assert len(acts) == len(case["acts"]), name
+        for i, (got, want) in enumerate(zip(acts, case["acts"])):
+            assert _norm(got) == want, f"{name} step {i}"
+            if i < len(case["steps"]) and case["steps"][i][0] == "notify":
+                notified += sum(1 for r in want if r[2] == "E")
+    assert notified > 20  # windows that closed because the clock moved, not because an item arrived
+    # the idle key: nothing at now = align + 5 s, both keys' window 0 at align + 11 s
+    c = cases["idle_key_closes_on_notify"]["acts"]
+    assert c[1] == [] and [r[:3] for r in c[2] if r[2] == "E"] == [[1, 0, "E"], [2, 0, "E"]]
+    # 20 idle seconds carried the watermark past the item that is only 1 s newer than the key's maximum
+    assert [r for r in cases["drift_makes_item_late"]["acts"][1] if r[2] == "L"] == [[7, 0, "L", 100]]
