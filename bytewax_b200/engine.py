@@ -109,7 +109,7 @@ class _GpuWindowStep:
         length = w.length
         offset = w.offset if isinstance(w, SlidingWindower) else w.length
         td_us = lambda td: (td.days * 86400 + td.seconds) * 1_000_000 + td.microseconds  # noqa: E731
-        wait = plan.clock.wait_for_system_duration
+        wait = getattr(plan.clock, "wait_for_system_duration", timedelta(0))  # (SystemClock: the watermark IS the system time)
         wait_us = None if wait >= timedelta(days=365 * 200) else td_us(wait)
         self.float_vals = False
         self.fold = None
@@ -151,7 +151,10 @@ class _GpuWindowStep:
             t = np.concatenate([c[1].ts_us for c in cols]).astype(np.int64)
             v = None if cols[0][1].vals is None else np.concatenate([c[1].vals for c in cols])
         else:
-            getter = plan.clock.ts_getter
+            getter = getattr(plan.clock, "ts_getter", None)
+            if getter is None:  # SystemClock (windowing.py:196-222): an item's timestamp is the system time of its batch
+                now_dt = _dt(self._now_us())
+                getter = lambda _v: now_dt  # noqa: E731
             for item in items:
                 try:
                     key, value = item
@@ -184,6 +187,10 @@ class _GpuWindowStep:
         return self._rows(self.fold.advance(), orig)
 
     def _now_us(self):
+        from bytewax_b200.operators import windowing as W
+
+        if isinstance(self.plan.clock, W.SystemClock):
+            return _us(W._get_system_utc())
         getter = getattr(self.plan.clock, "now_getter", None)
         return None if getter is None else _us(getter())
 

@@ -586,7 +586,8 @@ def fold_window(step_id: str, up: KeyedStream, clock: Clock, windower: Windower,
 
 
 def _plan_for(reduction: str, clock, windower, ordered, value_of=_identity) -> Optional[GpuFoldPlan]:
-    if isinstance(clock, EventClock) and isinstance(windower, (SlidingWindower, TumblingWindower)):
+    # (SystemClock == an event clock whose timestamps are the arrival times, wait 0: every item is at the watermark)
+    if isinstance(clock, (EventClock, SystemClock)) and isinstance(windower, (SlidingWindower, TumblingWindower)):
         return GpuFoldPlan(reduction, clock, windower, ordered, value_of)
     return None
 

@@ -301,3 +301,31 @@ def test_idle_key_closes_when_the_system_clock_moves():
     assert host[0][:3] == [("c", (0, 1)), ("a", (0, 11)), ("b", (0, 1))], host[0]
     assert host[1] == [("c", (1, 4))], host[1]
     assert _moving_clock_flow(True) == host
+
+
+def test_system_clock_windows_on_gpu(monkeypatch):
+    """SystemClock (windowing.py:190-222): timestamp == watermark == system time.  On the CUDA path it is an event clock
+    whose timestamps are the arrival times with wait 0, windows closing as the system clock passes them (notify phase)."""
+    S = timedelta(seconds=1)
+    now_box = [ALIGN]
+    monkeypatch.setattr(win, "_get_system_utc", lambda: now_box[0])
+    raw = [("a", 1.0, 1), ("b", 2.0, 1), ("a", 3.0, 1), ("z", 12.0, 1), ("a", 14.0, 1), ("z", 31.0, 1), ("b", 33.0, 1)]
+    items = [(k, (ALIGN + sy * S, v)) for k, sy, v in raw]
+
+    def tick(kv):
+        now_box[0] = kv[1][0]
+        return kv
+
+    outs = []
+    for gpu in (False, True):
+        now_box[0] = ALIGN
+        out = []
+        flow = Dataflow("test_df")
+        s = op.input("inp", flow, TestingSource(items, batch_size=1))
+        s = op.map("tick", s, tick)
+        wo = win.count_window("cnt", s, win.SystemClock(), TumblingWindower(timedelta(seconds=10), ALIGN), lambda kv: kv[0])
+        op.output("out", wo.down, TestingSink(out))
+        run_main(flow, gpu=gpu)
+        outs.append(out)
+    assert outs[0][:2] == [("a", (0, 2)), ("b", (0, 1))]  # closed when the clock read 12 s, long before EOF
+    assert outs[1] == outs[0]
