@@ -227,7 +227,21 @@ class _GpuWindowStep:
                 setattr(self, name, None)
 
     def _rows(self, em, orig) -> list:
-        from bytewax_b200.operators.windowing import WindowMetadata
+        from bytewax_b200.operators.windowing import WindowColumns, WindowMetadata
+
+        if getattr(self.plan, "columns_out", False) and not self.resort:
+            # one item per stream and activation: the library's rows as columns, already in the reference's order
+            out = []
+            if len(em.late_key):
+                out.append(("cols", WindowColumns("L", em.late_key, em.late_window_id, em.late_val)))
+            if len(em.closed_key):
+                np = self.np
+                w = em.closed_window_id
+                o, c = self.fold.window_bounds(0)
+                off = self.fold.window_bounds(1)[0] - o
+                out.append(("cols", WindowColumns("E", em.closed_key, w, em.closed_acc)))
+                out.append(("cols", WindowColumns("M", em.closed_key, w, None, o + w.astype(np.int64) * off, c + w.astype(np.int64) * off)))
+            return out
 
         lates = []
         for k, w, val, ep in zip(em.late_key.tolist(), em.late_window_id.tolist(), em.late_val.tolist(), em.late_epoch.tolist()):
@@ -642,8 +656,17 @@ class _Run:
         for _w, chunks in enumerate(self._take(st.up)):
             for epoch, items in chunks:
                 for item in items:
-                    if plan is not None and isinstance(item, tuple) and len(item) == 2 and isinstance(item[1], KeyedColumns):
-                        routed[0][epoch].append(item)
+                    if isinstance(item, tuple) and len(item) == 2 and isinstance(item[1], KeyedColumns):
+                        if plan is not None:
+                            routed[0][epoch].append(item)
+                        else:
+                            # no CUDA path: the rows of the batch as the items the host logic of `fold_columns` folds,
+                            # `(str(key), (ts_us, value))`, routed like any other keyed item
+                            c = item[1]
+                            vals = c.vals.tolist() if c.vals is not None else [1] * len(c)
+                            for k, t, v in zip(c.keys.tolist(), c.ts_us.tolist(), vals):
+                                ks = str(int(k))
+                                routed[_route(ks, self.W)][epoch].append((ks, (int(t), v)))
                         continue
                     try:
                         key, _value = item

@@ -508,8 +508,38 @@ class WindowOut(Generic[V, W]):
 
 
 def _unwrap(tag: str, ev):
+    if isinstance(ev, WindowColumns):  # columnar egress of `fold_columns` (the CUDA path): a whole stream's rows at once
+        return ev if ev.tag == tag else None
     wid, typ, obj = ev
     return (wid, obj) if typ == tag else None
+
+
+@dataclass
+class WindowColumns:
+    """One activation's rows of one output stream of `fold_columns(..., columns_out=True)` as numpy columns instead of
+    one Python tuple per row.  ``tag``: "E" closed windows (``values`` = accumulators), "L" late items (``values`` = the
+    late values), "M" metadata (``open_us`` / ``close_us``).  Item keys are ``str(key)``; ``rows()`` gives the tuples the
+    per-item streams would carry, in the same order."""
+
+    tag: str
+    keys: Any
+    window_ids: Any
+    values: Any = None
+    open_us: Any = None
+    close_us: Any = None
+
+    def __len__(self):
+        return len(self.keys)
+
+    def rows(self) -> list:
+        ks, ws = [str(int(k)) for k in self.keys], [int(w) for w in self.window_ids]
+        if self.tag == "M":
+            return [(k, (w, WindowMetadata(_COL_EPOCH + timedelta(microseconds=int(o)), _COL_EPOCH + timedelta(microseconds=int(c)))))
+                    for k, w, o, c in zip(ks, ws, self.open_us, self.close_us)]
+        return [(k, (w, v)) for k, w, v in zip(ks, ws, self.values.tolist())]
+
+
+_COL_EPOCH = datetime(1970, 1, 1, tzinfo=timezone.utc)
 
 
 @dataclass(frozen=True)
@@ -525,6 +555,7 @@ class GpuFoldPlan:
     windower: Any
     ordered: bool
     value_of: Callable[[Any], Any]  # item value -> number folded
+    columns_out: bool = False       # emit WindowColumns items instead of one tuple per row (`fold_columns`)
 
 
 @operator
@@ -590,6 +621,38 @@ def _plan_for(reduction: str, clock, windower, ordered, value_of=_identity) -> O
     if isinstance(clock, (EventClock, SystemClock)) and isinstance(windower, (SlidingWindower, TumblingWindower)):
         return GpuFoldPlan(reduction, clock, windower, ordered, value_of)
     return None
+
+
+_COLUMN_FOLDS = {
+    # reduction -> (builder, folder over (ts_us, value) items, merger)
+    "count": (lambda: 0, lambda a, _v: a + 1, _pyop.add),
+    "sum": (lambda: None, lambda a, v: v[1] if a is None else a + v[1], _pyop.add),
+    "min": (lambda: None, lambda a, v: v[1] if a is None else min(a, v[1]), min),
+    "max": (lambda: None, lambda a, v: v[1] if a is None else max(a, v[1]), max),
+}
+
+
+@operator
+def fold_columns(step_id: str, up: Stream, reduction: str, windower: Windower, wait: timedelta = ZERO_TD, ordered: bool = False,
+                 columns_out: bool = False, now_getter: Optional[Callable[[], datetime]] = None) -> WindowOut:
+    """Windowed ``count`` / ``sum`` / ``min`` / ``max`` by key over a stream of `bytewax_b200.inputs.KeyedColumns` items (this
+    package's columnar ingest contract): every item is a whole batch -- ``keys`` (uint64; the item key is
+    ``str(key)``), ``ts_us`` (event time), ``vals`` -- and becomes ONE activation of the CUDA fold, with no Python object per row.
+    Same semantics as ``count_window`` / ``reduce_window`` over the rows ``(str(key), value)`` with an `EventClock` on ``ts_us``:
+    without the CUDA path the engine expands the columns into exactly those items and runs the host logic.
+
+    ``columns_out=True``: on the CUDA path the three output streams carry one `WindowColumns` item per activation (numpy columns;
+    ``.rows()`` gives the tuples) instead of one tuple per row."""
+    if reduction not in _COLUMN_FOLDS:
+        raise ValueError(f"unknown reduction {reduction!r}; one of {sorted(_COLUMN_FOLDS)}")
+    if not isinstance(windower, (SlidingWindower, TumblingWindower)):
+        raise TypeError("fold_columns needs a SlidingWindower or TumblingWindower")
+    kw = {} if now_getter is None else {"now_getter": now_getter}
+    clock = EventClock(lambda v: _COL_EPOCH + timedelta(microseconds=int(v[0])), wait, **kw)
+    builder, folder, merger = _COLUMN_FOLDS[reduction]
+    keyed = op.key_on("batch", up, lambda _cols: "cols")  # (key, KeyedColumns): the stateful step takes it from here
+    plan = GpuFoldPlan(reduction, clock, windower, ordered, lambda v: v[1], columns_out)
+    return fold_window("fold", keyed, clock, windower, builder, folder, merger, ordered=ordered, _gpu_plan=plan)
 
 
 @operator

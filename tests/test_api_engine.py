@@ -393,3 +393,47 @@ def test_declared_detector_and_two_sided_join_carry_a_gpu_plan():
         assert any(isinstance(p, bop.GpuJoinPlan) for p in plans)
     # three sides / product: no device plan
     assert bop.GpuJoinPlan("last", "complete") == bop.GpuJoinPlan("last", "complete")
+
+
+def test_fold_columns_host_path_equals_the_per_item_operators():
+    """`fold_columns` over KeyedColumns batches without the CUDA path: the engine expands the columns into `(str(key), (ts_us,
+    value))` items; rows equal `count_window` / `reduce_window` over the same rows."""
+    import numpy as np
+
+    import bytewax_b200.operators as bop
+    import bytewax_b200.operators.windowing as bwin
+    from bytewax_b200.dataflow import Dataflow as DF
+    from bytewax_b200.inputs import KeyedColumns
+    from bytewax_b200.testing import TestingSink as Sink, TestingSource as Src, run_main as run
+
+    align = datetime(2022, 1, 1, tzinfo=timezone.utc)
+    a_us = 1_640_995_200_000_000
+    n, batches, items = 1500, [], []
+    for b in range(3):
+        i = np.arange(b * n, (b + 1) * n)
+        keys, ts, vals = (i * 2654435761 % 37).astype(np.uint64), (a_us + i * 9_000).astype(np.int64), (i % 11 - 3).astype(np.int64)
+        batches.append(KeyedColumns(keys=keys, ts_us=ts, vals=vals))
+        items.extend((str(int(k)), (align + timedelta(microseconds=int(t - a_us)), int(v))) for k, t, v in zip(keys, ts, vals))
+    windower = bwin.SlidingWindower(timedelta(seconds=10), timedelta(seconds=5), align)
+    for red, ref in (("count", None), ("sum", lambda a, b: (b[0], a[1] + b[1])), ("max", None)):
+        got, want = [], []
+        flow = DF("cols")
+        wo = bwin.fold_columns("f", bop.input("inp", flow, Src(batches)), red, windower, now_getter=lambda: align)
+        bop.output("o", wo.down, Sink(got))
+        run(flow)
+        flow = DF("items")
+        s = bop.input("inp", flow, Src(items, batch_size=n))
+        clock = bwin.EventClock(lambda v: v[0], timedelta(0), now_getter=lambda: align)
+        if red == "count":
+            wo = bwin.fold_window("f", s, clock, windower, lambda: 0, lambda a, _v: a + 1, lambda a, b: a + b, ordered=False)
+            fix = lambda kv: kv  # noqa: E731
+        elif red == "sum":
+            wo = bwin.reduce_window("f", s, clock, windower, ref)
+            fix = lambda kv: (kv[0], (kv[1][0], kv[1][1][1]))  # noqa: E731
+        else:
+            wo = bwin.max_window("f", s, clock, windower, by=lambda v: v[1])
+            fix = lambda kv: (kv[0], (kv[1][0], kv[1][1][1]))  # noqa: E731
+        bop.output("o", wo.down, Sink(want))
+        run(flow)
+        assert got == [fix(kv) for kv in want], red
+        assert len(got) > 100

@@ -329,3 +329,45 @@ def test_system_clock_windows_on_gpu(monkeypatch):
         outs.append(out)
     assert outs[0][:2] == [("a", (0, 2)), ("b", (0, 1))]  # closed when the clock read 12 s, long before EOF
     assert outs[1] == outs[0]
+
+
+@pytest.mark.parametrize("red", ["count", "sum", "min"])
+def test_fold_columns_public_operator(red):
+    """`win.fold_columns`: KeyedColumns batches in, one activation each on the CUDA path, rows equal the host engine's
+    (which expands the columns into items); with `columns_out=True` the output streams carry WindowColumns."""
+    A_US = 1_640_995_200_000_000
+    n = 100_000
+    rnd = np.random.default_rng(17)
+    batches = []
+    for b in range(4):
+        i = np.arange(b * n, (b + 1) * n)
+        ts = A_US + i * 100 + rnd.integers(-3_000_000, 3_000_000, n)  # disorder beyond the 1 s wait: some rows are late
+        batches.append(KeyedColumns(keys=(i * 2654435761 % 3000).astype(np.uint64), ts_us=ts.astype(np.int64),
+                                    vals=None if red == "count" else rnd.integers(-50, 50, n).astype(np.int64)))
+
+    def build(columns_out):
+        out, late, meta = [], [], []
+        flow = Dataflow("df")
+        s = op.input("inp", flow, TestingSource(batches))
+        wo = win.fold_columns("fold", s, red, SlidingWindower(timedelta(seconds=10), timedelta(seconds=5), ALIGN), timedelta(seconds=1),
+                              columns_out=columns_out, now_getter=lambda: FROZEN)
+        op.output("out", wo.down, TestingSink(out))
+        op.output("late", wo.late, TestingSink(late))
+        op.output("meta", wo.meta, TestingSink(meta))
+        return flow, (out, late, meta)
+
+    flow, host = build(False)
+    run_main(flow, gpu=False)
+    flow, dev = build(False)
+    run_main(flow, gpu=True)
+    assert len(host[0]) > 1000 and len(host[1]) > 100
+    assert dev[0] == host[0] and dev[2] == host[2]
+    # the host's late stream carries the expanded item (ts_us, value), the device's the value (nothing for counts)
+    assert [(k, w) for k, (w, _v) in dev[1]] == [(k, w) for k, (w, _v) in host[1]]
+    if red != "count":
+        assert [v for _k, (_w, v) in dev[1]] == [v[1] for _k, (_w, v) in host[1]]
+    flow, cols = build(True)
+    run_main(flow, gpu=True)
+    assert all(isinstance(c, win.WindowColumns) for _k, c in cols[0]) and len(cols[0]) <= len(batches) + 1
+    assert [r for _k, c in cols[0] for r in c.rows()] == host[0]
+    assert [r for _k, c in cols[2] for r in c.rows()] == host[2]

@@ -60,3 +60,21 @@ for name, rs in agg.items():
     ag = 16.0 * rows_per_launch / (t * 1e-6) / 1e9 if (t and big) else None
     print(f"| `{name[:70]}` | {n} | {t:.1f} | {avg('rd')/1e6:.1f} | {avg('wr')/1e6:.1f} | {tg:.0f} ({tg/peak:.3f}) | "
           + (f"{ag:.0f} ({ag/peak:.3f})" if ag else "-") + f" | {avg('inst')/1e6:.2f} | {avg('issue'):.1f} | {avg('regs'):.0f} | {avg('warps'):.1f} |")
+
+# `--traffic out.json`: DRAM bytes per launch of the streaming / fold kernels, the file bench.py reads `roofline.traffic` from
+if "--traffic" in sys.argv:
+    out_path = sys.argv[sys.argv.index("--traffic") + 1]
+    traffic = {}
+    if os.path.exists(out_path):
+        try:
+            old = json.load(open(out_path))
+            traffic = {k: v for k, v in old.items() if isinstance(v, dict)}
+        except Exception:
+            traffic = {}
+    for name, rs in agg.items():
+        short = name.split("<")[0].strip()
+        if short in ("k_scatter", "k_segfold", "k_fold"):
+            n = len(rs)
+            traffic[short] = {"dram_bytes_per_launch": sum((val(r, "rd") or 0) + (val(r, "wr") or 0) for r in rs) / n,
+                              "launches_averaged": n, "source": os.path.basename(rep) + " (ncu --set full, cold cache)"}
+    json.dump(traffic, open(out_path, "w"), indent=1)
