@@ -15,4 +15,10 @@ timeout 300 $N -k regex:'k_part_|k_slow_' -s 6 -c 10 -o gpurun_out/prof_xchg_r2 
 # 6. K5 / K6
 timeout 200 $N -k regex:'k_smap_eval|k_smap_update|k_smap_slots|k_keyed_heads' -s 4 -c 4 -o gpurun_out/prof_smap_r2 python bench.py --config c2 --steps 2 --warmup 1 --batch-rows 1048576 > gpurun_out/ncu_smap.log 2>&1; tail -1 gpurun_out/ncu_smap.log
 timeout 200 $N -k regex:'k_join_apply|k_keyed_heads' -s 2 -c 3 -o gpurun_out/prof_join_r2 python bench.py --config c4 --steps 2 --warmup 1 --batch-rows 524288 > gpurun_out/ncu_join.log 2>&1; tail -1 gpurun_out/ncu_join.log
-ls -la gpurun_out/*.ncu-rep
+# what travels back (gpurun_out is capped at 64 MiB): the raw metric pages as CSV for every report, the full report of the
+# streaming kernels only (source view of the two kernels that matter)
+for r in stream late direct xchg smap join; do
+  ncu -i gpurun_out/prof_${r}_r2.ncu-rep --page raw --csv > gpurun_out/raw_${r}_r2.csv 2>/dev/null
+  [ $r != stream ] && rm -f gpurun_out/prof_${r}_r2.ncu-rep
+done
+ls -la gpurun_out/
