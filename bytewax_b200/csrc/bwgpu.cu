@@ -274,6 +274,27 @@ struct bw_fold {
   u64 sort_cap = 0;
   u64 *d_sk = nullptr, *d_sk2 = nullptr, *d_gather = nullptr;
   u32 *d_perm = nullptr, *d_perm2 = nullptr;
+  // Rows of CLOSED epochs are ordered and copied to the host while later activations run (side stream s_out, its own
+  // sort scratch): bw_advance then only has the newest rows left to do.  One rank, see flush_rows().
+  struct OutScratch {
+    u64 cap = 0;
+    u64 *sk = nullptr, *sk2 = nullptr, *gather = nullptr;
+    u32 *perm = nullptr, *perm2 = nullptr;
+    void* cub = nullptr;
+    size_t cub_bytes = 0;
+  } fl;
+  struct RowMark {
+    u64 epoch = 0, next_epoch = 0;  // next_epoch: 1 + epoch of the activation folded after this one (0: none yet)
+    cudaEvent_t ev = nullptr;       // the counts below are on the host once this has happened
+    bool live = false;
+  } marks[4];
+  unsigned long long* h_marks = nullptr;  // pinned [4][2]: n_closed, n_late after the marked activation
+  u32 mark_head = 0;                      // marks enqueued so far
+  u64 done_c = 0, done_l = 0;             // rows already ordered and on the host
+  cudaStream_t s_out = nullptr;
+  bool flush_on = true;                   // env BW_FLUSH=0: order and copy everything in bw_advance
+  bool host_ingest = false;               // the caller commits HOST batches (PCIe-bound: the device has time to spare between
+                                          // activations; a device-resident caller keeps every SM busy and is left alone)
   // host output (pinned, grown on demand)
   u64 hout_cap_c = 0, hout_cap_l = 0;
   u64 *ho_ckey = nullptr, *ho_cacc = nullptr, *ho_ccount = nullptr, *ho_cepoch = nullptr;
@@ -350,6 +371,8 @@ struct bw_fold {
 #define FAIL(f, code, ...) CTX_FAIL((f)->ctx, code, __VA_ARGS__)
 static bw_status ensure_sort_cap(bw_fold* f, u64 n);
 static bw_status grow_host(bw_fold* f, u64 nc, u64 nl);
+static bw_status mark_rows(bw_fold* f, u64 epoch);
+static bw_status flush_rows(bw_fold* f);
 
 // ---------------------------------------------------------------------------
 // small kernels
@@ -642,6 +665,7 @@ static bw_status stream_alloc(bw_fold* f) {
   CU(ctx, dmalloc(&sb.tile_bad, 2 * (size_t)sb.tiles_cap));
   CU(ctx, dmalloc(&sb.chunk_max, 2 * (size_t)sb.tiles_cap * BW_SC_WARPS));
   if (const char* e = getenv("BW_LATE_SPLIT")) f->late_split = atoi(e) != 0;
+  if (const char* e = getenv("BW_FLUSH")) f->flush_on = atoi(e) != 0;
   // Shared memory of the scatter: up to 8 records per bucket assembled before they are written out (counts only: the
   // value column is not staged), then as many TMA stages of the input tile (2..4) as still fit.
   const size_t smem_budget = 208 * 1024;
@@ -1030,6 +1054,16 @@ void bw_fold_destroy(bw_fold* f) {
     cudaEventDestroy(t.a);
     cudaEventDestroy(t.b);
   }
+  if (f->s_out) {
+    cudaStreamSynchronize(f->s_out);
+    cudaStreamDestroy(f->s_out);
+    void* q[] = {f->fl.sk, f->fl.sk2, f->fl.gather, f->fl.perm, f->fl.perm2, f->fl.cub};
+    for (void* x : q)
+      if (x) cudaFree(x);
+    for (auto& m : f->marks)
+      if (m.ev) cudaEventDestroy(m.ev);
+    if (f->h_marks) cudaFreeHost(f->h_marks);
+  }
   if (f->s_compute) cudaStreamDestroy(f->s_compute);
   if (f->s_copy) cudaStreamDestroy(f->s_copy);
   if (f->s_pre) cudaStreamDestroy(f->s_pre);
@@ -1406,6 +1440,9 @@ static bw_status legacy_batch(bw_fold* f, const u64* d_keys, const void* d_vals,
   if (ctx->world > 1) {
     CU(ctx, cudaEventRecord(f->ev_fold_done, f->s_compute));
     f->fold_recorded = true;
+  } else {
+    bw_status mst = mark_rows(f, ord);
+    if (mst != BW_OK) return mst;
   }
   if (stage) {
     CU(ctx, cudaEventRecord(stage->consumed, f->s_compute));
@@ -1731,6 +1768,7 @@ static bw_status stream_resolve(bw_fold* f) {
     }
     if (st == BW_OK) st = close_stage(f, d.ord, d.batch_no, sb.side[d.side].sv);
   }
+  if (st == BW_OK) st = mark_rows(f, d.ord);
   if (d.stage) {
     CU(ctx, cudaEventRecord(d.stage->consumed, s));
     d.stage->used = true;
@@ -1769,19 +1807,21 @@ static bw_status run_batch(bw_fold* f, const u64* d_keys, const void* d_vals, co
     d.batch_no = batch_no;
     d.lanes = lanes;
     d.stage = stage;
-    return BW_OK;
+    return flush_rows(f);
   }
   {  // activations fold in order
     bw_status st = stream_resolve(f);
     if (st != BW_OK) return st;
   }
-  return legacy_batch(f, d_keys, d_vals, d_ts, rows, batch_no, ord, stage);
+  bw_status st = legacy_batch(f, d_keys, d_vals, d_ts, rows, batch_no, ord, stage);
+  return st == BW_OK ? flush_rows(f) : st;
 }
 
 bw_status bw_ingest_commit(bw_fold* f, const bw_batch* batch, uint64_t rows, uint64_t epoch) {
   if (!f || !batch) return BW_ERR_SPEC;
   bw_ctx* ctx = f->ctx;
   if (f->eof_done) FAIL(f, BW_ERR_STATE, "commit after eof");
+  f->host_ingest = true;
   if (batch->slot >= f->slots.size() || !f->slots[batch->slot].acquired) FAIL(f, BW_ERR_STATE, "commit of a slot that is not acquired");
   if (rows > f->spec.max_batch_rows) FAIL(f, BW_ERR_SPEC, "commit: rows > max_batch_rows");
   CU(ctx, cudaSetDevice(ctx->device));
@@ -1914,11 +1954,16 @@ static bw_status ensure_sort_cap(bw_fold* f, u64 n) {
 
 // Build the reference-order permutation of n rows (LSD passes of stable radix sorts).
 static bw_status order_rows(bw_fold* f, u64 n, const u64* key, const u64* seq, const u64* epoch, const i64* wid,
-                            bool wid_pass, u64 n_ordinals) {
+                            bool wid_pass, u64 n_ordinals, bool side = false) {
   bw_ctx* ctx = f->ctx;
-  cudaStream_t s = f->s_compute;
+  cudaStream_t s = side ? f->s_out : f->s_compute;
+  // (the side stream sorts in its own scratch: the main one is shared with the sort path of not-clean activations)
+  u64 *&d_sk = side ? f->fl.sk : f->d_sk, *&d_sk2 = side ? f->fl.sk2 : f->d_sk2;
+  u32 *&d_perm = side ? f->fl.perm : f->d_perm, *&d_perm2 = side ? f->fl.perm2 : f->d_perm2;
+  void* d_cub = side ? f->fl.cub : f->d_cub;
+  const size_t cub_bytes = side ? f->fl.cub_bytes : f->cub_bytes;
   const int grid = ctx->sm_count * 4;
-  k_iota<<<grid, 256, 0, s>>>(f->d_perm, n);
+  k_iota<<<grid, 256, 0, s>>>(d_perm, n);
   f->st.kernel_launches++;
   struct Pass {
     int kind, bits;
@@ -1932,10 +1977,10 @@ static bw_status order_rows(bw_fold* f, u64 n, const u64* key, const u64* seq, c
   passes.push_back({BW_SK_ALIGNED, 64});
   if (n_ordinals > 1) passes.push_back({BW_SK_EPOCH, ebits});
   for (const Pass& ps : passes) {
-    k_sortkey<<<grid, 256, 0, s>>>(ps.kind, key, seq, epoch, wid, f->d_perm, f->d_sk, n, f->min_epoch);
-    size_t tb = f->cub_bytes;
-    CU(ctx, cub::DeviceRadixSort::SortPairs(f->d_cub, tb, f->d_sk, f->d_sk2, f->d_perm, f->d_perm2, (int)n, 0, ps.bits, s));
-    std::swap(f->d_perm, f->d_perm2);
+    k_sortkey<<<grid, 256, 0, s>>>(ps.kind, key, seq, epoch, wid, d_perm, d_sk, n, f->min_epoch);
+    size_t tb = cub_bytes;
+    CU(ctx, cub::DeviceRadixSort::SortPairs(d_cub, tb, d_sk, d_sk2, d_perm, d_perm2, (int)n, 0, ps.bits, s));
+    std::swap(d_perm, d_perm2);
     f->st.kernel_launches++;
   }
   CU(ctx, cudaGetLastError());
@@ -1979,11 +2024,127 @@ static const char* status_name(u32 s) {
   }
 }
 
+// Order rows [lo, hi) of the closed or late columns and copy them to the same positions of the host arrays.
+static bw_status ship_rows(bw_fold* f, bool late, u64 lo, u64 hi, bool side) {
+  bw_ctx* ctx = f->ctx;
+  if (hi <= lo) return BW_OK;
+  cudaStream_t s = side ? f->s_out : f->s_compute;
+  const u64 n = hi - lo;
+  const bool ordered = f->spec.emit_order == BW_ORDER_REFERENCE;
+  const int grid = ctx->sm_count * 4;
+  const u64 n_ord = f->have_pending ? (f->last_epoch - f->min_epoch + 1) : 1;
+  // the window-id pass orders a key's rows where the sequence column ties: sliding windows emitted from one
+  // pane, and folds whose sequence is just the closing activation (FoldParams::seq_by_id)
+  const bool sliding = f->p.panes_per_window > 1 || f->p.panes_per_offset > 1 || f->p.seq_by_id;
+  const EmitBufs& e = f->e;
+  if (ordered) {
+    if (side && n > f->fl.cap) {  // (grow the side scratch: nothing is in flight on it once the stream is idle)
+      CU(ctx, cudaStreamSynchronize(s));
+      void* old[] = {f->fl.sk, f->fl.sk2, f->fl.gather, f->fl.perm, f->fl.perm2, f->fl.cub};
+      for (void* q : old)
+        if (q) cudaFree(q);
+      const u64 cap = std::max<u64>(2 * n, 1 << 16);
+      CU(ctx, dmalloc(&f->fl.sk, cap));
+      CU(ctx, dmalloc(&f->fl.sk2, cap));
+      CU(ctx, dmalloc(&f->fl.gather, cap));
+      CU(ctx, dmalloc(&f->fl.perm, cap));
+      CU(ctx, dmalloc(&f->fl.perm2, cap));
+      size_t b = 0;
+      cub::DeviceRadixSort::SortPairs(nullptr, b, f->fl.sk, f->fl.sk2, f->fl.perm, f->fl.perm2, (int)cap, 0, 64, s);
+      f->fl.cub_bytes = b + 256;
+      CU(ctx, cudaMalloc(&f->fl.cub, f->fl.cub_bytes));
+      f->fl.cap = cap;
+    }
+    bw_status st;
+    if (!late) st = order_rows(f, n, e.c_key + lo, e.c_seq + lo, e.c_epoch + lo, e.c_wid + lo, sliding, n_ord, side);
+    else  // rows of one late item were reserved contiguously in ascending window id; stable sorts keep that
+      st = order_rows(f, n, e.l_key + lo, e.l_seq + lo, e.l_epoch + lo, e.l_wid + lo, false, n_ord, side);
+    if (st != BW_OK) return st;
+  }
+  const u32* perm = side ? f->fl.perm : f->d_perm;
+  u64* gather = side ? f->fl.gather : f->d_gather;
+  auto ship = [&](const u64* src, u64* dst) -> bw_status {
+    if (ordered) {
+      k_gather_u64<<<grid, 256, 0, s>>>(src + lo, perm, gather, n);
+      f->st.kernel_launches++;
+      CU(ctx, cudaMemcpyAsync(dst + lo, gather, n * 8, cudaMemcpyDeviceToHost, s));
+    } else {
+      CU(ctx, cudaMemcpyAsync(dst + lo, src + lo, n * 8, cudaMemcpyDeviceToHost, s));
+    }
+    return BW_OK;
+  };
+  bw_status st;
+  if (!late) {
+    if ((st = ship(e.c_key, f->ho_ckey))) return st;
+    if ((st = ship((const u64*)e.c_wid, (u64*)f->ho_cwid))) return st;
+    if ((st = ship(e.c_acc, f->ho_cacc))) return st;
+    if ((st = ship(e.c_count, f->ho_ccount))) return st;
+    if ((st = ship(e.c_epoch, f->ho_cepoch))) return st;
+  } else {
+    if ((st = ship(e.l_key, f->ho_lkey))) return st;
+    if ((st = ship((const u64*)e.l_wid, (u64*)f->ho_lwid))) return st;
+    if ((st = ship(e.l_val, f->ho_lval))) return st;
+    if ((st = ship((const u64*)e.l_ts, (u64*)f->ho_lts))) return st;
+    if ((st = ship(e.l_epoch, f->ho_lepoch))) return st;
+  }
+  return BW_OK;
+}
+
+// After an activation's fold stage has been queued: remember how many rows exist once it is done.
+static bw_status mark_rows(bw_fold* f, u64 epoch) {
+  bw_ctx* ctx = f->ctx;
+  if (!f->flush_on || ctx->world > 1 || !f->host_ingest) return BW_OK;
+  if (!f->s_out) {
+    CU(ctx, cudaStreamCreateWithFlags(&f->s_out, cudaStreamNonBlocking));
+    CU(ctx, cudaHostAlloc((void**)&f->h_marks, 4 * 2 * sizeof(unsigned long long), cudaHostAllocDefault));
+    for (auto& m : f->marks) CU(ctx, cudaEventCreateWithFlags(&m.ev, cudaEventDisableTiming));
+  }
+  if (f->mark_head) f->marks[(f->mark_head - 1) & 3].next_epoch = epoch + 1;  // (+1: 0 means "none yet")
+  bw_fold::RowMark& m = f->marks[f->mark_head & 3];
+  m.epoch = epoch;
+  m.next_epoch = 0;
+  m.live = true;
+  CU(ctx, cudaMemcpyAsync(f->h_marks + 2 * (f->mark_head & 3), &f->d_ctr->n_closed, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                          f->s_compute));
+  CU(ctx, cudaEventRecord(m.ev, f->s_compute));
+  ++f->mark_head;
+  return BW_OK;
+}
+
+// Rows of epochs that are closed -- a later activation with a larger epoch has been folded -- and whose counts have
+// reached the host: order them and copy them out now, on the side stream, beside whatever the fold stream is doing.
+// Segments end on epoch boundaries and are shipped in epoch order, so the host arrays end up exactly as one sort of
+// everything would leave them (the order is epoch-major).
+static bw_status flush_rows(bw_fold* f) {
+  bw_ctx* ctx = f->ctx;
+  if (!f->flush_on || !f->s_out) return BW_OK;
+  for (u32 k = 0; k < 4 && k < f->mark_head; ++k) {  // newest first
+    const u32 at = (f->mark_head - 1 - k) & 3;
+    bw_fold::RowMark& m = f->marks[at];
+    if (!m.live) break;
+    if (!m.next_epoch || m.next_epoch - 1 <= m.epoch) continue;  // its epoch may still get rows
+    if (cudaEventQuery(m.ev) != cudaSuccess) continue;
+    const u64 nc = std::min<u64>(f->h_marks[2 * at], f->e.max_closed), nl = std::min<u64>(f->h_marks[2 * at + 1], f->e.max_late);
+    bw_status st = ship_rows(f, false, f->done_c, nc, true);
+    if (st != BW_OK) return st;
+    st = ship_rows(f, true, f->done_l, nl, true);
+    if (st != BW_OK) return st;
+    if (nc > f->done_c) f->done_c = nc;
+    if (nl > f->done_l) f->done_l = nl;
+    for (u32 j = k; j < 4 && j < f->mark_head; ++j) f->marks[(f->mark_head - 1 - j) & 3].live = false;  // this one and the older ones: done
+    CU(ctx, cudaGetLastError());
+    break;
+  }
+  return BW_OK;
+}
+
 static bw_status collect(bw_fold* f, bw_emit* out) {
   bw_ctx* ctx = f->ctx;
   cudaStream_t s = f->s_compute;
   CU(ctx, cudaMemcpyAsync(f->h_ctr, f->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
   CU(ctx, cudaStreamSynchronize(s));
+  if (f->s_out) CU(ctx, cudaStreamSynchronize(f->s_out));
+
   if (f->h_ctr->err) FAIL(f, (bw_status)f->h_ctr->err, "kernel raised status %u: %s", f->h_ctr->err, status_name(f->h_ctr->err));
   const u64 nc = std::min<u64>(f->h_ctr->n_closed, f->e.max_closed);
   const u64 nl = std::min<u64>(f->h_ctr->n_late, f->e.max_late);
@@ -1991,49 +2152,11 @@ static bw_status collect(bw_fold* f, bw_emit* out) {
   f->st.pane_nodes_used = f->h_ctr->pool_next - 1;
   bw_status st = grow_host(f, nc, nl);
   if (st != BW_OK) return st;
-  const bool ordered = f->spec.emit_order == BW_ORDER_REFERENCE;
-  const int grid = ctx->sm_count * 4;
-  const u64 n_ord = f->have_pending ? (f->last_epoch - f->min_epoch + 1) : 1;
-  // the window-id pass orders a key's rows where the sequence column ties: sliding windows emitted from one
-  // pane, and folds whose sequence is just the closing activation (FoldParams::seq_by_id)
-  const bool sliding = f->p.panes_per_window > 1 || f->p.panes_per_offset > 1 || f->p.seq_by_id;
-  auto ship = [&](u64 n, const u64* src, u64* dst, bool use_perm) -> bw_status {
-    if (use_perm) {
-      k_gather_u64<<<grid, 256, 0, s>>>(src, f->d_perm, f->d_gather, n);
-      f->st.kernel_launches++;
-      CU(ctx, cudaMemcpyAsync(dst, f->d_gather, n * 8, cudaMemcpyDeviceToHost, s));
-    } else {
-      CU(ctx, cudaMemcpyAsync(dst, src, n * 8, cudaMemcpyDeviceToHost, s));
-    }
-    return BW_OK;
-  };
-  if (nc) {
-    if (ordered) {
-      st = ensure_sort_cap(f, nc);
-      if (st != BW_OK) return st;
-      st = order_rows(f, nc, f->e.c_key, f->e.c_seq, f->e.c_epoch, f->e.c_wid, sliding, n_ord);
-      if (st != BW_OK) return st;
-    }
-    if ((st = ship(nc, f->e.c_key, f->ho_ckey, ordered))) return st;
-    if ((st = ship(nc, (const u64*)f->e.c_wid, (u64*)f->ho_cwid, ordered))) return st;
-    if ((st = ship(nc, f->e.c_acc, f->ho_cacc, ordered))) return st;
-    if ((st = ship(nc, f->e.c_count, f->ho_ccount, ordered))) return st;
-    if ((st = ship(nc, f->e.c_epoch, f->ho_cepoch, ordered))) return st;
-  }
-  if (nl) {
-    if (ordered) {
-      st = ensure_sort_cap(f, nl);
-      if (st != BW_OK) return st;
-      // rows of one late item were reserved contiguously in ascending window id; stable sorts keep that
-      st = order_rows(f, nl, f->e.l_key, f->e.l_seq, f->e.l_epoch, f->e.l_wid, false, n_ord);
-      if (st != BW_OK) return st;
-    }
-    if ((st = ship(nl, f->e.l_key, f->ho_lkey, ordered))) return st;
-    if ((st = ship(nl, (const u64*)f->e.l_wid, (u64*)f->ho_lwid, ordered))) return st;
-    if ((st = ship(nl, f->e.l_val, f->ho_lval, ordered))) return st;
-    if ((st = ship(nl, (const u64*)f->e.l_ts, (u64*)f->ho_lts, ordered))) return st;
-    if ((st = ship(nl, f->e.l_epoch, f->ho_lepoch, ordered))) return st;
-  }
+  // what the side stream has not already ordered and copied (everything, when nothing was flushed early)
+  if ((st = ship_rows(f, false, std::min(f->done_c, nc), nc, false))) return st;
+  if ((st = ship_rows(f, true, std::min(f->done_l, nl), nl, false))) return st;
+  f->done_c = f->done_l = 0;
+  for (auto& m : f->marks) m.live = false;
   // reset the row counters for the next round
   CU(ctx, cudaMemsetAsync(&f->d_ctr->n_closed, 0, sizeof(unsigned long long) * 2, s));
   CU(ctx, cudaStreamSynchronize(s));

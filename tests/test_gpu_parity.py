@@ -114,6 +114,32 @@ def test_moving_system_clock_per_step(ctx, golden_dir):
     assert woke > 20
 
 
+@pytest.mark.parametrize("red,length,offset,wait", [("count", 10, None, 0), ("sum", 10, 5, 2)])
+def test_rows_shipped_early_equal_one_sort(ctx, fold_mode, red, length, offset, wait, monkeypatch):
+    """Host commits: rows of closed epochs are ordered and copied out on a side stream while later activations run
+    (flush_rows); what `bw_advance` hands back must be exactly what ordering everything at the end gives (BW_FLUSH=0).
+    Epochs repeat (their rows must not be split across segments) and some rows are late."""
+    S = 1_000_000
+    A = 1_640_995_200_000_000
+    spec = dict(reduction=red, length_us=length * S, offset_us=offset * S if offset else None, align_us=A, wait_us=wait * S, ordered=False)
+    batches = _random_batches(77, 14, 20_000, 500, 6 * S, 3 * S, A)
+    epochs = [1, 1, 2, 3, 3, 3, 4, 5, 6, 6, 7, 8, 9, 9]
+    got = {}
+    for flush in ("0", "1"):
+        monkeypatch.setenv("BW_FLUSH", flush)
+        fold = _make_fold(ctx, spec, False, capacity_hint=2048, max_batch_rows=1 << 15, max_emit_rows=1 << 20, max_late_rows=1 << 20)
+        for (keys, ts, vals), ep in zip(batches, epochs):
+            fold.ingest(keys, vals, ts, ep)
+            fold.sync()  # (the counts of the folded activations reach the host: the next commit ships their rows)
+        em, em2 = fold.advance(), fold.eof()
+        got[flush] = [np.concatenate([getattr(em, f), getattr(em2, f)]) for f in
+                      ("closed_key", "closed_window_id", "closed_acc", "closed_epoch", "late_key", "late_window_id", "late_val", "late_ts_us", "late_epoch")]
+        fold.close()
+    assert len(got["1"][0]) > 1000 and len(got["1"][4]) > 100
+    for a, b in zip(got["0"], got["1"]):
+        assert np.array_equal(a, b)
+
+
 def test_golden_cases_single_advance(ctx, golden_dir):
     """All activations committed back to back, rows collected once: same rows, grouped by epoch."""
     with open(os.path.join(golden_dir, "window_fold_cases.json")) as f:
