@@ -215,7 +215,7 @@ struct PhaseTimer {
 struct EventPair {
   cudaEvent_t a, b;
   u64 rows;
-  int kind;  // 0: fold stage (k_fold / k_segfold), 1: scatter stage (k_scatter + k_verdict)
+  int kind;  // 0: fold stage (k_fold / k_segfold), 1: k_scatter, 2: k_verdict
 };
 
 typedef void (*scatter_kernel_t)(ScatterArgs, FoldParams);
@@ -292,6 +292,7 @@ struct bw_fold {
   u32 mark_head = 0;                      // marks enqueued so far
   u64 done_c = 0, done_l = 0;             // rows already ordered and on the host
   cudaStream_t s_out = nullptr;
+  u32 timer_stride = 4;                   // env BW_TIMER_STRIDE: every n-th activation's kernels are timed with CUDA events
   bool flush_on = true;                   // env BW_FLUSH=0: order and copy everything in bw_advance
   bool host_ingest = false;               // the caller commits HOST batches (PCIe-bound: the device has time to spare between
                                           // activations; a device-resident caller keeps every SM busy and is left alone)
@@ -666,6 +667,7 @@ static bw_status stream_alloc(bw_fold* f) {
   CU(ctx, dmalloc(&sb.chunk_max, 2 * (size_t)sb.tiles_cap * BW_SC_WARPS));
   if (const char* e = getenv("BW_LATE_SPLIT")) f->late_split = atoi(e) != 0;
   if (const char* e = getenv("BW_FLUSH")) f->flush_on = atoi(e) != 0;
+  if (const char* e = getenv("BW_TIMER_STRIDE")) f->timer_stride = (u32)std::max(1, atoi(e));
   // Shared memory of the scatter: up to 8 records per bucket assembled before they are written out (counts only: the
   // value column is not staged), then as many TMA stages of the input tile (2..4) as still fit.
   const size_t smem_budget = 208 * 1024;
@@ -1111,7 +1113,11 @@ bw_status bw_ingest_acquire(bw_fold* f, uint64_t max_rows, bw_batch* out) {
   return BW_OK;
 }
 
-static EventPair* next_timer(bw_fold* f) {
+// CUDA-event pair for one kernel launch of activation `batch_no`.  Every record with timing drains the stream for a few
+// microseconds, so only every timer_stride-th activation is timed (env BW_TIMER_STRIDE, default 4): the averages in bw_stats
+// are over that sample.
+static EventPair* next_timer(bw_fold* f, u32 batch_no) {
+  if (f->timer_stride > 1 && batch_no % f->timer_stride != 0) return nullptr;
   if (f->timers_used == f->timers.size()) {
     if (f->timers.size() >= 4096) return nullptr;
     EventPair ep;
@@ -1265,7 +1271,7 @@ static bw_status direct_fold(bw_fold* f, const BatchView& bv, u64 known, u32 bat
   if (n_sub < 1) n_sub = 1;
   for (u32 i = 0; i < n_sub; ++i) {
     const u64 n_hi = (known * (i + 1ULL)) / n_sub, n_lo = (known * (u64)i) / n_sub;
-    EventPair* ep = next_timer(f);
+    EventPair* ep = next_timer(f, batch_no);
     if (ep) {
       ep->rows = (ctx->world > 1) ? 0 : (n_hi - n_lo);
       ep->kind = 0;
@@ -1343,7 +1349,7 @@ static bw_status stream_front(bw_fold* f, const u64* d_keys, const void* d_vals,
   const int grid = (int)std::min<u64>(ntiles, (u64)std::min<u32>((u32)f->scatter_grid, sb.nlanes));
   f->last_scatter_grid = (u32)grid;
   if (multi && !usable && rows) CU(ctx, cudaMemsetAsync(&sb.side[side].sv->flags, 0xFF, sizeof(u32), s));  // every flag: legacy path
-  EventPair* ep = next_timer(f);
+  EventPair* ep = next_timer(f, batch_no);
   if (ep) {
     ep->rows = rows;
     ep->kind = 1;
@@ -1351,13 +1357,20 @@ static bw_status stream_front(bw_fold* f, const u64* d_keys, const void* d_vals,
   }
   f->pt.mark(5, 0, s);
   if (grid) f->scatter_kernel<<<grid, BW_SC_THREADS, f->scatter_smem, s>>>(A, f->p);
+  if (ep) CU(ctx, cudaEventRecord(ep->b, s));  // (the scatter kernel alone: the one-block verdict is timed apart)
+  EventPair* ev = next_timer(f, batch_no);
+  if (ev) {
+    ev->rows = 0;
+    ev->kind = 2;
+    CU(ctx, cudaEventRecord(ev->a, s));
+  }
   if (f->p.ts_from_value == 2) k_verdict_none<<<1, 1, 0, s>>>(f->p, f->d_ctr, sb.side[side].sv, vg, rows);
   else
     k_verdict<<<1, 1024, 0, s>>>(A.tile_min, A.tile_max, A.tile_bad, (u32)ntiles, f->p, f->d_ctr, sb.side[side].sv,
                                  f->has_ts ? d_ts : nullptr, (const u64*)d_vals, vg);
   CU(ctx, cudaGetLastError());
   f->pt.mark(5, 1, s);
-  if (ep) CU(ctx, cudaEventRecord(ep->b, s));
+  if (ev) CU(ctx, cudaEventRecord(ev->b, s));
   f->st.kernel_launches += 2;
   CU(ctx, cudaMemcpyAsync(&f->h_sv[side], sb.side[side].sv, sizeof(StreamVerdict), cudaMemcpyDeviceToHost, s));
   if (multi) f->vg_pending[side] = true;  // gathered by the next collective on the stream (gather_verdict)
@@ -1548,7 +1561,7 @@ static bw_status stream_resolve_multi(bw_fold* f, const Deferred& d) {
   }
   A.pcnt_in = (const u32*)((char*)f->precv_base + f->precv_cnt_off[d.side]);
   A.pin = (const Partial*)((char*)f->precv_base + f->precv_rec_off[d.side]);
-  EventPair* ep = next_timer(f);
+  EventPair* ep = next_timer(f, d.batch_no);
   if (ep) {
     ep->rows = d.rows;
     ep->kind = 0;
@@ -1712,7 +1725,7 @@ static bw_status stream_resolve(bw_fold* f) {
     A.npass = (u32)((q_hi - q_lo) / 2 + 1);
     A.batch_no = d.batch_no;
     A.epoch = d.ord;
-    EventPair* ep = next_timer(f);
+    EventPair* ep = next_timer(f, d.batch_no);
     if (ep) {
       ep->rows = d.rows;
       ep->kind = 0;
@@ -2340,10 +2353,13 @@ static void drain_timers(bw_fold* f) {
       if (f->timers[i].kind == 1) {
         f->st.sum_scatter_ms += ms;
         f->st.scatter_launches++;
+      } else if (f->timers[i].kind == 2) {
+        f->st.sum_verdict_ms += ms;
       } else {
         f->st.last_fold_ms = ms;
         f->st.sum_fold_ms += ms;
         f->st.fold_rows += f->timers[i].rows;
+        f->st.timed_folds++;
       }
     }
   }
@@ -2371,10 +2387,12 @@ bw_status bw_fold_reset_timers(bw_fold* f) {
   CU(f->ctx, cudaStreamSynchronize(f->s_compute));
   drain_timers(f);
   f->st.sum_scatter_ms = 0;
+  f->st.sum_verdict_ms = 0;
   f->st.scatter_launches = 0;
   f->st.sum_fold_ms = 0;
   f->st.last_fold_ms = 0;
   f->st.fold_rows = 0;
+  f->st.timed_folds = 0;
   f->st.fold_launches = 0;
   f->st.combined_folds = 0;
   f->st.split_batches = 0;

@@ -175,14 +175,16 @@ typedef struct bw_stats {
   uint64_t table_capacity;
   uint64_t pane_nodes_used;
   float last_fold_ms;       /* CUDA-event time of the most recent fold kernel */
-  float sum_fold_ms;        /* sum over fold kernels since bw_fold_create / reset */
+  float sum_fold_ms;        /* sum over the TIMED fold launches since bw_fold_create / reset (see timed_folds) */
   uint64_t fold_launches;
   uint64_t fold_rows;
   uint64_t combined_folds;  /* activations folded by the streaming path: bucket scatter + shared-memory segment fold */
-  float sum_scatter_ms;     /* CUDA-event time of the scatter + verdict stage of those activations */
-  float reserved0;
+  float sum_scatter_ms;     /* CUDA-event time of the k_scatter launches of those activations */
+  float sum_verdict_ms;     /* ... and of their k_verdict launches (one each) */
   uint64_t scatter_launches;
   uint64_t split_batches;   /* not-clean activations whose late rows were found without the sort (streaming fold for the rest) */
+  uint64_t timed_folds;     /* fold launches behind sum_fold_ms / fold_rows: every BW_TIMER_STRIDE-th activation (default 4) is
+                             * timed -- an event record with timing drains the stream for a few microseconds */
 } bw_stats;
 
 /* ---- context ---------------------------------------------------------- */

@@ -13,4 +13,4 @@ for s in range(6):
     fold.ingest_device(dk, dv, None, B)
     fold.sync()
 st = fold.stats()
-print(os.environ.get("BW_SC_DBG", "0"), "scatter+verdict avg ms", st.sum_scatter_ms / max(1, st.scatter_launches), "fold avg ms", st.sum_fold_ms / max(1, st.fold_launches))
+print(os.environ.get("BW_SC_DBG", "0"), "scatter+verdict avg ms", st.sum_scatter_ms / max(1, st.scatter_launches), "fold avg ms", st.sum_fold_ms / max(1, st.timed_folds))

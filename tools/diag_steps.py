@@ -1,5 +1,6 @@
 """Per-step fold kernel times for config C1 (diagnostic; not a bench number)."""
 import sys, os
+os.environ.setdefault("BW_TIMER_STRIDE", "1")  # (per-step numbers: time every activation)
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from bytewax_b200 import gpu, _native as N
 A = 1_640_995_200_000_000
