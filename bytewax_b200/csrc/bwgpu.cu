@@ -1862,7 +1862,11 @@ bw_status bw_ingest_commit(bw_fold* f, const bw_batch* batch, uint64_t rows, uin
   f->pre_wait = f->ev_in;
   CU(ctx, cudaEventRecord(f->ev_src_ready, f->s_copy));
   bw_status st = run_batch(f, sg.d_keys, sg.d_vals, sg.d_ts, rows, epoch, &sg);
-  if (st != BW_OK) return st;
+  if (st != BW_OK) {  // (the slot goes back to the ring on the error paths too: repeated failures must not use it up)
+    cudaEventSynchronize(f->ev_h2d);
+    sl.acquired = false;
+    return st;
+  }
   // the pinned slot may be refilled once its H2D is done
   CU(ctx, cudaEventSynchronize(f->ev_h2d));
   sl.acquired = false;
